@@ -1,0 +1,293 @@
+/*
+ * rechub_b200.h — C ABI of the B200 (sm_100a) embedding-and-interaction engine.
+ *
+ * This is the drop-in boundary for the hot path of datawhalechina/torch-rechub
+ * (SURVEY.md §8b).  The reference has no FFI of its own — its boundary is the Python class
+ * surface — so every entry point below names the reference function whose arithmetic it
+ * replaces (paths relative to the reference root, torch-rechub v0.8.0 @ 5a73b2e).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - every pointer marked "device" is a CUDA device pointer on the current device;
+ *     the library never allocates, frees or synchronises — the caller owns all buffers;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - tables and their gradient buffers are fp32, row-major (vocab, dim);
+ *   - return value: 0 = RH_OK, otherwise an rh_status; rh_last_error() returns a
+ *     thread-local human-readable message for the last failing call;
+ *   - out-of-range ids never touch memory: the row reads as zeros / the scatter is dropped and
+ *     `*err_flag` (device int32, may be NULL) is set to 1 + the field index.  The host
+ *     binding turns a non-zero flag into the reference's `IndexError: index out of range in self`.
+ */
+#ifndef RECHUB_B200_H_
+#define RECHUB_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RH_ABI_VERSION 1
+
+typedef enum rh_status {
+  RH_OK = 0,
+  RH_ERR_INVALID_ARG = 1,   /* bad shape / alignment / NULL where data is required        */
+  RH_ERR_UNSUPPORTED = 2,   /* configuration outside what the kernels implement           */
+  RH_ERR_CUDA = 3           /* a CUDA runtime call failed (message holds cudaGetErrorString) */
+} rh_status;
+
+#define RH_MAX_FIELDS 64    /* id columns per rh_fields_* launch (callers chunk beyond it)  */
+#define RH_MAX_DENSE  32    /* numeric columns per rh_fields_fwd launch                     */
+
+/* One id column looked up in one table: a SparseFeature of the reference
+ * (basic/features.py:42-71; lookup at basic/layers.py:83,85). */
+typedef struct rh_field {
+  const float* table;       /* device (vocab, dim) fp32                                          */
+  float*       table_grad;  /* device (vocab, dim) fp32, backward only; NULL = frozen table      */
+  const void*  ids;         /* device ids of this column, int64 (or int32 when ids_are_i32)       */
+  int64_t      id_stride;   /* elements between consecutive samples (1 for a (B,) column)         */
+  int32_t      ids_are_i32;
+  int32_t      vocab;       /* rows of the table (bounds check)                                   */
+  int32_t      padding_idx; /* row that receives no gradient (nn.Embedding padding_idx); -1 none  */
+  int32_t      tile_col;    /* first column of this field in the flattened tile; -1 = not emitted */
+  int32_t      fm_slot;     /* position among the FM/LR fields (LR weight offset = fm_slot*dim);
+                               -1 = the field takes no part in FM/LR                              */
+} rh_field;
+
+/* One numeric column copied into the tile: a DenseFeature (basic/features.py:74-87;
+ * `.float()` + concat at basic/layers.py:101,105,120). */
+typedef struct rh_dense {
+  const void* values;       /* device (B, width)                                                  */
+  int64_t     stride;       /* elements between consecutive samples                               */
+  int32_t     dtype;        /* 0 = fp32, 1 = fp64 (pandas default), 2 = int64, 3 = int32          */
+  int32_t     width;        /* values per sample (DenseFeature.embed_dim)                         */
+  int32_t     tile_col;     /* first destination column                                            */
+} rh_dense;
+
+int         rh_abi_version(void);
+const char* rh_last_error(void);
+/* Number of kernels this library has launched so far in this process (bench.py's gpu_launches). */
+unsigned long long rh_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused multi-field gather (+ FM second-order term + LR first-order term + flattened tile).
+ *
+ * Replaces, in ONE launch: EmbeddingLayer.forward's per-field index_select + unsqueeze + cat
+ * (basic/layers.py:77-127), FM.forward (basic/layers.py:313-319), LR.forward on the flattened
+ * embeddings (basic/layers.py:183-189 as called from models/ranking/deepfm.py:39), and the
+ * dense-value concat (basic/layers.py:101-120).
+ *
+ *   dim        row width shared by all `fields` of this launch (callers group by dim)
+ *   tile       device (batch, tile_ld) fp32 or NULL; field f fills columns
+ *              [tile_col, tile_col+dim), dense column j fills [tile_col, tile_col+width)
+ *   lr_weight  device (n_fm*dim) fp32, lr_bias device (1) fp32      (NULL when y_lr is NULL)
+ *   y_fm       device (batch) fp32 or NULL: 0.5 * sum_d[(sum_f e)^2 - sum_f e^2]
+ *   y_lr       device (batch) fp32 or NULL: <flatten(e), lr_weight> + lr_bias
+ *   field_sum  device (batch, dim) fp32 or NULL: sum_f e over FM fields (saved for backward)
+ * ------------------------------------------------------------------------------------------- */
+int rh_fields_fwd(const rh_field* fields, int n_fields, int dim,
+                  const rh_dense* dense, int n_dense,
+                  int batch,
+                  float* tile, int64_t tile_ld,
+                  const float* lr_weight, const float* lr_bias,
+                  float* y_fm, float* y_lr, float* field_sum,
+                  int32_t* err_flag, void* stream);
+
+/* Backward of rh_fields_fwd: the sparse-gradient scatter-add into the tables' gradient buffers.
+ *
+ * Replaces autograd's aten::embedding_dense_backward per lookup (reference: implicit in
+ * nn.Embedding(sparse=False), basic/initializers.py:17) plus the FM / LR / cat backward
+ * elementwise chain.  For row e = table[id] of FM field f:
+ *     g = d_tile[b, cols(f)] + d_y_fm[b] * (field_sum[b] - e) + d_y_lr[b] * lr_weight[f]
+ * and table_grad[id] += g (vector RED, duplicates accumulate; padding_idx rows are skipped).
+ *
+ *   tile        the forward tile (rows are re-read from it when the field was emitted) or NULL
+ *               (rows are re-gathered from the table)
+ *   d_tile      device (batch, d_tile_ld) fp32 or NULL (any row stride; 16-byte aligned rows go faster)
+ *   d_y_fm, d_y_lr   device (batch) fp32 or NULL
+ *   d_lr_weight device (n_fm*dim) fp32, ACCUMULATED into (caller zeroes) or NULL
+ *   d_lr_bias   device (1) fp32, accumulated into, or NULL
+ */
+int rh_fields_bwd(const rh_field* fields, int n_fields, int dim, int batch,
+                  const float* tile, int64_t tile_ld,
+                  const float* d_tile, int64_t d_tile_ld,
+                  const float* d_y_fm, const float* d_y_lr,
+                  const float* lr_weight, const float* field_sum,
+                  float* d_lr_weight, float* d_lr_bias,
+                  int32_t* err_flag, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Single-table lookups of arbitrary id shape (FieldTable.forward; SequenceFeature paths).
+ * ------------------------------------------------------------------------------------------- */
+
+/* out[i, :] = table[ids[i], :] for i < n  — nn.Embedding.forward as used at basic/layers.py:83-99
+ * (sequence features with pooling="concat": basic/layers.py:91-92,204-205). */
+int rh_rows_gather(const float* table, int vocab, int dim,
+                   const void* ids, int ids_are_i32, int64_t n,
+                   float* out, int32_t* err_flag, void* stream);
+
+/* table_grad[ids[i], :] += d_out[i, :], skipping padding_idx (embedding_dense_backward). */
+int rh_rows_scatter_add(float* table_grad, int vocab, int dim, int padding_idx,
+                        const void* ids, int ids_are_i32, int64_t n,
+                        const float* d_out, int32_t* err_flag, void* stream);
+
+/* Masked sum / mean pooling of a padded id sequence: SumPooling / AveragePooling with the
+ * InputMask rule (basic/layers.py:148-161, 209-251): position l counts when
+ * ids[b,l] != mask_id (mask_id = padding_idx, or -1 when the feature has none);
+ * mean divides by (count + 1e-16).   mode: 1 = sum, 2 = mean.   out: (batch, dim) with row stride
+ * out_ld (so the pooled vector can land directly in a tile column block). */
+int rh_seq_pool_fwd(const float* table, int vocab, int dim,
+                    const void* ids, int ids_are_i32, int batch, int seq_len,
+                    int mode, int64_t mask_id,
+                    float* out, int64_t out_ld, int32_t* err_flag, void* stream);
+
+int rh_seq_pool_bwd(float* table_grad, int vocab, int dim, int padding_idx,
+                    const void* ids, int ids_are_i32, int batch, int seq_len,
+                    int mode, int64_t mask_id,
+                    const float* d_out, int64_t d_out_ld, int32_t* err_flag, void* stream);
+
+/* table_grad[ids[i], :] = 0 — sparse replacement for zero-filling a dense (vocab, dim) gradient
+ * (the reference spends 66 % of its CPU step in aten::fill_). */
+int rh_rows_zero(float* table_grad, int vocab, int dim,
+                 const void* ids, int ids_are_i32, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Row-wise (lazy) optimisers over the rows touched by one batch.
+ * For every DISTINCT id in `ids` (first claimant wins through `stamp`, a device int32[vocab]
+ * holding the last step that updated the row):
+ *     g = table_grad[id]; table_grad[id] = 0;   then the update below on row `id` only.
+ *   kind 0 SGD      w -= lr * (g + wd*w)
+ *   kind 1 Adam     torch.optim.Adam arithmetic (L2-style weight_decay, bias correction with the
+ *                   row-independent global step) applied to touched rows only
+ *   kind 2 Adagrad  state1 += g^2 ; w -= lr * g / (sqrt(state1) + eps)       (g includes wd*w)
+ * state1/state2: device (vocab, dim) fp32 moment buffers (Adam: m, v; Adagrad: state1 = sum).
+ * stamp: device int32[vocab], zero-initialised.  step_dev / lr_dev: DEVICE scalars (int32 / fp32) so
+ * that a captured CUDA graph sees the step counter and a scheduler-updated learning rate on replay;
+ * rh_opt_advance increments *step_dev (call it once per optimiser step, before the updates).
+ * ------------------------------------------------------------------------------------------- */
+int rh_rowwise_update(float* table, float* table_grad, float* state1, float* state2,
+                      int32_t* stamp, int vocab, int dim,
+                      const void* ids, int ids_are_i32, int64_t n,
+                      int kind, const int32_t* step_dev, const float* lr_dev,
+                      float beta1, float beta2, float eps, float weight_decay, void* stream);
+int rh_opt_advance(int32_t* step_dev, void* stream);
+
+/* The same update for ALL tables of one batch in a single launch (grid.y = field): fields[i] gives
+ * table_grad / ids / id_stride / vocab of table i; tables / state1 / state2 / stamp are host arrays
+ * of n_fields device pointers.  Needs dim % 4 == 0.  This is the optimiser half of the
+ * "backward sparse-grad scatter-add into the tables" (BASELINE.json north_star). */
+int rh_fields_rowwise_update(const rh_field* fields, int n_fields, int dim, int batch,
+                             float* const* tables, float* const* state1, float* const* state2,
+                             int32_t* const* stamp, int kind,
+                             const int32_t* step_dev, const float* lr_dev,
+                             float beta1, float beta2, float eps, float weight_decay, void* stream);
+
+/* table_grad[ids] = 0 for all tables of one batch in a single launch (sparse zero_grad). */
+int rh_fields_zero(const rh_field* fields, int n_fields, int dim, int batch, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Interactions on dense tiles.
+ * ------------------------------------------------------------------------------------------- */
+
+/* FM.forward on a materialised (batch, n_fields, dim) tensor (basic/layers.py:313-319).
+ * reduce_sum != 0: y (batch);  reduce_sum == 0: y (batch, dim). */
+int rh_fm_fwd(const float* x, int batch, int n_fields, int dim, int reduce_sum,
+              float* y, void* stream);
+int rh_fm_bwd(const float* x, const float* d_y, int batch, int n_fields, int dim, int reduce_sum,
+              float* d_x, void* stream);
+
+/* CrossNetwork.forward (basic/layers.py:412-420): x_{l+1} = x0 * <w_l, x_l> + b_l + x_l for
+ * l < n_layers (<= 16), all layers in one launch, the row held in registers throughout.
+ *   w, b       host arrays of n_layers DEVICE pointers, each (width) fp32 — the reference keeps one
+ *              Linear(width,1,bias=False).weight and one bias Parameter per layer (layers.py:409-410)
+ *   xw_saved   device (n_layers, batch) fp32: the per-layer scalars <w_l, x_l> (kept for backward) */
+int rh_cross_fwd(const float* x0, int64_t x_ld, int batch, int width, int n_layers,
+                 const float* const* w, const float* const* b,
+                 float* out, int64_t out_ld, float* xw_saved, void* stream);
+
+/* Backward of rh_cross_fwd.  d_w, d_b: host arrays of n_layers device pointers, each (width) fp32,
+ * accumulated into (caller zeroes). */
+int rh_cross_bwd(const float* x0, int64_t x_ld, int batch, int width, int n_layers,
+                 const float* const* w, const float* const* b, const float* xw_saved,
+                 const float* d_out, int64_t d_out_ld,
+                 float* d_x0, int64_t d_x0_ld, float* const* d_w, float* const* d_b, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * MLP glue: BatchNorm1d (train / eval) + activation + dropout in one pass
+ * (basic/layers.py:276-292: Linear -> BatchNorm1d -> activation -> Dropout).
+ * ------------------------------------------------------------------------------------------- */
+
+/* Column statistics of h (rows, cols): mean[c], biased var[c]  (BatchNorm1d training forward).
+ * `scratch`: device (2*cols + 1) fp32, zeroed ONCE by the caller; the kernel leaves it zeroed.
+ * When running_mean/var are non-NULL they are updated with `momentum` (unbiased variance, as torch
+ * does); num_batches_tracked (device int64, may be NULL) is incremented. */
+int rh_colstats(const float* h, int64_t h_ld, int64_t rows, int cols,
+                float* mean, float* var, float* scratch,
+                float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                float momentum, void* stream);
+
+/* y = dropout(act(gamma * (h - mean) / sqrt(var + eps) + beta)).   mean/var NULL: no normalisation.
+ *   act: 0 identity, 1 ReLU, 2 Dice (basic/activation.py:15-25: per-ROW statistics over `cols`;
+ *        act_param = device alpha (1)), 3 PReLU (act_param = single slope), 4 sigmoid, 5 LeakyReLU(0.01)
+ *   keep_mask: device (rows, cols) uint8 or NULL (no dropout); kept values are scaled by 1/(1-p_drop) */
+int rh_bn_act_fwd(const float* h, int64_t h_ld, int64_t rows, int cols,
+                  const float* mean, const float* var, float bn_eps,
+                  const float* gamma, const float* beta,
+                  int act, const float* act_param, float dice_eps,
+                  const uint8_t* keep_mask, float p_drop,
+                  float* y, int64_t y_ld, void* stream);
+
+/* Backward of rh_bn_act_fwd through dropout, activation and batch norm; the pre-activation is
+ * recomputed from h.  d_h: gradient w.r.t. the Linear output h.
+ *   training != 0: batch statistics take part in the gradient (two launches: column sums, apply);
+ *                  d_gamma/d_beta (cols) double as the column-sum buffers and MUST be zero on entry.
+ *   training == 0: BN is affine (running statistics); d_gamma/d_beta are accumulated into if non-NULL.
+ *   d_act_param (1): accumulated into (Dice alpha / PReLU slope), may be NULL. */
+int rh_bn_act_bwd(const float* h, int64_t h_ld, int64_t rows, int cols,
+                  const float* mean, const float* var, float bn_eps,
+                  const float* gamma, const float* beta,
+                  int act, const float* act_param, float dice_eps,
+                  const uint8_t* keep_mask, float p_drop,
+                  const float* d_y, int64_t d_y_ld, int training,
+                  float* d_h, int64_t d_h_ld,
+                  float* d_gamma, float* d_beta, float* d_act_param, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * DIN target attention (models/ranking/din.py:77-93, ActivationUnit.forward).
+ * ------------------------------------------------------------------------------------------- */
+
+/* att_in[b*L + l, :] = [t, h, t-h, t*h] with h = hist_table[hist_ids[b,l]], t = tgt_table[tgt_ids[b]]
+ * (din.py:80-81) — the gather of the behaviour sequence fused with the feature construction.
+ * Also emits hist (batch, L, dim) and target (batch, dim) when non-NULL. */
+int rh_din_attn_input_fwd(const float* hist_table, int hist_vocab,
+                          const float* tgt_table, int tgt_vocab, int dim,
+                          const void* hist_ids, const void* tgt_ids, int ids_are_i32,
+                          int64_t tgt_id_stride, int batch, int seq_len,
+                          float* att_in, float* hist_out, float* tgt_out,
+                          int32_t* err_flag, void* stream);
+
+/* out[b,:] = sum_l w[b,l] * hist[b,l,:]   (din.py:92); optional softmax over l first (din.py:86-87). */
+int rh_din_weighted_sum_fwd(const float* att_w, const float* hist, int batch, int seq_len, int dim,
+                            int use_softmax, float* w_used, float* out, void* stream);
+
+/* Backward of the attention-pooling tail + the att_in construction, ending in the scatter-add into
+ * the two tables' gradient buffers:
+ *   d_out (batch, dim), d_att_in (batch*L, 4*dim) -> d_att_w (batch, L) [written],
+ *   hist_grad[hist_ids] += ..., tgt_grad[tgt_ids] += ... (+ d_tgt_extra (batch, dim), the gradient
+ *   reaching the target embedding from the final MLP's concat, may be NULL). */
+int rh_din_weighted_sum_bwd(const float* w_used, const float* hist, const float* d_out,
+                            int batch, int seq_len, int dim, int use_softmax,
+                            float* d_att_w, float* d_hist, void* stream);
+
+int rh_din_attn_input_bwd(float* hist_grad, int hist_vocab, int hist_padding_idx,
+                          float* tgt_grad, int tgt_vocab, int tgt_padding_idx, int dim,
+                          const void* hist_ids, const void* tgt_ids, int ids_are_i32,
+                          int64_t tgt_id_stride, int batch, int seq_len,
+                          const float* hist, const float* tgt,
+                          const float* d_att_in, const float* d_hist, const float* d_tgt_extra,
+                          int32_t* err_flag, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* RECHUB_B200_H_ */

@@ -1,0 +1,102 @@
+// rh_common.cuh — shared device/host helpers of the sm_100a engine.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "rechub_b200.h"
+
+namespace rh {
+
+// ---- host-side error plumbing ------------------------------------------------------------------
+void set_error(const char* fmt, ...);   // rh_api.cu (thread-local message)
+
+#define RH_REQUIRE(cond, status, ...)            \
+  do {                                           \
+    if (!(cond)) {                               \
+      ::rh::set_error(__VA_ARGS__);              \
+      return (status);                           \
+    }                                            \
+  } while (0)
+
+extern unsigned long long g_launches;  // rh_api.cu: kernels launched by this library (rh_launch_count)
+
+#define RH_LAUNCH_CHECK()                                                        \
+  do {                                                                           \
+    ++::rh::g_launches;                                                          \
+    cudaError_t e__ = cudaGetLastError();                                        \
+    if (e__ != cudaSuccess) {                                                    \
+      ::rh::set_error("%s:%d launch failed: %s", __FILE__, __LINE__,             \
+                      cudaGetErrorString(e__));                                  \
+      return RH_ERR_CUDA;                                                        \
+    }                                                                            \
+  } while (0)
+
+static inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+static inline int pow2_ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// ---- device helpers ----------------------------------------------------------------------------
+
+// 128-bit read-only load that does not allocate in L1: embedding rows are touched once per launch.
+__device__ __forceinline__ float4 ldg_row16(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// 128-bit streaming store (tile rows are consumed by the next kernel out of L2, never by this SM).
+__device__ __forceinline__ void stg_row16(float* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+
+// 128-bit vector reduction into global memory (REDG.E.ADD.F32x4 on sm_90+): one L2 atomic
+// transaction per 16 B instead of four.
+__device__ __forceinline__ void red_add_row16(float* p, const float4& v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ int64_t load_id(const void* ids, int64_t idx, bool is_i32) {
+  return is_i32 ? (int64_t)__ldg(reinterpret_cast<const int32_t*>(ids) + idx)
+                : (int64_t)__ldg(reinterpret_cast<const long long*>(ids) + idx);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float4 f4_add(const float4& a, const float4& b) {
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ float4 f4_fma(const float4& a, const float4& b, const float4& c) {
+  return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
+}
+__device__ __forceinline__ float4 f4_scale(const float4& a, float s) {
+  return make_float4(a.x * s, a.y * s, a.z * s, a.w * s);
+}
+__device__ __forceinline__ float f4_dot(const float4& a, const float4& b) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+
+}  // namespace rh

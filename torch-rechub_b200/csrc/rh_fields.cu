@@ -1,0 +1,550 @@
+// rh_fields.cu — fused multi-field embedding gather + FM + LR + flattened tile, and its backward
+// (sparse-gradient scatter-add).  The hot kernel of the DeepFM / DCN / DCNv2 front end.
+//
+// Reference arithmetic replaced (torch-rechub v0.8.0): basic/layers.py:77-127 (EmbeddingLayer.forward),
+// :313-319 (FM.forward), :183-189 (LR.forward); backward = aten::embedding_dense_backward per lookup.
+//
+// Bound: HBM latency/bandwidth (arithmetic intensity < 1 FLOP/B).  Design:
+//   forward : LPR = dim/4 lanes own one sample; each lane issues ALL its 16-byte row loads
+//             (one per field, up to CH in flight) before consuming any, so a 4096-sample batch
+//             has its whole 6.8 MB of rows outstanding at once (Little's law: ~6 MB @ ~0.8 us).
+//             FM and LR are reduced in registers + (log2 LPR) shuffles; the tile row is written
+//             with 16-byte streaming stores.
+//   backward: one (field, sample-chunk) per block so the LR weight gradient reduces in registers;
+//             per-row gradient goes out as ONE 16-byte vector RED per lane (REDG.E.ADD.F32x4).
+#include "rh_common.cuh"
+
+namespace rh {
+
+struct FieldDev {
+  const float* table;
+  float* grad;
+  const void* ids;
+  int32_t id_stride;
+  int32_t vocab;
+  int32_t pad_idx;
+  int32_t tile_col;
+  int32_t fm_slot;
+  int32_t is_i32;
+};
+
+struct DenseDev {
+  const void* src;
+  int32_t stride;
+  int32_t dtype;
+  int32_t width;
+  int32_t tile_col;
+};
+
+struct FwdParams {
+  FieldDev f[RH_MAX_FIELDS];
+  DenseDev d[RH_MAX_DENSE];
+  int32_t n_fields, n_dense, batch, dim;
+  int32_t tile_vec, pad0_;  // 1: tile rows/columns are 16-byte aligned -> vector stores
+  float* tile;
+  int64_t tile_ld;
+  const float* lrw;
+  const float* lrb;
+  float* yfm;
+  float* ylr;
+  float* fsum;
+  int32_t* err;
+};
+
+struct BwdParams {
+  FieldDev f[RH_MAX_FIELDS];
+  int32_t n_fields, batch, dim, tile_vec;  // tile_vec / dtile_vec: rows are 16-byte aligned
+  int32_t dtile_vec, pad1_;
+  const float* tile;
+  const float* dtile;
+  int64_t tile_ld;
+  int64_t dtile_ld;
+  const float* dyfm;
+  const float* dylr;
+  const float* lrw;
+  const float* fsum;
+  float* dlrw;
+  float* dlrb;
+  int32_t* err;
+};
+
+__device__ __forceinline__ float load_dense_value(const void* src, int64_t idx, int dtype) {
+  switch (dtype) {
+    case 0: return __ldg(reinterpret_cast<const float*>(src) + idx);
+    case 1: return (float)__ldg(reinterpret_cast<const double*>(src) + idx);
+    case 2: return (float)__ldg(reinterpret_cast<const long long*>(src) + idx);
+    default: return (float)__ldg(reinterpret_cast<const int32_t*>(src) + idx);
+  }
+}
+
+__device__ __forceinline__ float4 ld_tile4(const float* p, bool vec) {
+  if (vec) return ldg_row16(p);
+  return make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+}
+__device__ __forceinline__ void st_tile4(float* p, const float4& v, bool vec) {
+  if (vec) {
+    stg_row16(p, v);
+  } else {
+    p[0] = v.x;
+    p[1] = v.y;
+    p[2] = v.z;
+    p[3] = v.w;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward, 16-byte lanes.  LPR lanes per sample (LPR = pow2 >= dim/4), CH row loads in flight/lane.
+// ------------------------------------------------------------------------------------------------
+template <int LPR, int CH>
+__global__ void __launch_bounds__(128) fields_fwd_v4(const __grid_constant__ FwdParams p) {
+  const int spb = blockDim.x / LPR;
+  const int b = blockIdx.x * spb + (int)threadIdx.x / LPR;
+  const int q = (int)threadIdx.x % LPR;
+  const int dim = p.dim;
+  const bool live = b < p.batch;
+  const bool lane_on = live && (4 * q < dim);
+
+  float4 s = f4_zero(), ss = f4_zero();
+  float lr = 0.f;
+
+  for (int f0 = 0; f0 < p.n_fields; f0 += CH) {
+    int32_t rid[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      rid[j] = -1;
+      if (f0 + j < p.n_fields && live) {
+        const FieldDev& fd = p.f[f0 + j];
+        const int64_t id = load_id(fd.ids, (int64_t)b * fd.id_stride, fd.is_i32 != 0);
+        if ((uint64_t)id < (uint64_t)fd.vocab) {
+          rid[j] = (int32_t)id;
+        } else if (q == 0 && p.err != nullptr) {
+          *p.err = 1 + f0 + j;
+        }
+      }
+    }
+    float4 v[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      v[j] = f4_zero();
+      if (rid[j] >= 0 && lane_on) {
+        v[j] = ldg_row16(p.f[f0 + j].table + (int64_t)rid[j] * dim + 4 * q);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      if (f0 + j < p.n_fields && lane_on) {
+        const FieldDev& fd = p.f[f0 + j];
+        if (fd.tile_col >= 0 && p.tile != nullptr) {
+          st_tile4(p.tile + (int64_t)b * p.tile_ld + fd.tile_col + 4 * q, v[j], p.tile_vec != 0);
+        }
+        if (fd.fm_slot >= 0) {
+          s = f4_add(s, v[j]);
+          ss = f4_fma(v[j], v[j], ss);
+          if (p.lrw != nullptr) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(p.lrw + (int64_t)fd.fm_slot * dim + 4 * q));
+            lr += f4_dot(v[j], w);
+          }
+        }
+      }
+    }
+  }
+
+  if (p.yfm != nullptr || p.ylr != nullptr) {
+    float t = (s.x * s.x - ss.x) + (s.y * s.y - ss.y) + (s.z * s.z - ss.z) + (s.w * s.w - ss.w);
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) {
+      t += __shfl_xor_sync(0xffffffffu, t, o);
+      lr += __shfl_xor_sync(0xffffffffu, lr, o);
+    }
+    if (live && q == 0) {
+      if (p.yfm != nullptr) p.yfm[b] = 0.5f * t;
+      if (p.ylr != nullptr) p.ylr[b] = lr + (p.lrb != nullptr ? __ldg(p.lrb) : 0.f);
+    }
+  }
+  if (p.fsum != nullptr && lane_on) {
+    *reinterpret_cast<float4*>(p.fsum + (int64_t)b * dim + 4 * q) = s;
+  }
+
+  if (live && p.tile != nullptr) {
+    for (int j = 0; j < p.n_dense; ++j) {
+      const DenseDev& dd = p.d[j];
+      for (int k = (q - j % LPR + LPR) % LPR; k < dd.width; k += LPR) {
+        p.tile[(int64_t)b * p.tile_ld + dd.tile_col + k] = load_dense_value(dd.src, (int64_t)b * dd.stride + k, dd.dtype);
+      }
+    }
+  }
+}
+
+// forward, scalar lanes: any dim / any alignment, tile emission only (no FM/LR).
+__global__ void __launch_bounds__(256) fields_fwd_scalar(const __grid_constant__ FwdParams p) {
+  const int dim = p.dim;
+  const int64_t per_sample = (int64_t)p.n_fields * dim;
+  const int64_t total = (int64_t)p.batch * per_sample;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per_sample);
+    const int r = (int)(i - (int64_t)b * per_sample);
+    const int f = r / dim, d = r - f * dim;
+    const FieldDev& fd = p.f[f];
+    const int64_t id = load_id(fd.ids, (int64_t)b * fd.id_stride, fd.is_i32 != 0);
+    float v = 0.f;
+    if ((uint64_t)id < (uint64_t)fd.vocab) {
+      v = __ldg(fd.table + id * dim + d);
+    } else if (d == 0 && p.err != nullptr) {
+      *p.err = 1 + f;
+    }
+    if (fd.tile_col >= 0) p.tile[(int64_t)b * p.tile_ld + fd.tile_col + d] = v;
+  }
+  // dense columns
+  int dense_w = 0;
+  for (int j = 0; j < p.n_dense; ++j) dense_w += p.d[j].width;
+  const int64_t dtotal = (int64_t)p.batch * dense_w;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < dtotal; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / dense_w);
+    int r = (int)(i - (int64_t)b * dense_w);
+    int j = 0;
+    while (r >= p.d[j].width) {
+      r -= p.d[j].width;
+      ++j;
+    }
+    const DenseDev& dd = p.d[j];
+    p.tile[(int64_t)b * p.tile_ld + dd.tile_col + r] = load_dense_value(dd.src, (int64_t)b * dd.stride + r, dd.dtype);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward, 16-byte lanes.  grid = (sample chunks, fields); ITER samples per lane.
+// ------------------------------------------------------------------------------------------------
+template <int LPR, int ITER>
+__global__ void __launch_bounds__(128) fields_bwd_v4(const __grid_constant__ BwdParams p) {
+  __shared__ float4 sm_dw[4][32];
+  __shared__ float sm_db[4];
+
+  const int f = blockIdx.y;
+  const FieldDev& fd = p.f[f];
+  const int spi = blockDim.x / LPR;  // samples per iteration
+  const int q = (int)threadIdx.x % LPR;
+  const int sl = (int)threadIdx.x / LPR;
+  const int dim = p.dim;
+  const bool lane_on = 4 * q < dim;
+  const int base = blockIdx.x * spi * ITER;
+  const bool fm = fd.fm_slot >= 0 && (p.dyfm != nullptr || p.dylr != nullptr);
+  const bool from_tile = p.tile != nullptr && fd.tile_col >= 0;
+  const bool has_dtile = p.dtile != nullptr && fd.tile_col >= 0;
+
+  float4 w = f4_zero();
+  if (fm && p.lrw != nullptr && p.dylr != nullptr && lane_on) {
+    w = __ldg(reinterpret_cast<const float4*>(p.lrw + (int64_t)fd.fm_slot * dim + 4 * q));
+  }
+
+  int32_t rid[ITER];
+#pragma unroll
+  for (int i = 0; i < ITER; ++i) {
+    const int b = base + i * spi + sl;
+    rid[i] = -1;
+    if (b < p.batch) {
+      const int64_t id = load_id(fd.ids, (int64_t)b * fd.id_stride, fd.is_i32 != 0);
+      if ((uint64_t)id < (uint64_t)fd.vocab) {
+        rid[i] = (int32_t)id;
+      } else if (q == 0 && p.err != nullptr) {
+        *p.err = 1 + f;
+      }
+    }
+  }
+
+  float4 g[ITER], e[ITER], S[ITER];
+  float dyf[ITER], dyl[ITER];
+#pragma unroll
+  for (int i = 0; i < ITER; ++i) {
+    const int b = base + i * spi + sl;
+    g[i] = f4_zero();
+    e[i] = f4_zero();
+    S[i] = f4_zero();
+    dyf[i] = 0.f;
+    dyl[i] = 0.f;
+    if (rid[i] >= 0 && lane_on) {
+      if (has_dtile) g[i] = ld_tile4(p.dtile + (int64_t)b * p.dtile_ld + fd.tile_col + 4 * q, p.dtile_vec != 0);
+      if (fm) {
+        e[i] = from_tile ? ld_tile4(p.tile + (int64_t)b * p.tile_ld + fd.tile_col + 4 * q, p.tile_vec != 0)
+                         : ldg_row16(fd.table + (int64_t)rid[i] * dim + 4 * q);
+        if (p.dyfm != nullptr) {
+          S[i] = ldg_row16(p.fsum + (int64_t)b * dim + 4 * q);
+          dyf[i] = __ldg(p.dyfm + b);
+        }
+        if (p.dylr != nullptr) dyl[i] = __ldg(p.dylr + b);
+      }
+    }
+  }
+
+  float4 dw = f4_zero();
+  float db = 0.f;
+#pragma unroll
+  for (int i = 0; i < ITER; ++i) {
+    if (rid[i] >= 0 && lane_on) {
+      if (fm) {
+        // d/d e of 0.5*sum_d[(sum_f e)^2 - sum_f e^2] = S - e ;  d/d e of <e, w> = w
+        g[i].x += dyf[i] * (S[i].x - e[i].x) + dyl[i] * w.x;
+        g[i].y += dyf[i] * (S[i].y - e[i].y) + dyl[i] * w.y;
+        g[i].z += dyf[i] * (S[i].z - e[i].z) + dyl[i] * w.z;
+        g[i].w += dyf[i] * (S[i].w - e[i].w) + dyl[i] * w.w;
+        dw = f4_fma(e[i], make_float4(dyl[i], dyl[i], dyl[i], dyl[i]), dw);
+        if (q == 0) db += dyl[i];
+      }
+      if (fd.grad != nullptr && rid[i] != fd.pad_idx) {
+        red_add_row16(fd.grad + (int64_t)rid[i] * dim + 4 * q, g[i]);
+      }
+    }
+  }
+
+  // LR weight / bias gradient: reduce over the samples of this block, one RED set per block.
+  const bool want_dw = fm && p.dlrw != nullptr && p.dylr != nullptr;
+  const bool want_db = fd.fm_slot == 0 && p.dlrb != nullptr && p.dylr != nullptr && fm;
+  if (want_dw || want_db) {  // block-uniform
+#pragma unroll
+    for (int o = 16; o >= LPR; o >>= 1) {
+      dw.x += __shfl_xor_sync(0xffffffffu, dw.x, o);
+      dw.y += __shfl_xor_sync(0xffffffffu, dw.y, o);
+      dw.z += __shfl_xor_sync(0xffffffffu, dw.z, o);
+      dw.w += __shfl_xor_sync(0xffffffffu, dw.w, o);
+    }
+    db = warp_sum(db);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane < LPR) sm_dw[warp][lane] = dw;
+    if (lane == 0) sm_db[warp] = db;
+    __syncthreads();
+    const int nwarp = blockDim.x >> 5;
+    if (warp == 0) {
+      if (want_dw && lane < LPR && 4 * lane < dim) {
+        float4 t = sm_dw[0][lane];
+        for (int k = 1; k < nwarp; ++k) t = f4_add(t, sm_dw[k][lane]);
+        red_add_row16(p.dlrw + (int64_t)fd.fm_slot * dim + 4 * lane, t);
+      }
+      if (want_db && lane == 0) {
+        float t = sm_db[0];
+        for (int k = 1; k < nwarp; ++k) t += sm_db[k];
+        atomicAdd(p.dlrb, t);
+      }
+    }
+  }
+}
+
+// backward, scalar lanes: d_tile -> table gradients only.
+__global__ void __launch_bounds__(256) fields_bwd_scalar(const __grid_constant__ BwdParams p) {
+  const int dim = p.dim;
+  const int64_t per_sample = (int64_t)p.n_fields * dim;
+  const int64_t total = (int64_t)p.batch * per_sample;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per_sample);
+    const int r = (int)(i - (int64_t)b * per_sample);
+    const int f = r / dim, d = r - f * dim;
+    const FieldDev& fd = p.f[f];
+    if (fd.tile_col < 0 || fd.grad == nullptr) continue;
+    const int64_t id = load_id(fd.ids, (int64_t)b * fd.id_stride, fd.is_i32 != 0);
+    if ((uint64_t)id >= (uint64_t)fd.vocab) {
+      if (d == 0 && p.err != nullptr) *p.err = 1 + f;
+      continue;
+    }
+    if (id == fd.pad_idx) continue;
+    atomicAdd(fd.grad + id * dim + d, __ldg(p.dtile + (int64_t)b * p.dtile_ld + fd.tile_col + d));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int pack_fields(const rh_field* fields, int n_fields, FieldDev* out, bool need_grad) {
+  for (int i = 0; i < n_fields; ++i) {
+    const rh_field& s = fields[i];
+    RH_REQUIRE(s.table != nullptr && s.ids != nullptr, RH_ERR_INVALID_ARG, "field %d: table/ids is NULL", i);
+    RH_REQUIRE(s.vocab > 0, RH_ERR_INVALID_ARG, "field %d: vocab must be > 0", i);
+    RH_REQUIRE(s.id_stride >= 0 && s.id_stride < (int64_t)1 << 31, RH_ERR_INVALID_ARG, "field %d: id_stride %lld out of range", i,
+               (long long)s.id_stride);
+    FieldDev& d = out[i];
+    d.table = s.table;
+    d.grad = need_grad ? s.table_grad : nullptr;
+    d.ids = s.ids;
+    d.id_stride = (int32_t)s.id_stride;
+    d.vocab = s.vocab;
+    d.pad_idx = s.padding_idx;
+    d.tile_col = s.tile_col;
+    d.fm_slot = s.fm_slot;
+    d.is_i32 = s.ids_are_i32;
+  }
+  return RH_OK;
+}
+
+template <int LPR>
+static void launch_fwd_v4(const FwdParams& p, cudaStream_t st) {
+  const int threads = 64;
+  const int spb = threads / LPR;
+  const int grid = (p.batch + spb - 1) / spb;
+  if (p.n_fields <= 8) {
+    fields_fwd_v4<LPR, 8><<<grid, threads, 0, st>>>(p);
+  } else if (p.n_fields <= 16) {
+    fields_fwd_v4<LPR, 16><<<grid, threads, 0, st>>>(p);
+  } else {
+    fields_fwd_v4<LPR, 32><<<grid, threads, 0, st>>>(p);
+  }
+}
+
+template <int LPR>
+static void launch_bwd_v4(const BwdParams& p, cudaStream_t st) {
+  constexpr int ITER = 4;
+  const int threads = 128;
+  const int spb = threads / LPR * ITER;
+  dim3 grid((p.batch + spb - 1) / spb, p.n_fields);
+  fields_bwd_v4<LPR, ITER><<<grid, threads, 0, st>>>(p);
+}
+
+}  // namespace rh
+
+using namespace rh;
+
+extern "C" int rh_fields_fwd(const rh_field* fields, int n_fields, int dim, const rh_dense* dense, int n_dense, int batch,
+                             float* tile, int64_t tile_ld, const float* lr_weight, const float* lr_bias, float* y_fm,
+                             float* y_lr, float* field_sum, int32_t* err_flag, void* stream) {
+  RH_REQUIRE(n_fields >= 0 && n_fields <= RH_MAX_FIELDS, RH_ERR_INVALID_ARG, "n_fields %d not in [0,%d]", n_fields, RH_MAX_FIELDS);
+  RH_REQUIRE(n_dense >= 0 && n_dense <= RH_MAX_DENSE, RH_ERR_INVALID_ARG, "n_dense %d not in [0,%d]", n_dense, RH_MAX_DENSE);
+  RH_REQUIRE(n_fields == 0 || fields != nullptr, RH_ERR_INVALID_ARG, "fields is NULL");
+  RH_REQUIRE(n_dense == 0 || dense != nullptr, RH_ERR_INVALID_ARG, "dense is NULL");
+  RH_REQUIRE(batch >= 0, RH_ERR_INVALID_ARG, "negative batch");
+  RH_REQUIRE(n_fields == 0 || dim > 0, RH_ERR_INVALID_ARG, "dim must be > 0");
+  RH_REQUIRE(n_dense == 0 || tile != nullptr, RH_ERR_INVALID_ARG, "dense columns need a tile");
+  if (batch == 0 || (n_fields == 0 && n_dense == 0)) return RH_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+
+  static thread_local FwdParams p;
+  memset(&p, 0, sizeof(p));
+  int rc = pack_fields(fields, n_fields, p.f, false);
+  if (rc != RH_OK) return rc;
+  bool any_tile = false, any_fm = false, vec_ok = (dim % 4 == 0) && dim <= 128, tile_vec = true;
+  for (int i = 0; i < n_fields; ++i) {
+    any_tile |= fields[i].tile_col >= 0;
+    any_fm |= fields[i].fm_slot >= 0;
+    vec_ok &= aligned16(fields[i].table);
+    if (fields[i].tile_col >= 0) tile_vec &= (fields[i].tile_col % 4 == 0);
+  }
+  RH_REQUIRE(!any_tile || tile != nullptr, RH_ERR_INVALID_ARG, "a field has tile_col >= 0 but tile is NULL");
+  if (tile != nullptr) tile_vec &= aligned16(tile) && (tile_ld % 4 == 0);
+  const bool want_fm = (y_fm != nullptr || y_lr != nullptr || field_sum != nullptr) && any_fm;
+  if (want_fm) {
+    RH_REQUIRE(y_lr == nullptr || lr_weight != nullptr, RH_ERR_INVALID_ARG, "y_lr requested without lr_weight");
+    vec_ok &= (lr_weight == nullptr || aligned16(lr_weight)) && (field_sum == nullptr || aligned16(field_sum));
+    RH_REQUIRE(vec_ok, RH_ERR_UNSUPPORTED,
+               "fused FM/LR needs dim %% 4 == 0, dim <= 128 and 16-byte aligned tables (dim=%d)", dim);
+  }
+  for (int j = 0; j < n_dense; ++j) {
+    RH_REQUIRE(dense[j].values != nullptr && dense[j].width > 0 && dense[j].tile_col >= 0, RH_ERR_INVALID_ARG, "dense %d invalid", j);
+    RH_REQUIRE(dense[j].dtype >= 0 && dense[j].dtype <= 3, RH_ERR_INVALID_ARG, "dense %d: dtype %d unknown", j, dense[j].dtype);
+    RH_REQUIRE(dense[j].stride >= 0 && dense[j].stride < (int64_t)1 << 31, RH_ERR_INVALID_ARG, "dense %d: stride out of range", j);
+    p.d[j].src = dense[j].values;
+    p.d[j].stride = (int32_t)dense[j].stride;
+    p.d[j].dtype = dense[j].dtype;
+    p.d[j].width = dense[j].width;
+    p.d[j].tile_col = dense[j].tile_col;
+  }
+  p.n_fields = n_fields;
+  p.n_dense = n_dense;
+  p.batch = batch;
+  p.dim = n_fields > 0 ? dim : 4;
+  p.tile = tile;
+  p.tile_ld = tile_ld;
+  p.tile_vec = tile_vec ? 1 : 0;
+  p.lrw = want_fm ? lr_weight : nullptr;
+  p.lrb = want_fm ? lr_bias : nullptr;
+  p.yfm = want_fm ? y_fm : nullptr;
+  p.ylr = want_fm ? y_lr : nullptr;
+  p.fsum = want_fm ? field_sum : nullptr;
+  p.err = err_flag;
+
+  if (vec_ok) {
+    const int lpr = n_fields > 0 ? pow2_ceil(dim / 4) : 4;
+    switch (lpr) {
+      case 1: launch_fwd_v4<1>(p, st); break;
+      case 2: launch_fwd_v4<2>(p, st); break;
+      case 4: launch_fwd_v4<4>(p, st); break;
+      case 8: launch_fwd_v4<8>(p, st); break;
+      case 16: launch_fwd_v4<16>(p, st); break;
+      default: launch_fwd_v4<32>(p, st); break;
+    }
+  } else {
+    const int64_t work = (int64_t)batch * ((int64_t)n_fields * dim + 1);
+    int grid = (int)((work + 255) / 256);
+    const int cap = num_sms() * 8;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    fields_fwd_scalar<<<grid, 256, 0, st>>>(p);
+  }
+  RH_LAUNCH_CHECK();
+  return RH_OK;
+}
+
+extern "C" int rh_fields_bwd(const rh_field* fields, int n_fields, int dim, int batch, const float* tile, int64_t tile_ld,
+                             const float* d_tile, int64_t d_tile_ld, const float* d_y_fm, const float* d_y_lr, const float* lr_weight,
+                             const float* field_sum, float* d_lr_weight, float* d_lr_bias, int32_t* err_flag, void* stream) {
+  RH_REQUIRE(n_fields >= 0 && n_fields <= RH_MAX_FIELDS, RH_ERR_INVALID_ARG, "n_fields %d not in [0,%d]", n_fields, RH_MAX_FIELDS);
+  RH_REQUIRE(n_fields == 0 || fields != nullptr, RH_ERR_INVALID_ARG, "fields is NULL");
+  RH_REQUIRE(batch >= 0 && dim > 0, RH_ERR_INVALID_ARG, "bad batch/dim");
+  if (batch == 0 || n_fields == 0) return RH_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+
+  static thread_local BwdParams p;
+  memset(&p, 0, sizeof(p));
+  int rc = pack_fields(fields, n_fields, p.f, true);
+  if (rc != RH_OK) return rc;
+  bool any_fm = false, vec_ok = (dim % 4 == 0) && dim <= 128, tile_vec = true, dtile_vec = true;
+  for (int i = 0; i < n_fields; ++i) {
+    any_fm |= fields[i].fm_slot >= 0;
+    vec_ok &= aligned16(fields[i].table) && (fields[i].table_grad == nullptr || aligned16(fields[i].table_grad));
+    if (fields[i].tile_col >= 0) tile_vec &= (fields[i].tile_col % 4 == 0);
+  }
+  const bool want_fm = any_fm && (d_y_fm != nullptr || d_y_lr != nullptr);
+  dtile_vec = tile_vec;  // column alignment is shared
+  if (tile != nullptr) tile_vec &= aligned16(tile) && (tile_ld % 4 == 0);
+  if (d_tile != nullptr) dtile_vec &= aligned16(d_tile) && (d_tile_ld % 4 == 0);
+  if (want_fm) {
+    RH_REQUIRE(d_y_fm == nullptr || field_sum != nullptr, RH_ERR_INVALID_ARG, "d_y_fm needs field_sum");
+    RH_REQUIRE(d_y_lr == nullptr || lr_weight != nullptr, RH_ERR_INVALID_ARG, "d_y_lr needs lr_weight");
+    vec_ok &= (lr_weight == nullptr || aligned16(lr_weight)) && (field_sum == nullptr || aligned16(field_sum)) &&
+              (d_lr_weight == nullptr || aligned16(d_lr_weight));
+    RH_REQUIRE(vec_ok, RH_ERR_UNSUPPORTED, "fused FM/LR backward needs dim %% 4 == 0, dim <= 128 and 16-byte alignment (dim=%d)", dim);
+  }
+  p.n_fields = n_fields;
+  p.batch = batch;
+  p.dim = dim;
+  p.tile = tile;
+  p.dtile = d_tile;
+  p.tile_ld = tile_ld;
+  p.dtile_ld = d_tile_ld;
+  p.tile_vec = tile_vec ? 1 : 0;
+  p.dtile_vec = dtile_vec ? 1 : 0;
+  p.dyfm = want_fm ? d_y_fm : nullptr;
+  p.dylr = want_fm ? d_y_lr : nullptr;
+  p.lrw = lr_weight;
+  p.fsum = field_sum;
+  p.dlrw = d_lr_weight;
+  p.dlrb = d_lr_bias;
+  p.err = err_flag;
+
+  if (vec_ok) {
+    const int lpr = pow2_ceil(dim / 4);
+    switch (lpr) {
+      case 1: launch_bwd_v4<1>(p, st); break;
+      case 2: launch_bwd_v4<2>(p, st); break;
+      case 4: launch_bwd_v4<4>(p, st); break;
+      case 8: launch_bwd_v4<8>(p, st); break;
+      case 16: launch_bwd_v4<16>(p, st); break;
+      default: launch_bwd_v4<32>(p, st); break;
+    }
+  } else {
+    if (d_tile == nullptr) return RH_OK;  // nothing flows into the tables
+    const int64_t work = (int64_t)batch * n_fields * dim;
+    int grid = (int)((work + 255) / 256);
+    const int cap = num_sms() * 8;
+    if (grid > cap) grid = cap;
+    fields_bwd_scalar<<<grid, 256, 0, st>>>(p);
+  }
+  RH_LAUNCH_CHECK();
+  return RH_OK;
+}

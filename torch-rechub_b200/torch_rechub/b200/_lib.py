@@ -1,0 +1,139 @@
+"""ctypes binding of ``librechub_b200.so`` (C ABI declared in ``include/rechub_b200.h``).
+
+PyTorch is used for device memory and streams only: every call passes raw ``data_ptr()`` values and the
+current stream handle.  Nothing here computes.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PACKAGE_ROOT = os.path.abspath(os.path.join(_HERE, "..", ".."))  # .../torch-rechub_b200
+LIB_PATH = os.environ.get("RECHUB_B200_LIB", os.path.join(PACKAGE_ROOT, "lib", "librechub_b200.so"))
+RH_MAX_FIELDS = 64
+RH_MAX_DENSE = 32
+
+c_p = ctypes.c_void_p
+c_i = ctypes.c_int
+c_i64 = ctypes.c_int64
+c_f = ctypes.c_float
+
+
+class RhField(ctypes.Structure):
+    _fields_ = [("table", c_p), ("table_grad", c_p), ("ids", c_p), ("id_stride", c_i64), ("ids_are_i32", ctypes.c_int32), ("vocab", ctypes.c_int32), ("padding_idx", ctypes.c_int32), ("tile_col", ctypes.c_int32),
+                ("fm_slot", ctypes.c_int32)]
+
+
+class RhDense(ctypes.Structure):
+    _fields_ = [("values", c_p), ("stride", c_i64), ("dtype", ctypes.c_int32), ("width", ctypes.c_int32), ("tile_col", ctypes.c_int32)]
+
+
+# name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/rechub_b200.h one to one
+PROTOTYPES = {
+    "rh_abi_version": [],
+    "rh_last_error": [],
+    "rh_launch_count": [],
+    "rh_fields_fwd": [c_p, c_i, c_i, c_p, c_i, c_i, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
+    "rh_fields_bwd": [c_p, c_i, c_i, c_i, c_p, c_i64, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
+    "rh_rows_gather": [c_p, c_i, c_i, c_p, c_i, c_i64, c_p, c_p, c_p],
+    "rh_rows_scatter_add": [c_p, c_i, c_i, c_i, c_p, c_i, c_i64, c_p, c_p, c_p],
+    "rh_seq_pool_fwd": [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_i64, c_p, c_i64, c_p, c_p],
+    "rh_seq_pool_bwd": [c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_i64, c_p, c_i64, c_p, c_p],
+    "rh_rows_zero": [c_p, c_i, c_i, c_p, c_i, c_i64, c_p],
+    "rh_rowwise_update": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_i, c_i64, c_i, c_p, c_p, c_f, c_f, c_f, c_f, c_p],
+    "rh_opt_advance": [c_p, c_p],
+    "rh_fields_rowwise_update": [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_f, c_f, c_f, c_f, c_p],
+    "rh_fields_zero": [c_p, c_i, c_i, c_i, c_p],
+    "rh_fm_fwd": [c_p, c_i, c_i, c_i, c_i, c_p, c_p],
+    "rh_fm_bwd": [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p],
+    "rh_cross_fwd": [c_p, c_i64, c_i, c_i, c_i, c_p, c_p, c_p, c_i64, c_p, c_p],
+    "rh_cross_bwd": [c_p, c_i64, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_i64, c_p, c_i64, c_p, c_p, c_p],
+    "rh_colstats": [c_p, c_i64, c_i64, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_f, c_p],
+    "rh_bn_act_fwd": [c_p, c_i64, c_i64, c_i, c_p, c_p, c_f, c_p, c_p, c_i, c_p, c_f, c_p, c_f, c_p, c_i64, c_p],
+    "rh_bn_act_bwd": [c_p, c_i64, c_i64, c_i, c_p, c_p, c_f, c_p, c_p, c_i, c_p, c_f, c_p, c_f, c_p, c_i64, c_i, c_p, c_i64, c_p, c_p, c_p, c_p],
+    "rh_din_attn_input_fwd": [c_p, c_i, c_p, c_i, c_i, c_p, c_p, c_i, c_i64, c_i, c_i, c_p, c_p, c_p, c_p, c_p],
+    "rh_din_weighted_sum_fwd": [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p],
+    "rh_din_weighted_sum_bwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p],
+    "rh_din_attn_input_bwd": [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_p, c_i, c_i64, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
+}
+_RESTYPES = {"rh_last_error": ctypes.c_char_p, "rh_launch_count": ctypes.c_ulonglong}
+
+_lock = threading.Lock()
+_lib = None
+
+
+class EngineMissing(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded library; raises :class:`EngineMissing` (loudly) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise EngineMissing("librechub_b200.so not found at %s — CUDA tensors need the sm_100a engine; build it with "
+                                    "`python -c 'import __graft_entry__ as g; g.build()'` or `make -C torch-rechub_b200/csrc`. "
+                                    "There is no eager fallback for CUDA inputs." % LIB_PATH)
+            handle = ctypes.CDLL(LIB_PATH)
+            for name, argtypes in PROTOTYPES.items():
+                fn = getattr(handle, name)  # AttributeError if the .so does not export a declared symbol
+                fn.argtypes = argtypes
+                fn.restype = _RESTYPES.get(name, ctypes.c_int)
+            if handle.rh_abi_version() != 1:
+                raise EngineMissing("librechub_b200.so ABI version %d != 1" % handle.rh_abi_version())
+            _lib = handle
+    return _lib
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def check(status, what):
+    if status != 0:
+        msg = lib().rh_last_error()
+        msg = msg.decode() if msg else ""
+        if status == 2:
+            raise NotImplementedError("%s: %s" % (what, msg))
+        raise EngineError("%s failed (status %d): %s" % (what, status, msg))
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    """data_ptr of a tensor, or NULL."""
+    return None if t is None else t.data_ptr()
+
+
+# ---- out-of-range id flag --------------------------------------------------------------------------
+_err_flags = {}
+
+
+def err_flag(device):
+    """Per-device int32 flag the kernels set on an out-of-range id."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    t = _err_flags.get(key)
+    if t is None:
+        t = torch.zeros(1, dtype=torch.int32, device=device)
+        _err_flags[key] = t
+    return t
+
+
+def check_errors(device=None):
+    """Raise the reference's ``IndexError`` if any kernel since the last check saw an out-of-range id.
+
+    Costs one D2H read (a sync); CTRTrainer calls it where the reference already syncs (``loss.item()``).
+    """
+    flags = list(_err_flags.values()) if device is None else [err_flag(torch.device(device))]
+    for t in flags:
+        v = int(t.item())
+        if v != 0:
+            t.zero_()
+            raise IndexError("index out of range in self (embedding lookup, field #%d of the launch)" % (v - 1))

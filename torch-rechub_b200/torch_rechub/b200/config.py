@@ -1,0 +1,25 @@
+"""Module-level knobs of the engine (the reference's constructors are left untouched: SURVEY.md §5)."""
+import os
+
+
+def _flag(name, default):
+    v = os.environ.get(name)
+    if v is None:
+        return default
+    return v.strip().lower() not in ("0", "false", "no", "off", "")
+
+
+# Route the embedding tables of CTRTrainer to the fused row-wise (lazy) optimiser that mirrors the
+# configured torch optimiser on TOUCHED ROWS ONLY (SURVEY.md §7 hard part 2).  Off by default: the
+# default keeps the reference's exact dense-optimiser semantics (dense ``weight.grad`` + torch.optim).
+rowwise_optimizer = _flag("RECHUB_B200_ROWWISE_OPT", False)
+
+# Capture CTRTrainer's training step into a CUDA graph (static shapes only; ragged last batches run eagerly).
+cuda_graph = _flag("RECHUB_B200_CUDA_GRAPH", False)
+
+# Check the device-side out-of-range-id flag after every forward (one D2H sync per step).  When off the
+# flag is checked at the trainer's existing sync points (``loss.item()``) and by ``check_errors()``.
+eager_bounds_check = _flag("RECHUB_B200_EAGER_BOUNDS_CHECK", False)
+
+# Set by the graph runner while inputs live in static buffers that the next batch overwrites.
+static_inputs = False

@@ -1,0 +1,553 @@
+"""Autograd wrappers around the C-ABI kernels (CUDA tensors only).
+
+Every function here launches hand-written sm_100a kernels from ``librechub_b200.so`` on the current
+stream.  Table gradients never travel through autograd as tensors: the backward kernels scatter-add
+into the table's persistent dense gradient buffer (``table.grad_target``), which is what
+``weight.grad`` points at afterwards.
+"""
+import ctypes
+
+import torch
+
+from . import _lib, table as _table
+from ._lib import RhDense, RhField, check, ptr, stream_ptr
+
+_ID_DTYPES = (torch.int64, torch.int32)
+_DENSE_CODES = {torch.float32: 0, torch.float64: 1, torch.int64: 2, torch.int32: 3}
+
+
+def _as_ids(t):
+    """ids as the kernels read them: int64/int32, no copy when already so (reference: ``.long()``, layers.py:83)."""
+    return t if t.dtype in _ID_DTYPES else t.long()
+
+
+def _rowmajor(t):
+    """A 2-D view with unit inner stride (copy only when the layout forces it)."""
+    if t.dim() != 2:
+        t = t.reshape(t.shape[0], -1)
+    if t.stride(1) != 1 or (t.shape[0] > 1 and t.stride(0) < t.shape[1]):
+        t = t.contiguous()
+    return t
+
+
+def _pad4(n):
+    return (n + 3) // 4 * 4
+
+
+# =====================================================================================================
+# single-table lookup of any id shape  (FieldTable.forward)
+# =====================================================================================================
+class _RowsGather(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, weight, ids, padding_idx):
+        L = _lib.lib()
+        ids_c = _as_ids(ids).contiguous()
+        n = ids_c.numel()
+        vocab, dim = weight.shape
+        out = torch.empty(tuple(ids.shape) + (dim,), dtype=torch.float32, device=weight.device)
+        check(L.rh_rows_gather(weight.data_ptr(), vocab, dim, ids_c.data_ptr(), int(ids_c.dtype == torch.int32), n, out.data_ptr(), _lib.err_flag(weight.device).data_ptr(), stream_ptr()), "rh_rows_gather")
+        ctx.weight = weight
+        ctx.ids = ids_c
+        ctx.padding_idx = -1 if padding_idx is None else int(padding_idx)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        weight, ids = ctx.weight, ctx.ids
+        target, slot = _table.grad_target(weight)
+        if target is not None:
+            L = _lib.lib()
+            vocab, dim = weight.shape
+            g = d_out.contiguous()
+            check(L.rh_rows_scatter_add(target.data_ptr(), vocab, dim, ctx.padding_idx, ids.data_ptr(), int(ids.dtype == torch.int32), ids.numel(), g.data_ptr(), _lib.err_flag(weight.device).data_ptr(), stream_ptr()),
+                  "rh_rows_scatter_add")
+            _table.note_dirty(slot, ids)
+        return None, None, None
+
+
+def table_lookup(tbl, ids):
+    """``tbl(ids)`` for a CUDA :class:`FieldTable` (reference: nn.Embedding call at basic/layers.py:83-99)."""
+    w = tbl.weight
+    if w.dtype != torch.float32:
+        raise NotImplementedError("the sm_100a engine keeps tables in fp32 (got %s)" % w.dtype)
+    if not ids.is_cuda:
+        raise RuntimeError("Expected all tensors to be on the same device: table on %s, ids on cpu" % w.device)
+    return _RowsGather.apply(w, ids, tbl.padding_idx)
+
+
+# =====================================================================================================
+# the fused front end: multi-field gather (+ pooled sequences + dense columns) -> tile, (+ FM, + LR)
+# =====================================================================================================
+class FieldRef(object):
+    """One SparseFeature column of a plan."""
+    __slots__ = ("weight", "ids", "vocab", "dim", "padding_idx", "tile_col", "fm_slot")
+
+    def __init__(self, weight, ids, padding_idx, tile_col, fm_slot):
+        self.weight = weight
+        self.ids = ids
+        self.vocab, self.dim = weight.shape
+        self.padding_idx = -1 if padding_idx is None else int(padding_idx)
+        self.tile_col = tile_col
+        self.fm_slot = fm_slot
+
+
+class SeqRef(object):
+    """One pooled SequenceFeature column block of a plan (sum / mean pooling)."""
+    __slots__ = ("weight", "ids", "vocab", "dim", "padding_idx", "mask_id", "mode", "tile_col")
+
+    def __init__(self, weight, ids, padding_idx, mode, tile_col):
+        self.weight = weight
+        self.ids = ids
+        self.vocab, self.dim = weight.shape
+        self.padding_idx = -1 if padding_idx is None else int(padding_idx)
+        self.mask_id = -1 if padding_idx is None else int(padding_idx)  # InputMask rule, layers.py:154-157
+        self.mode = mode
+        self.tile_col = tile_col
+
+
+class DenseRef(object):
+    __slots__ = ("values", "width", "tile_col")
+
+    def __init__(self, values, width, tile_col):
+        self.values = values
+        self.width = width
+        self.tile_col = tile_col
+
+
+class TilePlan(object):
+    """What one fused front-end call has to produce."""
+
+    def __init__(self, batch, device):
+        self.batch = batch
+        self.device = device
+        self.fields = []  # FieldRef
+        self.seqs = []  # SeqRef
+        self.dense = []  # DenseRef
+        self.tile_width = 0  # logical columns of the tile (0: no tile)
+        self.n_fm = 0
+        self.fm_dim = 0
+        self.want_fm = False
+        self.want_lr = False
+        self.by_name = {}
+
+    def weights(self):
+        seen, out = set(), []
+        for r in list(self.fields) + list(self.seqs):
+            if id(r.weight) not in seen:
+                seen.add(id(r.weight))
+                out.append(r.weight)
+        return out
+
+    def field_groups(self):
+        """Fields grouped by row width, in chunks of <= RH_MAX_FIELDS (one launch each).
+        FM fields must all sit in ONE group (checked by the caller)."""
+        by_dim = {}
+        for f in sorted(self.fields, key=lambda r: r.fm_slot < 0):  # FM fields first (stable): they share one launch
+            by_dim.setdefault(f.dim, []).append(f)
+        groups = []
+        for dim, fs in by_dim.items():
+            for i in range(0, len(fs), _lib.RH_MAX_FIELDS):
+                groups.append((dim, fs[i:i + _lib.RH_MAX_FIELDS]))
+        return groups
+
+
+def _field_array(refs, grads=None):
+    arr = (RhField * len(refs))()
+    for i, r in enumerate(refs):
+        a = arr[i]
+        ids = r.ids
+        a.table = r.weight.data_ptr()
+        a.table_grad = None if grads is None or grads[i] is None else grads[i].data_ptr()
+        a.ids = ids.data_ptr()
+        a.id_stride = ids.stride(0) if ids.dim() > 0 and ids.shape[0] > 1 else 1
+        a.ids_are_i32 = int(ids.dtype == torch.int32)
+        a.vocab = r.vocab
+        a.padding_idx = r.padding_idx
+        a.tile_col = r.tile_col
+        a.fm_slot = r.fm_slot
+    return arr
+
+
+def _dense_array(refs):
+    arr = (RhDense * max(len(refs), 1))()
+    for i, r in enumerate(refs):
+        v = r.values
+        a = arr[i]
+        a.values = v.data_ptr()
+        a.stride = v.stride(0) if v.shape[0] > 1 else r.width
+        a.dtype = _DENSE_CODES[v.dtype]
+        a.width = r.width
+        a.tile_col = r.tile_col
+    return arr
+
+
+class _FusedTile(torch.autograd.Function):
+    """tile, y_fm, y_lr = front(plan).  Inputs carried for autograd connectivity only: lr weight/bias, table weights."""
+
+    @staticmethod
+    def forward(ctx, plan, lr_weight, lr_bias, *weights):
+        L = _lib.lib()
+        dev = plan.device
+        B = plan.batch
+        st = stream_ptr()
+        err = _lib.err_flag(dev).data_ptr()
+        tile = None
+        ld = 0
+        if plan.tile_width > 0:
+            ld = _pad4(plan.tile_width)
+            tile = torch.empty((B, ld), dtype=torch.float32, device=dev)  # columns >= tile_width are padding, never read
+        y_fm = torch.empty(B, dtype=torch.float32, device=dev) if plan.want_fm else None
+        y_lr = torch.empty(B, dtype=torch.float32, device=dev) if plan.want_lr else None
+        fsum = torch.empty((B, plan.fm_dim), dtype=torch.float32, device=dev) if plan.want_fm else None
+
+        groups = plan.field_groups()
+        dense_left = list(plan.dense)
+        if not groups and dense_left:
+            groups = [(4, [])]
+        for dim, refs in groups:
+            has_fm = any(r.fm_slot >= 0 for r in refs)
+            dn = dense_left[:_lib.RH_MAX_DENSE]
+            dense_left = dense_left[len(dn):]
+            check(
+                L.rh_fields_fwd(_field_array(refs) if refs else None, len(refs), dim,
+                                _dense_array(dn) if dn else None, len(dn), B, ptr(tile), ld, ptr(lr_weight) if (has_fm and plan.want_lr) else None,
+                                ptr(lr_bias) if (has_fm and plan.want_lr) else None,
+                                ptr(y_fm) if has_fm else None, ptr(y_lr) if (has_fm and plan.want_lr) else None, ptr(fsum) if has_fm else None, err, st), "rh_fields_fwd")
+        while dense_left:  # more than RH_MAX_DENSE numeric columns
+            dn = dense_left[:_lib.RH_MAX_DENSE]
+            dense_left = dense_left[len(dn):]
+            check(L.rh_fields_fwd(None, 0, 4, _dense_array(dn), len(dn), B, ptr(tile), ld, None, None, None, None, None, err, st), "rh_fields_fwd")
+        for s in plan.seqs:
+            ids = s.ids
+            check(
+                L.rh_seq_pool_fwd(s.weight.data_ptr(), s.vocab, s.dim, ids.data_ptr(), int(ids.dtype == torch.int32), B, ids.shape[1], s.mode, s.mask_id, tile.data_ptr() + 4 * s.tile_col, ld, err, st),
+                "rh_seq_pool_fwd")
+
+        ctx.plan = plan
+        ctx.ld = ld
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(tile, fsum, lr_weight)
+        tile_view = None
+        if tile is not None:
+            tile_view = tile if ld == plan.tile_width else tile[:, :plan.tile_width]
+        return tile_view, y_fm, y_lr
+
+    @staticmethod
+    def backward(ctx, d_tile, d_yfm, d_ylr):
+        L = _lib.lib()
+        plan = ctx.plan
+        tile, fsum, lr_weight = ctx.saved_tensors
+        B = plan.batch
+        st = stream_ptr()
+        err = _lib.err_flag(plan.device).data_ptr()
+        d_ld = 0
+        if d_tile is not None:
+            d_tile = _rowmajor(d_tile)
+            d_ld = d_tile.stride(0) if B > 1 else d_tile.shape[1]
+        if d_yfm is not None:
+            d_yfm = d_yfm.contiguous()
+        if d_ylr is not None:
+            d_ylr = d_ylr.contiguous()
+        d_lrw = d_lrb = None
+        if d_ylr is not None and lr_weight is not None:
+            n = lr_weight.numel()
+            buf = torch.zeros(_pad4(n) + 1, dtype=torch.float32, device=plan.device)
+            d_lrw = buf[:n].view_as(lr_weight)
+            d_lrb = buf[_pad4(n):_pad4(n) + 1]
+
+        for dim, refs in plan.field_groups():
+            targets = [_table.grad_target(r.weight) for r in refs]
+            grads = [t[0] for t in targets]
+            has_fm = any(r.fm_slot >= 0 for r in refs) and (d_yfm is not None or d_ylr is not None)
+            if d_tile is None and not has_fm:
+                continue
+            check(
+                L.rh_fields_bwd(_field_array(refs, grads), len(refs), dim, B, ptr(tile), ctx.ld, ptr(d_tile), d_ld, ptr(d_yfm) if has_fm else None,
+                                ptr(d_ylr) if has_fm else None, ptr(lr_weight) if has_fm else None, ptr(fsum) if has_fm else None, ptr(d_lrw) if has_fm else None,
+                                ptr(d_lrb) if has_fm else None, err, st), "rh_fields_bwd")
+            for r, (g, slot) in zip(refs, targets):
+                if g is not None:
+                    _table.note_dirty(slot, r.ids)
+        if d_tile is not None:
+            for s in plan.seqs:
+                g, slot = _table.grad_target(s.weight)
+                if g is None:
+                    continue
+                ids = s.ids
+                check(
+                    L.rh_seq_pool_bwd(g.data_ptr(), s.vocab, s.dim, s.padding_idx, ids.data_ptr(), int(ids.dtype == torch.int32), B, ids.shape[1], s.mode, s.mask_id, d_tile.data_ptr() + 4 * s.tile_col, d_ld, err, st),
+                    "rh_seq_pool_bwd")
+                _table.note_dirty(slot, ids)
+        return (None, d_lrw, d_lrb) + (None,) * len(plan.weights())
+
+
+def fused_tile(plan, lr_weight=None, lr_bias=None):
+    """Run a :class:`TilePlan`; returns ``(tile (B, width) or None, y_fm (B,) or None, y_lr (B,) or None)``."""
+    ws = plan.weights()
+    for w in ws:
+        if w.dtype != torch.float32:
+            raise NotImplementedError("the sm_100a engine keeps tables in fp32 (got %s)" % w.dtype)
+    return _FusedTile.apply(plan, lr_weight, lr_bias, *ws)
+
+
+# =====================================================================================================
+# FM on a materialised (B, F, D) tensor
+# =====================================================================================================
+class _FM(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, x, reduce_sum):
+        L = _lib.lib()
+        xc = x.contiguous()
+        B, F, D = xc.shape
+        y = torch.empty((B, 1) if reduce_sum else (B, D), dtype=torch.float32, device=x.device)
+        check(L.rh_fm_fwd(xc.data_ptr(), B, F, D, int(reduce_sum), y.data_ptr(), stream_ptr()), "rh_fm_fwd")
+        ctx.save_for_backward(xc)
+        ctx.reduce_sum = reduce_sum
+        return y
+
+    @staticmethod
+    def backward(ctx, d_y):
+        L = _lib.lib()
+        (xc,) = ctx.saved_tensors
+        B, F, D = xc.shape
+        d_x = torch.empty_like(xc)
+        g = d_y.contiguous()
+        check(L.rh_fm_bwd(xc.data_ptr(), g.data_ptr(), B, F, D, int(ctx.reduce_sum), d_x.data_ptr(), stream_ptr()), "rh_fm_bwd")
+        return d_x, None
+
+
+def fm(x, reduce_sum=True):
+    if x.dtype != torch.float32 or x.dim() != 3:
+        raise NotImplementedError("FM kernel takes a (B, F, D) fp32 tensor")
+    return _FM.apply(x, bool(reduce_sum))
+
+
+# =====================================================================================================
+# CrossNetwork
+# =====================================================================================================
+def _ptr_array(tensors):
+    arr = (ctypes.c_void_p * max(len(tensors), 1))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+class _Cross(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, x, n_layers, *params):
+        L = _lib.lib()
+        ws, bs = params[:n_layers], params[n_layers:]
+        x2 = _rowmajor(x)
+        B, W = x2.shape
+        x_ld = x2.stride(0) if B > 1 else W
+        out_ld = _pad4(W)
+        out = torch.empty((B, out_ld), dtype=torch.float32, device=x.device)
+        xw = torch.empty((max(n_layers, 1), B), dtype=torch.float32, device=x.device)
+        wc = [w.contiguous() for w in ws]
+        bc = [b.contiguous() for b in bs]
+        check(L.rh_cross_fwd(x2.data_ptr(), x_ld, B, W, n_layers, _ptr_array(wc), _ptr_array(bc), out.data_ptr(), out_ld, xw.data_ptr(), stream_ptr()), "rh_cross_fwd")
+        ctx.n_layers = n_layers
+        ctx.save_for_backward(x2, xw, *wc, *bc)
+        return out if out_ld == W else out[:, :W]
+
+    @staticmethod
+    def backward(ctx, d_out):
+        L = _lib.lib()
+        n = ctx.n_layers
+        saved = ctx.saved_tensors
+        x2, xw = saved[0], saved[1]
+        wc, bc = saved[2:2 + n], saved[2 + n:2 + 2 * n]
+        B, W = x2.shape
+        x_ld = x2.stride(0) if B > 1 else W
+        g = _rowmajor(d_out)
+        g_ld = g.stride(0) if B > 1 else W
+        dx_ld = _pad4(W)
+        d_x = torch.empty((B, dx_ld), dtype=torch.float32, device=x2.device)
+        Wp = _pad4(W)
+        gbuf = torch.zeros((2 * max(n, 1), Wp), dtype=torch.float32, device=x2.device)
+        d_ws = [gbuf[l, :W] for l in range(n)]
+        d_bs = [gbuf[n + l, :W] for l in range(n)]
+        check(
+            L.rh_cross_bwd(x2.data_ptr(), x_ld, B, W, n, _ptr_array(wc), _ptr_array(bc), xw.data_ptr(), g.data_ptr(), g_ld, d_x.data_ptr(), dx_ld, _ptr_array(d_ws), _ptr_array(d_bs), stream_ptr()), "rh_cross_bwd")
+        d_x = d_x if dx_ld == W else d_x[:, :W]
+        return (d_x, None) + tuple(dw.view_as(w) for dw, w in zip(d_ws, wc)) + tuple(d_bs)
+
+
+def cross_network(x, weights, biases):
+    """CrossNetwork.forward on CUDA; ``weights[l]``: (1, W) Linear weight, ``biases[l]``: (W,) (layers.py:409-420)."""
+    n = len(weights)
+    if x.dtype != torch.float32:
+        x = x.float()
+    return _Cross.apply(x, n, *weights, *biases)
+
+
+# =====================================================================================================
+# BatchNorm1d + activation + dropout
+# =====================================================================================================
+ACT_CODES = {"none": 0, "relu": 1, "dice": 2, "prelu": 3, "sigmoid": 4, "leakyrelu": 5}
+_scratch = {}
+
+
+def _colstats_scratch(device, cols):
+    key = (device.index, cols)
+    t = _scratch.get(key)
+    if t is None:
+        t = torch.zeros(2 * cols + 1, dtype=torch.float32, device=device)
+        _scratch[key] = t
+    return t
+
+
+class _BnAct(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, h, gamma, beta, act_param, cfg):
+        # cfg: dict(running_mean, running_var, num_batches_tracked, momentum, eps, training, act, dice_eps, p_drop)
+        L = _lib.lib()
+        h2 = _rowmajor(h)
+        rows, cols = h2.shape
+        h_ld = h2.stride(0) if rows > 1 else cols
+        dev = h.device
+        st = stream_ptr()
+        training = cfg["training"]
+        if training:
+            stats = torch.empty((2, cols), dtype=torch.float32, device=dev)
+            mean, var = stats[0], stats[1]
+            rm, rv, nbt = cfg["running_mean"], cfg["running_var"], cfg["num_batches_tracked"]
+            check(L.rh_colstats(h2.data_ptr(), h_ld, rows, cols, mean.data_ptr(), var.data_ptr(), _colstats_scratch(dev, cols).data_ptr(), ptr(rm), ptr(rv), ptr(nbt), float(cfg["momentum"]), st), "rh_colstats")
+        else:
+            mean, var = cfg["running_mean"], cfg["running_var"]
+        mask = None
+        p = float(cfg["p_drop"])
+        if training and p > 0.0:
+            mask = torch.empty((rows, cols), dtype=torch.uint8, device=dev).bernoulli_(1.0 - p)
+        y = torch.empty((rows, cols), dtype=torch.float32, device=dev)
+        check(
+            L.rh_bn_act_fwd(h2.data_ptr(), h_ld, rows, cols, ptr(mean), ptr(var), float(cfg["eps"]), ptr(gamma), ptr(beta), cfg["act"], ptr(act_param), float(cfg["dice_eps"]), ptr(mask), p, y.data_ptr(), cols, st),
+            "rh_bn_act_fwd")
+        ctx.cfg = cfg
+        ctx.has_param = act_param is not None
+        ctx.save_for_backward(h2, mean, var, gamma, beta, act_param, mask)
+        return y
+
+    @staticmethod
+    def backward(ctx, d_y):
+        L = _lib.lib()
+        cfg = ctx.cfg
+        h2, mean, var, gamma, beta, act_param, mask = ctx.saved_tensors
+        rows, cols = h2.shape
+        h_ld = h2.stride(0) if rows > 1 else cols
+        g = _rowmajor(d_y)
+        g_ld = g.stride(0) if rows > 1 else cols
+        dev = h2.device
+        d_h = torch.empty((rows, cols), dtype=torch.float32, device=dev)
+        gbuf = torch.zeros(2 * cols + 1, dtype=torch.float32, device=dev)
+        d_gamma, d_beta, d_alpha = gbuf[:cols], gbuf[cols:2 * cols], gbuf[2 * cols:]
+        check(
+            L.rh_bn_act_bwd(h2.data_ptr(), h_ld, rows, cols, ptr(mean), ptr(var), float(cfg["eps"]), ptr(gamma), ptr(beta), cfg["act"], ptr(act_param), float(cfg["dice_eps"]), ptr(mask), float(cfg["p_drop"]),
+                            g.data_ptr(), g_ld, int(bool(cfg["training"])), d_h.data_ptr(), cols, d_gamma.data_ptr(), d_beta.data_ptr(), d_alpha.data_ptr() if ctx.has_param else None, stream_ptr()), "rh_bn_act_bwd")
+        return d_h, (d_gamma if gamma is not None else None), (d_beta if beta is not None else None), (d_alpha.view_as(act_param) if ctx.has_param else None), None
+
+
+def bn_act(h, bn, act_code, act_param, dice_eps, p_drop, training):
+    """``dropout(act(bn(h)))`` for a 2-D ``h`` — one tower layer after its Linear (basic/layers.py:282-285)."""
+    cfg = {
+        "running_mean": bn.running_mean,
+        "running_var": bn.running_var,
+        "num_batches_tracked": bn.num_batches_tracked,
+        "momentum": bn.momentum,
+        "eps": bn.eps,
+        "training": bool(training),
+        "act": act_code,
+        "dice_eps": dice_eps,
+        "p_drop": p_drop,
+    }
+    return _BnAct.apply(h, bn.weight, bn.bias, act_param, cfg)
+
+
+# =====================================================================================================
+# DIN target attention pieces
+# =====================================================================================================
+class _DinAttnInput(torch.autograd.Function):
+    """(att_in (B*L, 4D), hist (B, L, D), target (B, D)) from the two tables; backward ends in the scatter-add."""
+
+    @staticmethod
+    def forward(ctx, hist_w, tgt_w, hist_ids, tgt_ids, hist_pad, tgt_pad):
+        L = _lib.lib()
+        dev = hist_w.device
+        hi = _as_ids(hist_ids).contiguous()
+        ti = _as_ids(tgt_ids)
+        if ti.dtype != hi.dtype:
+            ti = ti.to(hi.dtype)
+        B, S = hi.shape
+        D = hist_w.shape[1]
+        att_in = torch.empty((B * S, 4 * D), dtype=torch.float32, device=dev)
+        hist = torch.empty((B, S, D), dtype=torch.float32, device=dev)
+        tgt = torch.empty((B, D), dtype=torch.float32, device=dev)
+        t_stride = ti.stride(0) if B > 1 else 1
+        check(
+            L.rh_din_attn_input_fwd(hist_w.data_ptr(), hist_w.shape[0], tgt_w.data_ptr(), tgt_w.shape[0], D, hi.data_ptr(), ti.data_ptr(), int(hi.dtype == torch.int32), t_stride, B, S, att_in.data_ptr(),
+                                    hist.data_ptr(), tgt.data_ptr(), _lib.err_flag(dev).data_ptr(), stream_ptr()), "rh_din_attn_input_fwd")
+        ctx.hist_w, ctx.tgt_w, ctx.hi, ctx.ti = hist_w, tgt_w, hi, ti
+        ctx.pads = (-1 if hist_pad is None else int(hist_pad), -1 if tgt_pad is None else int(tgt_pad))
+        ctx.t_stride = t_stride
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(hist, tgt)
+        return att_in, hist, tgt
+
+    @staticmethod
+    def backward(ctx, d_att_in, d_hist, d_tgt):
+        L = _lib.lib()
+        hist, tgt = ctx.saved_tensors
+        B, S, D = hist.shape
+        dev = hist.device
+        if d_att_in is None:
+            d_att_in = torch.zeros((B * S, 4 * D), dtype=torch.float32, device=dev)
+        gh, hslot = _table.grad_target(ctx.hist_w)
+        gt, tslot = _table.grad_target(ctx.tgt_w)
+        check(
+            L.rh_din_attn_input_bwd(ptr(gh), ctx.hist_w.shape[0], ctx.pads[0], ptr(gt), ctx.tgt_w.shape[0], ctx.pads[1], D, ctx.hi.data_ptr(), ctx.ti.data_ptr(), int(ctx.hi.dtype == torch.int32), ctx.t_stride, B, S,
+                                    hist.data_ptr(), tgt.data_ptr(), d_att_in.contiguous().data_ptr(), ptr(d_hist.contiguous()) if d_hist is not None else None,
+                                    ptr(d_tgt.contiguous()) if d_tgt is not None else None, _lib.err_flag(dev).data_ptr(), stream_ptr()), "rh_din_attn_input_bwd")
+        if gh is not None:
+            _table.note_dirty(hslot, ctx.hi)
+        if gt is not None:
+            _table.note_dirty(tslot, ctx.ti)
+        return None, None, None, None, None, None
+
+
+def din_attention_input(hist_table, tgt_table, hist_ids, tgt_ids):
+    return _DinAttnInput.apply(hist_table.weight, tgt_table.weight, hist_ids, tgt_ids, hist_table.padding_idx, tgt_table.padding_idx)
+
+
+class _DinWeightedSum(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, att_w, hist, use_softmax):
+        L = _lib.lib()
+        B, S, D = hist.shape
+        w = att_w.contiguous()
+        h = hist.contiguous()
+        out = torch.empty((B, D), dtype=torch.float32, device=hist.device)
+        w_used = torch.empty((B, S), dtype=torch.float32, device=hist.device) if use_softmax else None
+        check(L.rh_din_weighted_sum_fwd(w.data_ptr(), h.data_ptr(), B, S, D, int(use_softmax), ptr(w_used), out.data_ptr(), stream_ptr()), "rh_din_weighted_sum_fwd")
+        ctx.use_softmax = use_softmax
+        ctx.save_for_backward(w_used if use_softmax else w, h)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        L = _lib.lib()
+        w_used, h = ctx.saved_tensors
+        B, S, D = h.shape
+        d_w = torch.empty((B, S), dtype=torch.float32, device=h.device)
+        d_h = torch.empty_like(h)
+        check(L.rh_din_weighted_sum_bwd(w_used.data_ptr(), h.data_ptr(), d_out.contiguous().data_ptr(), B, S, D, int(ctx.use_softmax), d_w.data_ptr(), d_h.data_ptr(), stream_ptr()), "rh_din_weighted_sum_bwd")
+        return d_w, d_h, None
+
+
+def din_weighted_sum(att_w, hist, use_softmax):
+    """``sum_l w[b,l] * hist[b,l,:]`` with optional softmax over l (din.py:86-92)."""
+    return _DinWeightedSum.apply(att_w, hist, bool(use_softmax))

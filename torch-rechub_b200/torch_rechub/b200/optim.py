@@ -1,0 +1,191 @@
+"""Row-wise (lazy) optimisers for the embedding tables + the hybrid optimiser CTRTrainer uses in fast mode.
+
+The reference hands ALL parameters, tables included, to a dense torch optimiser
+(``trainers/ctr_trainer.py:60-61``): Adam over 26 x (1M x 16) floats moves ~11.6 GB per step whatever the
+batch touched (SURVEY.md §7 hard part 2).  ``RowwiseOptimizer`` applies the same update rule to the rows the
+batch touched, in ONE launch for all tables (``rh_fields_rowwise_update``), consuming and re-zeroing the dense
+gradient buffer rows on the way (so no separate zero_grad work is left).
+
+Semantic deviation (deliberate, opt-in): untouched rows do not decay / do not move by momentum — the
+"lazy"/"sparse" Adam family (cf. ``torch.optim.SparseAdam``).  Gradients are identical to the reference's;
+parity tests assert logits and ``weight.grad``, and the exact dense optimiser remains the default.
+"""
+import ctypes
+
+import torch
+
+from . import _lib, table as _table
+from ._lib import RhField, check, stream_ptr
+
+_KINDS = {torch.optim.SGD: 0, torch.optim.Adam: 1, torch.optim.Adagrad: 2}
+
+
+def _ptrs(tensors):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+class RowwiseOptimizer(object):
+    """Updates table rows touched since the last step.  ``params``: table weight Parameters (2-D, fp32, CUDA)."""
+
+    def __init__(self, params, kind, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self.params = list(params)
+        self.kind = kind
+        self.lr = float(lr)
+        self.betas = (float(betas[0]), float(betas[1]))
+        self.eps = float(eps)
+        self.weight_decay = float(weight_decay)
+        self.state = {}  # id(param) -> dict(m, v, stamp)
+        dev = self.params[0].device
+        self._step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._lr_dev = torch.full((1,), self.lr, dtype=torch.float32, device=dev)
+        self._lr_host = self.lr
+
+    # -- state ---------------------------------------------------------------------------------------
+    def _state(self, p):
+        st = self.state.get(id(p))
+        if st is None:
+            st = {"stamp": torch.zeros(p.shape[0], dtype=torch.int32, device=p.device)}
+            if self.kind in (1, 2):
+                st["m"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+            if self.kind == 1:
+                st["v"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+            self.state[id(p)] = st
+        return st
+
+    def set_lr(self, lr):
+        lr = float(lr)
+        if lr != self._lr_host:
+            self._lr_host = lr
+            self._lr_dev.fill_(lr)  # a device scalar: captured graphs see the new value on replay
+
+    # -- step ----------------------------------------------------------------------------------------
+    def step(self):
+        L = _lib.lib()
+        st = stream_ptr()
+        check(L.rh_opt_advance(self._step_dev.data_ptr(), st), "rh_opt_advance")
+        # one (table, id-list) entry per lookup recorded by the backward kernels
+        entries = []
+        for p in self.params:
+            slot = _table._slots.get(p)
+            if slot is None or slot.buffer is None or not slot.pending:
+                continue
+            if slot.all_dirty or p.grad is None or p.grad.data_ptr() != slot.buffer.data_ptr():
+                raise RuntimeError("RowwiseOptimizer needs the engine's sparse-tracked gradient buffer; a dense gradient "
+                                   "(e.g. an L1/L2 penalty on embedding tables) reached this table — use the dense optimiser "
+                                   "(torch_rechub.b200.config.rowwise_optimizer = False) for that configuration")
+            for ids, _ in slot.pending:
+                entries.append((p, slot, ids))
+        # group by (dim, batch) so that one launch covers all tables of a batch
+        groups = {}
+        for p, slot, ids in entries:
+            if p.shape[1] % 4 == 0 and ids.dim() == 1:
+                groups.setdefault((p.shape[1], ids.shape[0]), []).append((p, slot, ids))
+            else:
+                self._single(L, p, slot, ids, st)
+        for (dim, batch), items in groups.items():
+            for i in range(0, len(items), _lib.RH_MAX_FIELDS):
+                chunk = items[i:i + _lib.RH_MAX_FIELDS]
+                arr = (RhField * len(chunk))()
+                tables, s1, s2, stamps = [], [], [], []
+                for j, (p, slot, ids) in enumerate(chunk):
+                    stt = self._state(p)
+                    a = arr[j]
+                    a.table = p.data_ptr()
+                    a.table_grad = slot.buffer.data_ptr()
+                    a.ids = ids.data_ptr()
+                    a.id_stride = ids.stride(0) if ids.shape[0] > 1 else 1
+                    a.ids_are_i32 = int(ids.dtype == torch.int32)
+                    a.vocab = p.shape[0]
+                    a.padding_idx = -1
+                    a.tile_col = -1
+                    a.fm_slot = -1
+                    tables.append(p)
+                    s1.append(stt.get("m"))
+                    s2.append(stt.get("v"))
+                    stamps.append(stt["stamp"])
+                check(
+                    L.rh_fields_rowwise_update(arr, len(chunk), dim, batch, _ptrs(tables), _ptrs(s1) if self.kind != 0 else None, _ptrs(s2) if self.kind == 1 else None, _ptrs(stamps), self.kind,
+                                               self._step_dev.data_ptr(), self._lr_dev.data_ptr(), self.betas[0], self.betas[1], self.eps, self.weight_decay, st), "rh_fields_rowwise_update")
+        for p in self.params:
+            _table.mark_clean(p)
+
+    def _single(self, L, p, slot, ids, st):
+        stt = self._state(p)
+        idc = ids.contiguous()
+        m, v = stt.get("m"), stt.get("v")
+        check(
+            L.rh_rowwise_update(p.data_ptr(), slot.buffer.data_ptr(), None if m is None else m.data_ptr(), None if v is None else v.data_ptr(), stt["stamp"].data_ptr(), p.shape[0], p.shape[1], idc.data_ptr(),
+                                int(idc.dtype == torch.int32), idc.numel(), self.kind, self._step_dev.data_ptr(), self._lr_dev.data_ptr(), self.betas[0], self.betas[1], self.eps, self.weight_decay, st),
+            "rh_rowwise_update")
+
+    def zero_grad(self, set_to_none=True):
+        for p in self.params:
+            if set_to_none:
+                p.grad = None
+            elif p.grad is not None:
+                _table.clean(p)
+
+
+class HybridOptimizer(object):
+    """Row-wise optimiser for the tables + the user's torch optimiser for everything else.
+
+    Quacks like a torch optimiser where CTRTrainer needs it (``step``, ``zero_grad``, ``param_groups``,
+    ``state_dict``); schedulers attach to ``scheduler_target`` (the dense torch optimiser) and the tables follow
+    its learning rate.
+    """
+
+    def __init__(self, rowwise, dense):
+        self.rowwise = rowwise
+        self.dense = dense
+        self.scheduler_target = dense
+
+    @classmethod
+    def build(cls, model, optimizer_fn, optimizer_params):
+        """None when the configuration has no row-wise counterpart (then the trainer stays on the dense optimiser)."""
+        from .table import FieldTable
+        kind = _KINDS.get(optimizer_fn)
+        if kind is None:
+            return None
+        allowed = {"lr", "weight_decay", "betas", "eps"} if kind == 1 else ({"lr", "weight_decay"} if kind == 0 else {"lr", "weight_decay", "eps"})
+        if not set(optimizer_params).issubset(allowed):
+            return None  # momentum / amsgrad / lr_decay ...: keep exact dense semantics
+        tables = []
+        for mod in model.modules():
+            if isinstance(mod, FieldTable) and mod.weight.is_cuda and mod.weight.requires_grad and mod.weight.dtype == torch.float32:
+                tables.append(mod.weight)
+        if not tables:
+            return None
+        tset = {id(p) for p in tables}
+        others = [p for p in model.parameters() if id(p) not in tset]
+        dense_kwargs = dict(optimizer_params)
+        if others:
+            if kind == 1:
+                dense_kwargs.setdefault("capturable", True)  # step counter on the device: CUDA-graph safe
+            dense = optimizer_fn(others, **dense_kwargs)
+        else:
+            return None
+        defaults = {0: dict(lr=1e-3), 1: dict(lr=1e-3, betas=(0.9, 0.999), eps=1e-8), 2: dict(lr=1e-2, eps=1e-10)}[kind]
+        kw = dict(defaults)
+        kw.update({k: v for k, v in optimizer_params.items()})
+        rw = RowwiseOptimizer(tables, kind, **kw)
+        return cls(rw, dense)
+
+    @property
+    def param_groups(self):
+        return self.dense.param_groups
+
+    def step(self):
+        lr = self.dense.param_groups[0]["lr"]
+        self.rowwise.set_lr(float(lr) if not torch.is_tensor(lr) else float(lr.item()))
+        self.rowwise.step()
+        self.dense.step()
+
+    def zero_grad(self, set_to_none=True):
+        self.rowwise.zero_grad(set_to_none)
+        self.dense.zero_grad(set_to_none)
+
+    def state_dict(self):
+        return self.dense.state_dict()

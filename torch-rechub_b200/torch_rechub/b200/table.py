@@ -1,0 +1,131 @@
+"""Embedding tables and their persistent gradient buffers.
+
+``FieldTable`` is the ``nn.Embedding`` every feature descriptor creates (reference
+``basic/initializers.py:16-21``).  It stays an ``nn.Embedding`` (state_dict key ``<name>.weight``,
+``isinstance`` checks of ``basic/loss_func.py:47``) and adds the engine behaviour for CUDA weights:
+
+* lookups run through ``rh_rows_gather`` / ``rh_fields_fwd``;
+* the backward pass scatter-adds row gradients into ONE persistent dense ``(vocab, dim)`` buffer that is
+  handed to autograd as ``weight.grad`` — the same dense gradient the reference gets from
+  ``aten::embedding_dense_backward``, without allocating and zero-filling
+  ``vocab x dim`` floats per lookup per step (66 % of the reference's CPU step).  The buffer is cleaned
+  SPARSELY: only the rows dirtied by the previous step are re-zeroed.
+"""
+import weakref
+
+import torch
+import torch.nn as nn
+
+from . import _lib, config
+
+
+class GradSlot(object):
+    """Engine-side gradient state of one table weight."""
+    __slots__ = ("buffer", "pending", "all_dirty", "__weakref__")
+
+    def __init__(self):
+        self.buffer = None  # (vocab, dim) fp32, zero outside the rows listed in `pending`
+        self.pending = []  # [(ids tensor (any shape, int64/int32), is_snapshot)] rows dirtied since last clean
+        self.all_dirty = False  # a foreign dense gradient was accumulated into the buffer
+
+
+_slots = weakref.WeakKeyDictionary()  # weight Parameter -> GradSlot
+
+
+def slot_of(weight):
+    s = _slots.get(weight)
+    if s is None:
+        s = GradSlot()
+        _slots[weight] = s
+        # a dense gradient arriving through autograd's AccumulateGrad (e.g. an L2 penalty on the table)
+        # may touch every row: remember to clean everything next time.
+        if hasattr(weight, "register_post_accumulate_grad_hook"):
+
+            def _mark(param, _slot_ref=weakref.ref(s)):
+                sl = _slot_ref()
+                if sl is not None and sl.buffer is not None and param.grad is not None and param.grad.data_ptr() == sl.buffer.data_ptr():
+                    sl.all_dirty = True
+
+            weight.register_post_accumulate_grad_hook(_mark)
+    return s
+
+
+def _ensure_buffer(weight, slot):
+    w = weight.detach()
+    if slot.buffer is None or slot.buffer.shape != w.shape or slot.buffer.device != w.device:
+        slot.buffer = torch.zeros_like(w, memory_format=torch.contiguous_format)
+        slot.pending = []
+        slot.all_dirty = False
+    return slot.buffer
+
+
+def clean(weight, slot=None):
+    """Re-zero the rows dirtied since the last clean (sparse ``zero_grad``)."""
+    slot = slot or slot_of(weight)
+    if slot.buffer is None:
+        return
+    if slot.all_dirty:
+        slot.buffer.zero_()
+    else:
+        L = _lib.lib()
+        vocab, dim = slot.buffer.shape
+        for ids, _ in slot.pending:
+            _lib.check(L.rh_rows_zero(slot.buffer.data_ptr(), vocab, dim, ids.data_ptr(), int(ids.dtype == torch.int32), ids.numel(), _lib.stream_ptr()), "rh_rows_zero")
+    slot.pending = []
+    slot.all_dirty = False
+
+
+def grad_target(weight):
+    """Dense gradient tensor the backward kernels must scatter into, attached as ``weight.grad``.
+
+    Returns ``(tensor, slot_or_None)``; ``slot`` is None when ``weight.grad`` is a foreign dense tensor
+    (then the kernels add straight into it and nothing is tracked).
+    """
+    if not weight.requires_grad:
+        return None, None
+    slot = slot_of(weight)
+    g = weight.grad
+    if g is not None and (slot.buffer is None or g.data_ptr() != slot.buffer.data_ptr()):
+        if g.is_sparse or g.shape != weight.shape or not g.is_contiguous():
+            raise RuntimeError("table weight has an incompatible .grad (sparse or strided); call zero_grad() first")
+        return g, None
+    buf = _ensure_buffer(weight, slot)
+    if g is None:
+        if slot.pending or slot.all_dirty:
+            clean(weight, slot)
+        weight.grad = buf
+    return buf, slot
+
+
+def note_dirty(slot, ids):
+    """Record that the rows ``ids`` of the slot's buffer now hold gradient."""
+    if slot is None:
+        return
+    if config.static_inputs:
+        slot.pending.append((ids.detach().clone(), True))
+    else:
+        slot.pending.append((ids.detach(), False))
+
+
+def mark_clean(weight):
+    """Called by the row-wise optimiser: it consumed AND re-zeroed every pending row."""
+    slot = _slots.get(weight)
+    if slot is not None:
+        slot.pending = []
+
+
+class FieldTable(nn.Embedding):
+    """``nn.Embedding`` whose CUDA lookups / gradients go through the sm_100a engine.
+
+    CPU weights behave exactly like ``nn.Embedding`` (dense ``weight.grad`` from autograd).
+    Options of ``nn.Embedding`` that the reference never sets (``max_norm``, ``scale_grad_by_freq``,
+    ``sparse``) are honoured on CPU and rejected on CUDA.
+    """
+
+    def forward(self, ids):
+        if not self.weight.is_cuda:
+            return super().forward(ids)
+        if self.max_norm is not None or self.scale_grad_by_freq or self.sparse:
+            raise NotImplementedError("FieldTable on CUDA supports the reference's nn.Embedding configuration only " "(max_norm=None, scale_grad_by_freq=False, sparse=False)")
+        from . import ops
+        return ops.table_lookup(self, ids)
