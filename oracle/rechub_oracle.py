@@ -1,0 +1,405 @@
+"""TEST INFRASTRUCTURE ONLY — numpy restatement (forward AND hand-derived backward) of the reference's CTR hot path.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline leg may import this file; the product
+(``torch-rechub_b200/``) never does.  Every function cites the reference lines it restates (paths relative to the
+reference root, torch-rechub v0.8.0 @ 5a73b2e).  No torch: plain numpy, float64 by default, so it is an
+independent check of both the CUDA kernels and the package's torch composite path.
+
+Parity status: the reference's own tests hold NO numeric golden vectors for this path (SURVEY.md §8c,
+``tests/test_e2e_ranking.py:106-107`` asserts only 0 <= AUC <= 1).  The oracle is therefore pinned against outputs of
+the live reference itself: ``tests/golden/*.npz`` (generated in the build container by ``tests/golden/make_golden.py``
+importing ``/root/reference``) hold state_dicts, inputs, logits and dense table gradients of the reference's
+DeepFM / DCN / DCNv2 / DIN, and ``tests/test_oracle.py`` checks this file against them to 1e-6.
+
+Conventions: ``sd`` is a model ``state_dict`` as numpy arrays with the reference's key layout;
+``x`` maps feature name -> numpy array; models return a dict with ``logit`` (pre-sigmoid), ``prob`` and — for the
+``*_forward_backward`` functions — ``grads`` keyed like ``sd`` for BCELoss(mean) against ``y``.
+Dropout is not modelled (p = 0 / eval only): the reference's RNG stream cannot be reproduced.
+"""
+import numpy as np
+
+BN_EPS = 1e-5  # torch.nn.BatchNorm1d default
+DICE_EPS = 1e-3  # basic/activation.py:10
+
+
+def _f(a, dtype):
+    return np.asarray(a, dtype=dtype)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# primitives
+# ---------------------------------------------------------------------------------------------------------
+def embedding_lookup(weight, ids):
+    """nn.Embedding forward: rows of ``weight`` (basic/layers.py:83,85).  Float ids truncate like ``.long()``."""
+    idx = np.asarray(ids).astype(np.int64)
+    if idx.size and (idx.min() < 0 or idx.max() >= weight.shape[0]):
+        raise IndexError("index out of range in self")
+    return weight[idx]
+
+
+def embedding_grad(weight_shape, ids, d_out, padding_idx=None, dtype=np.float64):
+    """aten::embedding_dense_backward: dense (V, D) gradient, duplicates accumulate, padding row stays 0."""
+    g = np.zeros(weight_shape, dtype=dtype)
+    idx = np.asarray(ids).astype(np.int64).reshape(-1)
+    d = d_out.reshape(-1, weight_shape[1])
+    if padding_idx is not None:
+        keep = idx != padding_idx
+        idx, d = idx[keep], d[keep]
+    np.add.at(g, idx, d)
+    return g
+
+
+def fm_forward(e, reduce_sum=True):
+    """FM.forward (basic/layers.py:313-319): 0.5 * sum_d[(sum_f e)^2 - sum_f e^2]; e: (B, F, D)."""
+    s = e.sum(axis=1)
+    ix = s * s - (e * e).sum(axis=1)
+    if reduce_sum:
+        ix = ix.sum(axis=1, keepdims=True)
+    return 0.5 * ix
+
+
+def fm_backward(e, d_y, reduce_sum=True):
+    """d/de of fm_forward: d_y * (sum_f e - e)."""
+    s = e.sum(axis=1, keepdims=True)
+    g = d_y[:, None, :] if not reduce_sum else d_y.reshape(-1, 1, 1)
+    return g * (s - e)
+
+
+def input_mask(ids, padding_idx):
+    """InputMask.forward (basic/layers.py:148-161): ids != padding_idx, or != -1 when the feature has none."""
+    return (np.asarray(ids).astype(np.int64) != (padding_idx if padding_idx is not None else -1))
+
+
+def seq_pool(weight, ids, pooling, padding_idx, dtype=np.float64):
+    """SumPooling / AveragePooling with the mask (basic/layers.py:209-251): mean = bmm(mask, x) / (sum(mask) + 1e-16)."""
+    e = embedding_lookup(weight, ids).astype(dtype)  # (B, L, D)
+    m = input_mask(ids, padding_idx).astype(dtype)  # (B, L)
+    pooled = (e * m[:, :, None]).sum(axis=1)
+    if pooling == "sum":
+        return pooled
+    if pooling == "mean":
+        return pooled / (m.sum(axis=1, keepdims=True) + 1e-16)
+    raise ValueError(pooling)
+
+
+def dice_forward(x, alpha, eps=DICE_EPS):
+    """Dice.forward (basic/activation.py:15-25): per-ROW mean / summed variance over the neuron axis."""
+    avg = x.mean(axis=1, keepdims=True)
+    var = ((x - avg)**2 + eps).sum(axis=1, keepdims=True)
+    ps = 1.0 / (1.0 + np.exp(-(x - avg) / np.sqrt(var)))
+    return ps * x + (1 - ps) * alpha * x, (avg, var, ps)
+
+
+def dice_backward(x, alpha, cache, d_out):
+    avg, var, ps = cache
+    n = x.shape[1]
+    s = np.sqrt(var)
+    c = 1.0 - alpha
+    a = d_out * x * c * ps * (1 - ps)
+    a1 = a.sum(axis=1, keepdims=True)
+    a2 = (a * (x - avg)).sum(axis=1, keepdims=True)
+    d_x = d_out * (alpha + c * ps) + a / s - a1 / (n * s) - (x - avg) * a2 / s**3
+    d_alpha = (d_out * x * (1 - ps)).sum()
+    return d_x, d_alpha
+
+
+def _act_forward(kind, z, param):
+    if kind == "relu":
+        return np.maximum(z, 0), None
+    if kind == "dice":
+        return dice_forward(z, param)
+    if kind == "prelu":
+        return np.where(z > 0, z, param * z), None
+    if kind == "sigmoid":
+        return 1 / (1 + np.exp(-z)), None
+    if kind == "leakyrelu":
+        return np.where(z > 0, z, 0.01 * z), None
+    raise ValueError(kind)
+
+
+def _act_backward(kind, z, param, cache, d_a):
+    if kind == "relu":
+        return d_a * (z > 0), None
+    if kind == "dice":
+        return dice_backward(z, param, cache, d_a)
+    if kind == "prelu":
+        return np.where(z > 0, d_a, param * d_a), (d_a * np.minimum(z, 0)).sum()
+    if kind == "sigmoid":
+        sg = 1 / (1 + np.exp(-z))
+        return d_a * sg * (1 - sg), None
+    if kind == "leakyrelu":
+        return np.where(z > 0, d_a, 0.01 * d_a), None
+    raise ValueError(kind)
+
+
+def mlp_forward(sd, prefix, x, n_hidden, activation="relu", train=True, output_layer=True, dtype=np.float64):
+    """MLP.forward (basic/layers.py:276-292): [Linear -> BatchNorm1d -> act -> Dropout(p=0)] * n_hidden (+ Linear(.,1)).
+    ``prefix`` like ``"mlp.mlp."``; module indices 4i (Linear), 4i+1 (BN), 4i+2 (activation params)."""
+    caches = []
+    h = x
+    for i in range(n_hidden):
+        W, b = _f(sd[prefix + "%d.weight" % (4 * i)], dtype), _f(sd[prefix + "%d.bias" % (4 * i)], dtype)
+        gamma, beta = _f(sd[prefix + "%d.weight" % (4 * i + 1)], dtype), _f(sd[prefix + "%d.bias" % (4 * i + 1)], dtype)
+        lin = h @ W.T + b
+        if train:
+            mu, var = lin.mean(axis=0), lin.var(axis=0)  # biased variance, as BatchNorm1d normalises with
+        else:
+            mu, var = _f(sd[prefix + "%d.running_mean" % (4 * i + 1)], dtype), _f(sd[prefix + "%d.running_var" % (4 * i + 1)], dtype)
+        rstd = 1.0 / np.sqrt(var + BN_EPS)
+        xhat = (lin - mu) * rstd
+        z = xhat * gamma + beta
+        pkey = prefix + ("%d.alpha" % (4 * i + 2) if activation == "dice" else "%d.weight" % (4 * i + 2))
+        param = _f(sd[pkey], dtype)[0] if activation in ("dice", "prelu") else None
+        a, acache = _act_forward(activation, z, param)
+        caches.append((h, W, lin, rstd, xhat, gamma, z, param, acache))
+        h = a
+    if output_layer:
+        W, b = _f(sd[prefix + "%d.weight" % (4 * n_hidden)], dtype), _f(sd[prefix + "%d.bias" % (4 * n_hidden)], dtype)
+        caches.append((h, W))
+        h = h @ W.T + b
+    return h, caches
+
+
+def mlp_backward(prefix, caches, d_out, n_hidden, activation="relu", train=True, output_layer=True):
+    grads = {}
+    g = d_out
+    if output_layer:
+        h, W = caches[-1]
+        grads[prefix + "%d.weight" % (4 * n_hidden)] = g.T @ h
+        grads[prefix + "%d.bias" % (4 * n_hidden)] = g.sum(axis=0)
+        g = g @ W
+    for i in reversed(range(n_hidden)):
+        h, W, lin, rstd, xhat, gamma, z, param, acache = caches[i]
+        d_z, d_param = _act_backward(activation, z, param, acache, g)
+        if d_param is not None:
+            grads[prefix + ("%d.alpha" % (4 * i + 2) if activation == "dice" else "%d.weight" % (4 * i + 2))] = np.array([d_param])
+        grads[prefix + "%d.weight" % (4 * i + 1)] = (d_z * xhat).sum(axis=0)
+        grads[prefix + "%d.bias" % (4 * i + 1)] = d_z.sum(axis=0)
+        if train:  # batch statistics take part in the gradient
+            n = lin.shape[0]
+            d_lin = gamma * rstd * (d_z - d_z.mean(axis=0) - xhat * (d_z * xhat).mean(axis=0))
+        else:
+            d_lin = d_z * gamma * rstd
+        grads[prefix + "%d.weight" % (4 * i)] = d_lin.T @ h
+        grads[prefix + "%d.bias" % (4 * i)] = d_lin.sum(axis=0)
+        g = d_lin @ W
+    return g, grads
+
+
+def bce_and_dlogit(logit, y):
+    """BCELoss(mean) on sigmoid(logit) (trainers/ctr_trainer.py:68,88) and dLoss/dlogit = (p - y) / B."""
+    p = 1 / (1 + np.exp(-logit))
+    eps = 1e-300
+    loss = -np.mean(y * np.log(np.maximum(p, eps)) + (1 - y) * np.log(np.maximum(1 - p, eps)))
+    return loss, (p - y) / logit.shape[0], p
+
+
+# ---------------------------------------------------------------------------------------------------------
+# EmbeddingLayer
+# ---------------------------------------------------------------------------------------------------------
+def embedding_tile(sd, x, sparse_names, dense_names, table_of=None, dtype=np.float64):
+    """EmbeddingLayer.forward(squeeze_dim=True) (basic/layers.py:77-127): sparse block first (list order), dense appended."""
+    table_of = table_of or {}
+    embs = [embedding_lookup(_f(sd["embedding.embed_dict.%s.weight" % table_of.get(n, n)], dtype), x[n]) for n in sparse_names]
+    parts = [np.concatenate(embs, axis=1)] if embs else []
+    dense = [_f(x[n], np.float32).astype(dtype).reshape(len(x[n]), -1) for n in dense_names]
+    if dense:
+        parts.append(np.concatenate(dense, axis=1))
+    return np.concatenate(parts, axis=1), embs
+
+
+# ---------------------------------------------------------------------------------------------------------
+# models
+# ---------------------------------------------------------------------------------------------------------
+def deepfm_forward_backward(sd, x, y, dense_names, deep_sparse_names, fm_names, n_hidden, activation="relu", train=True, backward=True, dtype=np.float64):
+    """DeepFM.forward (models/ranking/deepfm.py:34-43) + BCELoss backward.
+    deep tile = [deep sparse embeddings..., dense values]; FM/LR over ``fm_names`` embeddings."""
+    y = _f(y, dtype)
+    tile, deep_embs = embedding_tile(sd, x, deep_sparse_names, dense_names, dtype=dtype)
+    e_fm = np.stack([embedding_lookup(_f(sd["embedding.embed_dict.%s.weight" % n], dtype), x[n]) for n in fm_names], axis=1)  # (B, F, D)
+    B, F, D = e_fm.shape
+    lw, lb = _f(sd["linear.fc.weight"], dtype), _f(sd["linear.fc.bias"], dtype)
+    y_lin = e_fm.reshape(B, F * D) @ lw.T + lb
+    y_fm = fm_forward(e_fm)
+    y_deep, caches = mlp_forward(sd, "mlp.mlp.", tile, n_hidden, activation, train, True, dtype)
+    logit = (y_lin + y_fm + y_deep)[:, 0]
+    loss, d_logit, prob = bce_and_dlogit(logit, y)
+    out = {"logit": logit, "prob": prob, "loss": loss, "y_fm": y_fm[:, 0], "y_linear": y_lin[:, 0], "tile": tile}
+    if not backward:
+        return out
+    g = d_logit[:, None]
+    d_tile, grads = mlp_backward("mlp.mlp.", caches, g, n_hidden, activation, train, True)
+    grads["linear.fc.weight"] = g.T @ e_fm.reshape(B, F * D)
+    grads["linear.fc.bias"] = g.sum(axis=0)
+    d_e = fm_backward(e_fm, g) + (g @ lw).reshape(B, F, D)
+    for k, n in enumerate(fm_names):
+        key = "embedding.embed_dict.%s.weight" % n
+        grads[key] = grads.get(key, 0) + embedding_grad(sd[key].shape, x[n], d_e[:, k, :], dtype=dtype)
+    col = 0
+    for n, e in zip(deep_sparse_names, deep_embs):
+        key = "embedding.embed_dict.%s.weight" % n
+        w = e.shape[1]
+        grads[key] = grads.get(key, 0) + embedding_grad(sd[key].shape, x[n], d_tile[:, col:col + w], dtype=dtype)
+        col += w
+    out["grads"] = grads
+    return out
+
+
+def cross_forward(x0, ws, bs):
+    """CrossNetwork.forward (basic/layers.py:412-420): x <- x0 * (w_i . x) + b_i + x."""
+    xs, x = [x0], x0
+    for w, b in zip(ws, bs):
+        x = x0 * (x @ w.reshape(-1, 1)) + b + x
+        xs.append(x)
+    return x, xs
+
+
+def cross_backward(x0, ws, bs, xs, d_out):
+    g, g_x0 = d_out, np.zeros_like(x0)
+    d_ws, d_bs = [None] * len(ws), [None] * len(ws)
+    for l in reversed(range(len(ws))):
+        s = xs[l] @ ws[l].reshape(-1, 1)  # (B,1)
+        t = (g * x0).sum(axis=1, keepdims=True)  # dL/ds
+        d_bs[l] = g.sum(axis=0)
+        d_ws[l] = (t * xs[l]).sum(axis=0)
+        g_x0 = g_x0 + g * s
+        g = g + t * ws[l].reshape(1, -1)
+    return g + g_x0, d_ws, d_bs
+
+
+def dcn_forward_backward(sd, x, y, dense_names, sparse_names, n_cross, n_hidden, activation="relu", train=True, backward=True, dtype=np.float64):
+    """DCN.forward (models/ranking/dcn.py:32-38): cross(e) || MLP(e) -> cat -> LR -> sigmoid."""
+    y = _f(y, dtype)
+    tile, embs = embedding_tile(sd, x, sparse_names, dense_names, dtype=dtype)
+    ws = [_f(sd["cn.w.%d.weight" % i], dtype).reshape(-1) for i in range(n_cross)]
+    bs = [_f(sd["cn.b.%d" % i], dtype) for i in range(n_cross)]
+    cn_out, xs = cross_forward(tile, ws, bs)
+    mlp_out, caches = mlp_forward(sd, "mlp.mlp.", tile, n_hidden, activation, train, False, dtype)
+    stack = np.concatenate([cn_out, mlp_out], axis=1)
+    lw, lb = _f(sd["linear.fc.weight"], dtype), _f(sd["linear.fc.bias"], dtype)
+    logit = (stack @ lw.T + lb)[:, 0]
+    loss, d_logit, prob = bce_and_dlogit(logit, y)
+    out = {"logit": logit, "prob": prob, "loss": loss, "cross_out": cn_out, "tile": tile}
+    if not backward:
+        return out
+    g = d_logit[:, None]
+    grads = {"linear.fc.weight": g.T @ stack, "linear.fc.bias": g.sum(axis=0)}
+    d_stack = g @ lw
+    W = tile.shape[1]
+    d_tile_c, d_ws, d_bs = cross_backward(tile, ws, bs, xs, d_stack[:, :W])
+    d_tile_m, mg = mlp_backward("mlp.mlp.", caches, d_stack[:, W:], n_hidden, activation, train, False)
+    grads.update(mg)
+    for i in range(n_cross):
+        grads["cn.w.%d.weight" % i] = d_ws[i].reshape(1, -1)
+        grads["cn.b.%d" % i] = d_bs[i]
+    d_tile = d_tile_c + d_tile_m
+    col = 0
+    for n, e in zip(sparse_names, embs):
+        key = "embedding.embed_dict.%s.weight" % n
+        w = e.shape[1]
+        grads[key] = grads.get(key, 0) + embedding_grad(sd[key].shape, x[n], d_tile[:, col:col + w], dtype=dtype)
+        col += w
+    out["grads"] = grads
+    return out
+
+
+def crossnetmix_forward(sd, prefix, x, n_layers, n_experts, dtype=np.float64):
+    """CrossNetMix.forward (basic/layers.py:470-506)."""
+    x0 = x[:, :, None]
+    xl = x0
+    gates = [_f(sd[prefix + "gating.%d.weight" % e], dtype) for e in range(n_experts)]
+    for i in range(n_layers):
+        U, V, C = (_f(sd[prefix + "%s.%d" % (k, i)], dtype) for k in ("u_list", "v_list", "c_list"))
+        bias = _f(sd[prefix + "bias.%d" % i], dtype)
+        outs, scores = [], []
+        for e in range(n_experts):
+            scores.append(xl[:, :, 0] @ gates[e].T)  # (B,1)
+            v = np.tanh(V[e].T @ xl)  # (B, r, 1)
+            v = np.tanh(C[e] @ v)
+            uv = U[e] @ v  # (B, W, 1)
+            outs.append((x0 * (uv + bias))[:, :, 0])
+        outs = np.stack(outs, axis=2)  # (B, W, E)
+        sc = np.stack(scores, axis=1)  # (B, E, 1)
+        sc = np.exp(sc - sc.max(axis=1, keepdims=True))
+        sc = sc / sc.sum(axis=1, keepdims=True)
+        xl = outs @ sc + xl
+    return xl[:, :, 0]
+
+
+def dcnv2_forward(sd, x, dense_names, sparse_names, n_cross, n_hidden, n_experts=4, activation="relu", train=True, dtype=np.float64):
+    """DCNv2.forward, default ``parallel`` structure with CrossNetMix (models/ranking/dcn_v2.py:47-59)."""
+    tile, _ = embedding_tile(sd, x, sparse_names, dense_names, dtype=dtype)
+    cross_out = crossnetmix_forward(sd, "crossnet.", tile, n_cross, n_experts, dtype)
+    dnn_out, _ = mlp_forward(sd, "parallel_dnn.mlp.", tile, n_hidden, activation, train, False, dtype)
+    final = np.concatenate([cross_out, dnn_out], axis=1)
+    logit = (final @ _f(sd["linear.fc.weight"], dtype).T + _f(sd["linear.fc.bias"], dtype))[:, 0]
+    return {"logit": logit, "prob": 1 / (1 + np.exp(-logit)), "tile": tile}
+
+
+def din_forward_backward(sd, x, y, feature_names, history_names, target_names, shared_with, n_att_hidden, n_hidden, use_softmax=False, train=True, backward=True, dtype=np.float64):
+    """DIN.forward + ActivationUnit.forward (models/ranking/din.py:38-55, 77-93), Dice everywhere, no padding mask.
+    ``shared_with[h]`` names the table a history feature looks up."""
+    y = _f(y, dtype)
+    tbl = lambda n: _f(sd["embedding.embed_dict.%s.weight" % shared_with.get(n, n)], dtype)
+    e_feat = [embedding_lookup(tbl(n), x[n]) for n in feature_names]
+    e_hist = [embedding_lookup(tbl(n), x[n]) for n in history_names]  # (B, L, D) each
+    e_tgt = [embedding_lookup(tbl(n), x[n]) for n in target_names]
+    pooled, att_caches = [], []
+    for i, h in enumerate(e_hist):
+        B, L, D = h.shape
+        t = np.broadcast_to(e_tgt[i][:, None, :], (B, L, D))
+        att_in = np.concatenate([t, h, t - h, t * h], axis=-1).reshape(B * L, 4 * D)
+        w, caches = mlp_forward(sd, "attention_layers.%d.attention.mlp." % i, att_in, n_att_hidden, "dice", train, True, dtype)
+        w = w.reshape(B, L)
+        w_used = w
+        if use_softmax:
+            ex = np.exp(w - w.max(axis=1, keepdims=True))
+            w_used = ex / ex.sum(axis=1, keepdims=True)
+        pooled.append((w_used[:, :, None] * h).sum(axis=1))
+        att_caches.append((caches, w_used, t, h))
+    mlp_in = np.concatenate(pooled + e_tgt + e_feat, axis=1)
+    out_, caches = mlp_forward(sd, "mlp.mlp.", mlp_in, n_hidden, "dice", train, True, dtype)
+    logit = out_[:, 0]
+    loss, d_logit, prob = bce_and_dlogit(logit, y)
+    out = {"logit": logit, "prob": prob, "loss": loss, "mlp_in": mlp_in}
+    if not backward:
+        return out
+    d_in, grads = mlp_backward("mlp.mlp.", caches, d_logit[:, None], n_hidden, "dice", train, True)
+    D = e_tgt[0].shape[1]
+    col = 0
+    d_pooled = []
+    for _ in pooled:
+        d_pooled.append(d_in[:, col:col + D])
+        col += D
+    d_tgt = []
+    for _ in e_tgt:
+        d_tgt.append(d_in[:, col:col + D].copy())
+        col += D
+    d_feat = []
+    for e in e_feat:
+        d_feat.append(d_in[:, col:col + e.shape[1]])
+        col += e.shape[1]
+
+    def add(name, ids, d):
+        key = "embedding.embed_dict.%s.weight" % shared_with.get(name, name)
+        grads[key] = grads.get(key, 0) + embedding_grad(sd[key].shape, ids, d, dtype=dtype)
+
+    for i, (caches_i, w_used, t, h) in enumerate(att_caches):
+        B, L, Dh = h.shape
+        d_w = (d_pooled[i][:, None, :] * h).sum(axis=2)  # (B, L)
+        d_h = w_used[:, :, None] * d_pooled[i][:, None, :]
+        if use_softmax:
+            d_w = w_used * (d_w - (w_used * d_w).sum(axis=1, keepdims=True))
+        d_att_in, g_i = mlp_backward("attention_layers.%d.attention.mlp." % i, caches_i, d_w.reshape(B * L, 1), n_att_hidden, "dice", train, True)
+        grads.update(g_i)
+        d_att_in = d_att_in.reshape(B, L, 4, Dh)
+        d0, d1, d2, d3 = (d_att_in[:, :, k, :] for k in range(4))
+        d_h = d_h + d1 - d2 + d3 * t
+        d_tgt[i] += (d0 + d2 + d3 * h).sum(axis=1)
+        add(history_names[i], x[history_names[i]], d_h)
+    for n, d in zip(target_names, d_tgt):
+        add(n, x[n], d)
+    for n, d in zip(feature_names, d_feat):
+        add(n, x[n], d)
+    out["grads"] = grads
+    return out

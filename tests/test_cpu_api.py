@@ -1,0 +1,156 @@
+"""CPU-side checks: the package's CPU route against the golden vectors and the live reference (bitwise), the
+state_dict/API surface, the C-ABI library's exported symbols, and the reference's own tests run against this package."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import _golden
+import _live_reference as live
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "torch-rechub_b200")
+
+
+@pytest.mark.parametrize("name", _golden.NAMES)
+def test_package_cpu_route_matches_reference_golden(name):
+    import torch_rechub.basic.features as F
+    import torch_rechub.models.ranking as M
+    rec = _golden.load(name)
+    model = _golden.build_model(name, rec, F, M)
+    assert list(model.state_dict().keys()) == list(rec["sd"].keys())  # checkpoint layout = the reference's
+    x, y = _golden.torch_inputs(rec)
+    model.eval()  # first: the golden state_dict holds the running statistics the reference's eval pass used
+    with torch.no_grad():
+        assert np.abs(model(x).numpy() - rec["eval_prob"]).max() <= 1e-7
+    model.train()
+    p = model(x)
+    assert np.abs(p.detach().numpy() - rec["train_prob"]).max() <= 1e-7
+    torch.nn.BCELoss()(p, y).backward()
+    for k, prm in model.named_parameters():
+        ref = rec["grad"][k]
+        scale = max(np.abs(ref).max(), 1e-3)
+        if k.endswith(".bias") and k[:-4] + "weight" in rec["grad"]:
+            scale = max(scale, np.abs(rec["grad"][k[:-4] + "weight"]).max())
+        assert np.abs(prm.grad.numpy() - ref).max() <= 1e-5 * scale, k
+
+
+@pytest.mark.skipif(not live.live_reference_available(), reason="live reference only exists in the build container")
+def test_same_seed_same_weights_same_outputs_as_live_reference():
+    """Initialisers consume the RNG like the reference (initializers.py:16-21): same seed -> identical tables, and the
+    CPU route is the same op sequence -> bitwise identical probabilities and (DeepFM/DCN/WideDeep) gradients."""
+    import torch_rechub.basic.features as F
+    import torch_rechub.models.ranking as M
+    RF, RM = live.ref_module("basic.features"), live.ref_module("models.ranking")
+
+    def build(mf, mm):
+        torch.manual_seed(7)
+        dense = [mf.DenseFeature("I%d" % i) for i in range(3)]
+        sparse = [mf.SparseFeature("C%d" % i, vocab_size=50 + i, embed_dim=8) for i in range(4)] + [mf.SparseFeature("P", vocab_size=9, embed_dim=8, padding_idx=0)]
+        return [
+            mm.DeepFM(dense + sparse, sparse, {"dims": [16, 8], "dropout": 0.0, "activation": "relu"}),
+            mm.DCN(dense + sparse, n_cross_layers=3, mlp_params={"dims": [16, 8]}),
+            mm.WideDeep(dense, sparse, {"dims": [8]}),
+        ]
+
+    g = torch.Generator().manual_seed(0)
+    x = {"I%d" % i: torch.rand(32, generator=g) for i in range(3)}
+    x.update({"C%d" % i: torch.randint(0, 50, (32,), generator=g) for i in range(4)})
+    x["P"] = torch.randint(0, 9, (32,), generator=g)
+    for a, b in zip(build(F, M), build(RF, RM)):
+        sa, sb = a.state_dict(), b.state_dict()
+        assert list(sa) == list(sb)
+        assert all(torch.equal(sa[k], sb[k]) for k in sa)
+    # gradients: fresh models (the feature objects above share tables across the three models of one build)
+    for idx in range(3):
+        a, b = build(F, M)[idx], build(RF, RM)[idx]
+        ya, yb = a(x), b(x)
+        assert torch.equal(ya, yb)
+        ya.sum().backward()
+        yb.sum().backward()
+        for (n, p), q in zip(a.named_parameters(), b.parameters()):
+            assert torch.equal(p.grad, q.grad), n
+    # feature objects reused across models share ONE table
+    from torch_rechub.basic.layers import EmbeddingLayer
+    f = F.SparseFeature("z", 10, 4)
+    assert EmbeddingLayer([f]).embed_dict["z"] is EmbeddingLayer([f]).embed_dict["z"] is f.embed
+
+
+def test_layer_contracts():
+    from torch_rechub.basic.features import DenseFeature, SequenceFeature, SparseFeature
+    from torch_rechub.basic.layers import EmbeddingLayer, InputMask
+    from torch_rechub.utils.data import get_auto_embedding_dim
+    assert SparseFeature("a", 10000).embed_dim == get_auto_embedding_dim(10000) == 60
+    assert repr(SparseFeature("a", 10, 4)) == "<SparseFeature a with Embedding shape (10, 4)>"
+    assert repr(SequenceFeature("s", 10, 4)) == "<SequenceFeature s with Embedding shape (10, 4)>"
+    assert repr(DenseFeature("d")) == "<DenseFeature d>"
+    feats = [SparseFeature("a", 10, 4), DenseFeature("d"), SparseFeature("b", 10, 4, shared_with="a")]
+    layer = EmbeddingLayer(feats)
+    assert list(layer.embed_dict.keys()) == ["a"] and layer.n_dense == 1
+    assert isinstance(layer.embed_dict["a"], torch.nn.Embedding)
+    x = {"a": torch.tensor([1, 2]), "b": torch.tensor([2.9, 1.0]), "d": torch.tensor([0.5, 0.25], dtype=torch.float64)}
+    out = layer(x, feats, squeeze_dim=True)
+    assert out.shape == (2, 9) and out.dtype == torch.float32
+    w = layer.embed_dict["a"].weight
+    assert torch.equal(out[0], torch.cat([w[1], w[2], torch.tensor([0.5])]))  # sparse first, dense appended; float ids truncate
+    assert layer(x, feats).shape == (2, 2, 4)
+    with pytest.raises(ValueError):
+        layer(x, [feats[1]], squeeze_dim=False)
+    with pytest.raises(ValueError):
+        InputMask()(x, [feats[1]])
+    with pytest.raises(IndexError):
+        layer({"a": torch.tensor([10])}, [feats[0]])
+    bad = SequenceFeature("s", 5, 4, pooling="max")
+    with pytest.raises(ValueError):
+        EmbeddingLayer([bad])({"s": torch.zeros(1, 2).long()}, [bad])
+
+
+def test_out_of_scope_models_are_importable_but_refuse_to_build():
+    from torch_rechub.models.ranking import EDCN, AutoInt, DeepFFM, FatDeepFFM, FiBiNet  # run_criteo.py:10 imports these
+    for cls in (EDCN, AutoInt, DeepFFM, FatDeepFFM, FiBiNet):
+        with pytest.raises(NotImplementedError):
+            cls()
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "rechub_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(rh_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 25
+    lib_path = os.path.join(PKG, "lib", "librechub_b200.so")
+    assert os.path.exists(lib_path), "build the engine first (python -c 'import __graft_entry__ as g; g.build()')"
+    from torch_rechub.b200 import _lib
+    handle = _lib.lib()  # dlopen + argtypes for every prototype; no compute
+    for name in declared:
+        assert hasattr(handle, name), "librechub_b200.so does not export %s" % name
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    assert handle.rh_abi_version() == 1
+
+
+def test_cuda_route_has_no_silent_fallback(monkeypatch):
+    """A missing engine library must raise, not fall back to eager ops."""
+    from torch_rechub.b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/librechub_b200.so")
+    with pytest.raises(_lib.EngineMissing):
+        _lib.lib()
+
+
+@pytest.mark.skipif(not live.live_reference_available(), reason="the reference's test files only exist in the build container")
+def test_reference_own_tests_pass_against_this_package(tmp_path):
+    """The reference's own test files, byte-for-byte, run against THIS package.  They are copied to a scratch directory
+    first because they put their own parent directory (the reference checkout) at the front of sys.path."""
+    import shutil
+    tdir = tmp_path / "suite" / "tests"
+    tdir.mkdir(parents=True)
+    for name in ("test_regularization.py", "test_e2e_ranking.py"):
+        shutil.copy(os.path.join(live.REFERENCE_ROOT, "tests", name), tdir / name)
+    env = dict(os.environ, PYTHONPATH=PKG)
+    cmd = [sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", str(tdir), "-k", "regularization or WideDeep or (DCN and not EDCN)"]
+    res = subprocess.run(cmd, env=env, cwd=str(tdir), capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
+    assert "passed" in res.stdout

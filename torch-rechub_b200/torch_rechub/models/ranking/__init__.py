@@ -1,4 +1,5 @@
-"""Ranking models on the B200 hot path: DeepFM, DCN, DCNv2, DIN.
+"""Ranking models on the B200 hot path: DeepFM, DCN, DCNv2, DIN, plus WideDeep
+(the plainest EmbeddingLayer consumer; the reference's ranking e2e test drives it).
 
 The reference exports more ranking models (``models/ranking/__init__.py:1-14``).  They are outside this
 engine's scope: their names stay importable so the reference's example scripts
@@ -11,6 +12,7 @@ from .dcn import DCN
 from .dcn_v2 import DCNv2
 from .deepfm import DeepFM
 from .din import DIN
+from .widedeep import WideDeep
 
 
 def _out_of_scope(name):

@@ -1,0 +1,31 @@
+"""Wide & Deep (mirror of reference ``torch_rechub/models/ranking/widedeep.py``) — a two-call user of the fused
+``EmbeddingLayer`` front end, kept because the reference's own ranking e2e test drives it (tests/test_e2e_ranking.py:53)."""
+import torch
+
+from ...basic.layers import LR, MLP, EmbeddingLayer
+
+
+class WideDeep(torch.nn.Module):
+    """``sigmoid(LR(e_wide) + MLP(e_deep))``.
+
+    Args:
+        wide_features (list): features of the linear (wide) part.
+        deep_features (list): features of the MLP (deep) part.
+        mlp_params (dict): ``{"dims": list, "activation": str, "dropout": float, "output_layer": bool}``.
+    """
+
+    def __init__(self, wide_features, deep_features, mlp_params):
+        super(WideDeep, self).__init__()
+        self.wide_features = wide_features
+        self.deep_features = deep_features
+        self.wide_dims = sum([fea.embed_dim for fea in wide_features])
+        self.deep_dims = sum([fea.embed_dim for fea in deep_features])
+        self.linear = LR(self.wide_dims)
+        self.embedding = EmbeddingLayer(wide_features + deep_features)
+        self.mlp = MLP(self.deep_dims, **mlp_params)
+
+    def forward(self, x):
+        input_wide = self.embedding(x, self.wide_features, squeeze_dim=True)
+        input_deep = self.embedding(x, self.deep_features, squeeze_dim=True)
+        y = self.linear(input_wide) + self.mlp(input_deep)
+        return torch.sigmoid(y.squeeze(1))
