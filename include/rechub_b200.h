@@ -163,14 +163,17 @@ int rh_rows_zero(float* table_grad, int vocab, int dim,
  * state1/state2: device (vocab, dim) fp32 moment buffers (Adam: m, v; Adagrad: state1 = sum).
  * stamp: device int32[vocab], zero-initialised.  step_dev / lr_dev: DEVICE scalars (int32 / fp32) so
  * that a captured CUDA graph sees the step counter and a scheduler-updated learning rate on replay;
- * rh_opt_advance increments *step_dev (call it once per optimiser step, before the updates).
+ * rh_opt_advance increments *step_dev and refreshes the Adam bias corrections (call it once per optimiser step,
+ * before the updates).
  * ------------------------------------------------------------------------------------------- */
 int rh_rowwise_update(float* table, float* table_grad, float* state1, float* state2,
                       int32_t* stamp, int vocab, int dim,
                       const void* ids, int ids_are_i32, int64_t n,
-                      int kind, const int32_t* step_dev, const float* lr_dev,
+                      int kind, const int32_t* step_dev, const float* lr_dev, const float* bias_corr_dev,
                       float beta1, float beta2, float eps, float weight_decay, void* stream);
-int rh_opt_advance(int32_t* step_dev, void* stream);
+/* ++*step_dev, and (Adam) bias_corr_dev[0] = 1 - beta1^step, bias_corr_dev[1] = sqrt(1 - beta2^step) in fp64, once
+ * per optimiser step instead of once per thread.  bias_corr_dev: device float[2], may be NULL for SGD/Adagrad. */
+int rh_opt_advance(int32_t* step_dev, float* bias_corr_dev, float beta1, float beta2, void* stream);
 
 /* The same update for ALL tables of one batch in a single launch (grid.y = field): fields[i] gives
  * table_grad / ids / id_stride / vocab of table i; tables / state1 / state2 / stamp are host arrays
@@ -179,7 +182,7 @@ int rh_opt_advance(int32_t* step_dev, void* stream);
 int rh_fields_rowwise_update(const rh_field* fields, int n_fields, int dim, int batch,
                              float* const* tables, float* const* state1, float* const* state2,
                              int32_t* const* stamp, int kind,
-                             const int32_t* step_dev, const float* lr_dev,
+                             const int32_t* step_dev, const float* lr_dev, const float* bias_corr_dev,
                              float beta1, float beta2, float eps, float weight_decay, void* stream);
 
 /* table_grad[ids] = 0 for all tables of one batch in a single launch (sparse zero_grad). */
@@ -217,24 +220,28 @@ int rh_cross_bwd(const float* x0, int64_t x_ld, int batch, int width, int n_laye
  * (basic/layers.py:276-292: Linear -> BatchNorm1d -> activation -> Dropout).
  * ------------------------------------------------------------------------------------------- */
 
-/* Column statistics of h (rows, cols): mean[c], biased var[c]  (BatchNorm1d training forward).
- * `scratch`: device (2*cols + 1) fp32, zeroed ONCE by the caller; the kernel leaves it zeroed.
- * When running_mean/var are non-NULL they are updated with `momentum` (unbiased variance, as torch
- * does); num_batches_tracked (device int64, may be NULL) is incremented. */
+/* Column statistics of h (rows, cols) for BatchNorm1d's training forward.
+ *   stats    device (2*cols + 1) fp32: [0,cols) mean, [cols,2*cols) biased variance, [2*cols] the bit pattern of this
+ *            forward's step counter (num_batches_tracked after the increment) = the dropout stream id of the layer
+ *   scratch  device (2*cols + 1) fp32, zeroed ONCE by the caller; the kernel leaves it zeroed
+ * running_mean/var (may be NULL) are updated with `momentum` (unbiased variance, as torch does);
+ * num_batches_tracked (device int64, may be NULL) is incremented. */
 int rh_colstats(const float* h, int64_t h_ld, int64_t rows, int cols,
-                float* mean, float* var, float* scratch,
+                float* stats, float* scratch,
                 float* running_mean, float* running_var, int64_t* num_batches_tracked,
                 float momentum, void* stream);
 
 /* y = dropout(act(gamma * (h - mean) / sqrt(var + eps) + beta)).   mean/var NULL: no normalisation.
  *   act: 0 identity, 1 ReLU, 2 Dice (basic/activation.py:15-25: per-ROW statistics over `cols`;
  *        act_param = device alpha (1)), 3 PReLU (act_param = single slope), 4 sigmoid, 5 LeakyReLU(0.01)
- *   keep_mask: device (rows, cols) uint8 or NULL (no dropout); kept values are scaled by 1/(1-p_drop) */
+ *   dropout (p_drop > 0): the keep decision is a pure function of (dropout_seed, *dropout_counter, element index),
+ *        regenerated in the backward pass — no mask is stored.  dropout_counter: device fp32 holding an int bit pattern
+ *        (stats[2*cols] of rh_colstats) or NULL.  Kept values are scaled by 1/(1-p_drop). */
 int rh_bn_act_fwd(const float* h, int64_t h_ld, int64_t rows, int cols,
                   const float* mean, const float* var, float bn_eps,
                   const float* gamma, const float* beta,
                   int act, const float* act_param, float dice_eps,
-                  const uint8_t* keep_mask, float p_drop,
+                  float p_drop, uint32_t dropout_seed, const float* dropout_counter,
                   float* y, int64_t y_ld, void* stream);
 
 /* Backward of rh_bn_act_fwd through dropout, activation and batch norm; the pre-activation is
@@ -247,10 +254,18 @@ int rh_bn_act_bwd(const float* h, int64_t h_ld, int64_t rows, int cols,
                   const float* mean, const float* var, float bn_eps,
                   const float* gamma, const float* beta,
                   int act, const float* act_param, float dice_eps,
-                  const uint8_t* keep_mask, float p_drop,
+                  float p_drop, uint32_t dropout_seed, const float* dropout_counter,
                   const float* d_y, int64_t d_y_ld, int training,
                   float* d_h, int64_t d_h_ld,
                   float* d_gamma, float* d_beta, float* d_act_param, void* stream);
+
+/* One launch of SGD / Adam / Adagrad (kinds as rh_rowwise_update) over n_tensors small dense tensors — the tower's
+ * weights (the dense half of optimizer.step(), trainers/ctr_trainer.py:99).  params/grads/state1/state2: host arrays of
+ * device pointers; numel: host array.  lr_dev / bias_corr_dev: the device scalars of rh_opt_advance. */
+int rh_dense_update(int n_tensors, float* const* params, const float* const* grads,
+                    float* const* state1, float* const* state2, const int64_t* numel,
+                    int kind, const float* lr_dev, const float* bias_corr_dev,
+                    float beta1, float beta2, float eps, float weight_decay, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * DIN target attention (models/ranking/din.py:77-93, ActivationUnit.forward).

@@ -1,0 +1,98 @@
+"""world_size-2 gloo test of the field-sharded engine (host-side logic of b200.dist): a 2-rank sharded DeepFM / DCN
+step must reproduce the DataParallel semantics of the reference — per-rank BatchNorm statistics, global-batch-mean loss."""
+import copy
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "torch-rechub_b200")
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _make(kind):
+    from torch_rechub.basic.features import DenseFeature, SparseFeature
+    from torch_rechub.basic.initializers import RandomNormal
+    from torch_rechub.models.ranking import DCN, DeepFM
+    torch.manual_seed(5)
+    init = RandomNormal(0, 0.05)
+    dense = [DenseFeature("I%d" % i) for i in range(2)]
+    sparse = [SparseFeature("C%d" % i, 31 + i, 8, initializer=init) for i in range(5)]
+    if kind == "deepfm":
+        return DeepFM(dense + sparse, sparse, {"dims": [16, 8], "dropout": 0.0, "activation": "relu"})
+    return DCN(dense + sparse, n_cross_layers=2, mlp_params={"dims": [16, 8]})
+
+
+def _batch(rank, b=24):
+    g = torch.Generator().manual_seed(100 + rank)
+    x = {"I%d" % i: torch.rand(b, generator=g) for i in range(2)}
+    x.update({"C%d" % i: torch.randint(0, 31, (b,), generator=g) for i in range(5)})
+    return x, torch.randint(0, 2, (b,), generator=g).float()
+
+
+def _worker(rank, world, port, kind, out):
+    if PKG not in sys.path:
+        sys.path.insert(0, PKG)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), RECHUB_B200_SHARD_ON_CPU="1")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from torch_rechub.trainers import CTRTrainer
+    model = _make(kind)
+    full_sd = copy.deepcopy(model.state_dict())
+    trainer = CTRTrainer(model, optimizer_fn=torch.optim.SGD, optimizer_params={"lr": 0.1}, device="cpu")
+    assert trainer._dist is not None and trainer._dist.world == world
+    n_owned = sum(1 for f in trainer._dist.fronts for n, o in f.owner.items() if o == rank)
+    assert n_owned in (2, 3) and len(trainer._dist.foreign) == 5 - n_owned
+    x, y = _batch(rank)
+    model.train()
+    loss = trainer._train_step(x, y)
+    sd = trainer._dist.full_state_dict()
+    out[rank] = {"loss": float(loss), "sd": {k: v.clone() for k, v in sd.items()}, "init": full_sd}
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind", ["deepfm", "dcn"])
+def test_two_rank_sharded_step_matches_dataparallel_semantics(kind):
+    world = 2
+    out = mp.get_context("spawn").Manager().dict()
+    mp.spawn(_worker, args=(world, _free_port(), kind, out), nprocs=world, join=True)
+    # single-process emulation: per-rank sub-batch forward (own BatchNorm statistics), loss = mean over the global batch
+    ref = _make(kind)
+    ref.load_state_dict(out[0]["init"])
+    ref.train()
+    opt = torch.optim.SGD(ref.parameters(), lr=0.1)
+    opt.zero_grad()
+    total = 0.0
+    bn_mods = [m for m in ref.modules() if isinstance(m, torch.nn.BatchNorm1d)]
+    saved_stats = [(m.running_mean.clone(), m.running_var.clone()) for m in bn_mods]
+    for r in range(world):
+        for m, (rm, rv) in zip(bn_mods, saved_stats):  # each replica starts from the same running statistics
+            m.running_mean.copy_(rm)
+            m.running_var.copy_(rv)
+        x, y = _batch(r)
+        loss = torch.nn.BCELoss()(ref(x), y) / world
+        loss.backward()
+        total += float(loss)
+    opt.step()
+    assert abs(out[0]["loss"] - total) < 1e-6 and abs(out[1]["loss"] - total) < 1e-6
+    want = ref.state_dict()
+    for k, v in out[0]["sd"].items():
+        if "running_" in k or "num_batches" in k:
+            continue  # buffers are per replica (DataParallel keeps replica 0's)
+        assert torch.allclose(v, want[k], rtol=1e-5, atol=1e-6), k
+    for k, v in out[1]["sd"].items():  # both ranks hold identical replicated weights and identical gathered tables
+        if "running_" in k or "num_batches" in k:
+            continue
+        assert torch.equal(v, out[0]["sd"][k]), k

@@ -244,7 +244,7 @@ def test_out_of_range_id_raises_index_error():
     layer = EmbeddingLayer(feats).to(DEV)
     _lib.check_errors()
     out = layer({"a": torch.tensor([1, 10, 3], device=DEV)}, feats)
-    assert float(out[1].abs().max()) == 0.0  # the bad row reads as zeros, memory untouched
+    assert float(out[1].detach().abs().max()) == 0.0  # the bad row reads as zeros, memory untouched
     with pytest.raises(IndexError):
         _lib.check_errors()
     layer({"a": torch.tensor([-1], device=DEV)}, feats)
@@ -332,4 +332,4 @@ def test_double_lookup_accumulates_and_sparse_zero():
         if step == 0:
             first = g.clone()
         else:
-            assert torch.allclose(g, first, rtol=1e-5, atol=1e-8)
+            assert torch.allclose(g, first, rtol=1e-5, atol=1e-6)  # duplicates accumulate through atomics: order varies

@@ -266,17 +266,14 @@ __global__ void __launch_bounds__(256) rowwise_update_kernel(float* __restrict__
                                                              float* __restrict__ st2, int32_t* __restrict__ stamp, int vocab, int dim,
                                                              const void* __restrict__ ids, bool is_i32, int64_t n, OptArgs a,
                                                              const int32_t* __restrict__ step_dev, const float* __restrict__ lr_dev,
-                                                             bool vec, int G) {
+                                                             const float* __restrict__ bc_dev, bool vec, int G) {
   // G (power of two <= 32) consecutive threads own one entry of `ids`.  The group's lane 0 claims
   // the row through stamp[id] (first claimant of this step wins: duplicates of an id are skipped)
   // and broadcasts the verdict; the owner group then updates the row's `lanes` 16-byte (or scalar) slots.
   const int step = *step_dev;
   const float lr = *lr_dev;
-  float bc1 = 1.f, bc2s = 1.f;
-  if (a.kind == 1) {
-    bc1 = (float)(1.0 - pow((double)a.beta1, (double)step));
-    bc2s = (float)sqrt(1.0 - pow((double)a.beta2, (double)step));
-  }
+  // Adam bias corrections 1 - beta1^t and sqrt(1 - beta2^t): computed ONCE per step by rh_opt_advance (fp64)
+  const float bc1 = a.kind == 1 ? bc_dev[0] : 1.f, bc2s = a.kind == 1 ? bc_dev[1] : 1.f;
   const int lanes = vec ? dim / 4 : dim;
   const int g = (int)threadIdx.x & (G - 1);
   const int lane = (int)threadIdx.x & 31;
@@ -337,16 +334,14 @@ struct MultiP {
 
 __global__ void __launch_bounds__(128) fields_rowwise_update_kernel(const __grid_constant__ MultiP p, OptArgs a,
                                                                     const int32_t* __restrict__ step_dev,
-                                                                    const float* __restrict__ lr_dev, int G) {
+                                                                    const float* __restrict__ lr_dev,
+                                                                    const float* __restrict__ bc_dev, int G) {
   // same claim protocol as rowwise_update_kernel; 16-byte lanes only (dim % 4 == 0)
   const int f = blockIdx.y;
   const int step = *step_dev;
   const float lr = *lr_dev;
-  float bc1 = 1.f, bc2s = 1.f;
-  if (a.kind == 1) {
-    bc1 = (float)(1.0 - pow((double)a.beta1, (double)step));
-    bc2s = (float)sqrt(1.0 - pow((double)a.beta2, (double)step));
-  }
+  // Adam bias corrections 1 - beta1^t and sqrt(1 - beta2^t): computed ONCE per step by rh_opt_advance (fp64)
+  const float bc1 = a.kind == 1 ? bc_dev[0] : 1.f, bc2s = a.kind == 1 ? bc_dev[1] : 1.f;
   const int dim = p.dim, lanes = dim / 4;
   const int g = (int)threadIdx.x & (G - 1);
   const int lane = (int)threadIdx.x & 31;
@@ -390,7 +385,14 @@ __global__ void __launch_bounds__(128) fields_zero_kernel(const __grid_constant_
   if ((uint64_t)id < (uint64_t)p.vocab[f]) *reinterpret_cast<float4*>(p.grad[f] + id * p.dim + 4 * q) = f4_zero();
 }
 
-__global__ void opt_advance_kernel(int32_t* step_dev) { *step_dev += 1; }
+__global__ void opt_advance_kernel(int32_t* step_dev, float* bc_dev, float beta1, float beta2) {
+  const int step = *step_dev + 1;
+  *step_dev = step;
+  if (bc_dev != nullptr) {
+    bc_dev[0] = (float)(1.0 - pow((double)beta1, (double)step));
+    bc_dev[1] = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  }
+}
 
 }  // namespace rh
 
@@ -491,8 +493,9 @@ extern "C" int rh_seq_pool_bwd(float* table_grad, int vocab, int dim, int paddin
 
 extern "C" int rh_rowwise_update(float* table, float* table_grad, float* state1, float* state2, int32_t* stamp, int vocab, int dim,
                                  const void* ids, int ids_are_i32, int64_t n, int kind, const int32_t* step_dev, const float* lr_dev,
-                                 float beta1, float beta2, float eps, float weight_decay, void* stream) {
+                                 const float* bias_corr_dev, float beta1, float beta2, float eps, float weight_decay, void* stream) {
   RH_REQUIRE(table && table_grad && stamp && ids && step_dev && lr_dev, RH_ERR_INVALID_ARG, "rh_rowwise_update: NULL pointer");
+  RH_REQUIRE(kind != 1 || bias_corr_dev != nullptr, RH_ERR_INVALID_ARG, "rh_rowwise_update: Adam needs bias_corr_dev");
   RH_REQUIRE(kind >= 0 && kind <= 2, RH_ERR_INVALID_ARG, "rh_rowwise_update: kind %d unknown", kind);
   RH_REQUIRE(kind == 0 || state1 != nullptr, RH_ERR_INVALID_ARG, "rh_rowwise_update: state1 required");
   RH_REQUIRE(kind != 1 || state2 != nullptr, RH_ERR_INVALID_ARG, "rh_rowwise_update: state2 required for Adam");
@@ -504,14 +507,14 @@ extern "C" int rh_rowwise_update(float* table, float* table_grad, float* state1,
   int G = pow2_ceil(vec ? dim / 4 : dim);
   if (G > 32) G = 32;
   rowwise_update_kernel<<<grid_for(n * G, 256), 256, 0, (cudaStream_t)stream>>>(table, table_grad, state1, state2, stamp, vocab, dim, ids,
-                                                                                ids_are_i32 != 0, n, a, step_dev, lr_dev, vec, G);
+                                                                                ids_are_i32 != 0, n, a, step_dev, lr_dev, bias_corr_dev, vec, G);
   RH_LAUNCH_CHECK();
   return RH_OK;
 }
 
-extern "C" int rh_opt_advance(int32_t* step_dev, void* stream) {
+extern "C" int rh_opt_advance(int32_t* step_dev, float* bias_corr_dev, float beta1, float beta2, void* stream) {
   RH_REQUIRE(step_dev != nullptr, RH_ERR_INVALID_ARG, "rh_opt_advance: NULL");
-  opt_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+  opt_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, bias_corr_dev, beta1, beta2);
   RH_LAUNCH_CHECK();
   return RH_OK;
 }
@@ -548,8 +551,9 @@ static int pack_multi(rh::MultiP& p, const rh_field* fields, int n_fields, int d
 
 extern "C" int rh_fields_rowwise_update(const rh_field* fields, int n_fields, int dim, int batch, float* const* tables,
                                         float* const* state1, float* const* state2, int32_t* const* stamp, int kind,
-                                        const int32_t* step_dev, const float* lr_dev, float beta1, float beta2, float eps,
-                                        float weight_decay, void* stream) {
+                                        const int32_t* step_dev, const float* lr_dev, const float* bias_corr_dev, float beta1,
+                                        float beta2, float eps, float weight_decay, void* stream) {
+  RH_REQUIRE(kind != 1 || bias_corr_dev != nullptr, RH_ERR_INVALID_ARG, "rh_fields_rowwise_update: Adam needs bias_corr_dev");
   RH_REQUIRE(kind >= 0 && kind <= 2, RH_ERR_INVALID_ARG, "rh_fields_rowwise_update: kind %d unknown", kind);
   RH_REQUIRE(step_dev && lr_dev, RH_ERR_INVALID_ARG, "rh_fields_rowwise_update: step/lr NULL");
   RH_REQUIRE(kind == 0 || state1 != nullptr, RH_ERR_INVALID_ARG, "rh_fields_rowwise_update: state1 required");
@@ -567,7 +571,7 @@ extern "C" int rh_fields_rowwise_update(const rh_field* fields, int n_fields, in
   OptArgs a{kind, beta1, beta2, eps, weight_decay};
   const int threads = 128;
   dim3 grid((unsigned)(((int64_t)batch * G + threads - 1) / threads), n_fields);
-  fields_rowwise_update_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(p, a, step_dev, lr_dev, G);
+  fields_rowwise_update_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(p, a, step_dev, lr_dev, bias_corr_dev, G);
   RH_LAUNCH_CHECK();
   return RH_OK;
 }

@@ -17,6 +17,9 @@ rowwise_optimizer = _flag("RECHUB_B200_ROWWISE_OPT", False)
 # Capture CTRTrainer's training step into a CUDA graph (static shapes only; ragged last batches run eagerly).
 cuda_graph = _flag("RECHUB_B200_CUDA_GRAPH", False)
 
+# Also capture the sharded (multi-GPU) step, NCCL collectives included, into the graph.
+dist_cuda_graph = _flag("RECHUB_B200_DIST_CUDA_GRAPH", True)
+
 # Check the device-side out-of-range-id flag after every forward (one D2H sync per step).  When off the
 # flag is checked at the trainer's existing sync points (``loss.item()``) and by ``check_errors()``.
 eager_bounds_check = _flag("RECHUB_B200_EAGER_BOUNDS_CHECK", False)

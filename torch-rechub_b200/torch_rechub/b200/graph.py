@@ -25,6 +25,8 @@ class GraphedStep(object):
         self.static_y = None
         self.loss = None
         self.calls = 0
+        self.stream = None  # warm-up AND capture run on this side stream (autograd binds AccumulateGrad nodes to the stream
+        # they were first used on; a default-stream node inside a capture invalidates it)
         self.enabled = isinstance(trainer.optimizer, _optim.HybridOptimizer)
         if not self.enabled:
             print("[rechub-b200] cuda_graph needs config.rowwise_optimizer (dense optimisers run eagerly)")
@@ -41,8 +43,9 @@ class GraphedStep(object):
         self.static_y = y.to(dev).float().clone()
         self.sig = self._signature(x_dict, y)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.loss = self.trainer._train_step(self.static_x, self.static_y)
+        torch.cuda.current_stream().synchronize()
+        with torch.cuda.graph(self.graph, stream=self._side_stream()):
+            self.loss = self.trainer._train_step(self.static_x, self.static_y).detach()
 
     def load_inputs(self, x_dict, y):
         """Batch -> static buffers (straight from pinned host memory when the batch is still on the host)."""
@@ -53,10 +56,23 @@ class GraphedStep(object):
                 self.static_x[k].copy_(v, non_blocking=True)
         self.static_y.copy_(y, non_blocking=True)
 
+    def _side_stream(self):
+        if self.stream is None:
+            self.stream = torch.cuda.Stream(device=self.trainer.device)
+        return self.stream
+
     def _eager(self, x_dict, y):
         dev = self.trainer.device
         x_dict = x_dict.to(dev) if isinstance(x_dict, PackedColumns) else {k: v.to(dev) for k, v in x_dict.items()}
-        return self.trainer._train_step(x_dict, y.to(dev).float())
+        y = y.to(dev).float()
+        if not self.enabled:
+            return self.trainer._train_step(x_dict, y).detach()
+        cur, side = torch.cuda.current_stream(), self._side_stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            loss = self.trainer._train_step(x_dict, y).detach()
+        cur.wait_stream(side)
+        return loss
 
     def __call__(self, x_dict, y):
         self.calls += 1

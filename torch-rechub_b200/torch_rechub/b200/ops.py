@@ -400,59 +400,96 @@ def _colstats_scratch(device, cols):
     return t
 
 
-class _BnAct(torch.autograd.Function):
+_salt_counter = [0]
+
+
+def _dropout_seed(module):
+    """Per-layer dropout stream seed: deterministic under torch.manual_seed and the order layers are first used in."""
+    salt = getattr(module, "_rh_salt", None)
+    if salt is None:
+        _salt_counter[0] += 1
+        salt = module._rh_salt = _salt_counter[0]
+    return (torch.initial_seed() * 0x9E3779B1 + salt * 0x85EBCA6B) & 0xFFFFFFFF
+
+
+class _TowerLayer(torch.autograd.Function):
+    """y = dropout(act(bn(x @ W^T + b))): one tower layer (basic/layers.py:282-285) as GEMM + statistics + ONE fused pass.
+
+    The GEMMs are library calls (cuBLAS through torch.mm, fp32); everything between them is rh_colstats /
+    rh_bn_act_fwd / rh_bn_act_bwd.  No activation, mask or normalised copy is stored: backward recomputes from h.
+    """
 
     @staticmethod
-    def forward(ctx, h, gamma, beta, act_param, cfg):
-        # cfg: dict(running_mean, running_var, num_batches_tracked, momentum, eps, training, act, dice_eps, p_drop)
+    def forward(ctx, x, W, b, gamma, beta, act_param, cfg):
         L = _lib.lib()
-        h2 = _rowmajor(h)
-        rows, cols = h2.shape
-        h_ld = h2.stride(0) if rows > 1 else cols
-        dev = h.device
+        x2 = _rowmajor(x if x.dtype == torch.float32 else x.float())
+        rows, K = x2.shape
+        cols = W.shape[0]
+        dev = x2.device
         st = stream_ptr()
-        training = cfg["training"]
-        if training:
-            stats = torch.empty((2, cols), dtype=torch.float32, device=dev)
-            mean, var = stats[0], stats[1]
-            rm, rv, nbt = cfg["running_mean"], cfg["running_var"], cfg["num_batches_tracked"]
-            check(L.rh_colstats(h2.data_ptr(), h_ld, rows, cols, mean.data_ptr(), var.data_ptr(), _colstats_scratch(dev, cols).data_ptr(), ptr(rm), ptr(rv), ptr(nbt), float(cfg["momentum"]), st), "rh_colstats")
+        h = torch.empty((rows, cols), dtype=torch.float32, device=dev)
+        if b is not None:
+            torch.addmm(b, x2, W.t(), out=h)
         else:
+            torch.mm(x2, W.t(), out=h)
+        training = cfg["training"]
+        counter = None
+        if training:
+            stats = torch.empty(2 * cols + 1, dtype=torch.float32, device=dev)
+            check(L.rh_colstats(h.data_ptr(), cols, rows, cols, stats.data_ptr(), _colstats_scratch(dev, cols).data_ptr(), ptr(cfg["running_mean"]), ptr(cfg["running_var"]), ptr(cfg["num_batches_tracked"]),
+                                float(cfg["momentum"]), st), "rh_colstats")
+            mean, var, counter = stats[:cols], stats[cols:2 * cols], stats[2 * cols:]
+        else:
+            stats = None
             mean, var = cfg["running_mean"], cfg["running_var"]
-        mask = None
         p = float(cfg["p_drop"])
-        if training and p > 0.0:
-            mask = torch.empty((rows, cols), dtype=torch.uint8, device=dev).bernoulli_(1.0 - p)
         y = torch.empty((rows, cols), dtype=torch.float32, device=dev)
         check(
-            L.rh_bn_act_fwd(h2.data_ptr(), h_ld, rows, cols, ptr(mean), ptr(var), float(cfg["eps"]), ptr(gamma), ptr(beta), cfg["act"], ptr(act_param), float(cfg["dice_eps"]), ptr(mask), p, y.data_ptr(), cols, st),
-            "rh_bn_act_fwd")
+            L.rh_bn_act_fwd(h.data_ptr(), cols, rows, cols, ptr(mean), ptr(var), float(cfg["eps"]), ptr(gamma), ptr(beta), cfg["act"], ptr(act_param), float(cfg["dice_eps"]), p, cfg["seed"], ptr(counter), y.data_ptr(), cols,
+                            st), "rh_bn_act_fwd")
         ctx.cfg = cfg
         ctx.has_param = act_param is not None
-        ctx.save_for_backward(h2, mean, var, gamma, beta, act_param, mask)
+        ctx.has_bias = b is not None
+        ctx.save_for_backward(x2, W, h, stats, mean if stats is None else None, var if stats is None else None, gamma, beta, act_param)
         return y
 
     @staticmethod
     def backward(ctx, d_y):
         L = _lib.lib()
         cfg = ctx.cfg
-        h2, mean, var, gamma, beta, act_param, mask = ctx.saved_tensors
-        rows, cols = h2.shape
-        h_ld = h2.stride(0) if rows > 1 else cols
+        x2, W, h, stats, rmean, rvar, gamma, beta, act_param = ctx.saved_tensors
+        rows, K = x2.shape
+        cols = W.shape[0]
+        dev = h.device
+        training = stats is not None
+        if training:
+            mean, var, counter = stats[:cols], stats[cols:2 * cols], stats[2 * cols:]
+        else:
+            mean, var, counter = rmean, rvar, None
         g = _rowmajor(d_y)
         g_ld = g.stride(0) if rows > 1 else cols
-        dev = h2.device
         d_h = torch.empty((rows, cols), dtype=torch.float32, device=dev)
-        gbuf = torch.zeros(2 * cols + 1, dtype=torch.float32, device=dev)
-        d_gamma, d_beta, d_alpha = gbuf[:cols], gbuf[cols:2 * cols], gbuf[2 * cols:]
+        gbuf = torch.zeros(3 * cols + 1, dtype=torch.float32, device=dev)
+        d_gamma, d_beta, d_b, d_alpha = gbuf[:cols], gbuf[cols:2 * cols], gbuf[2 * cols:3 * cols], gbuf[3 * cols:]
         check(
-            L.rh_bn_act_bwd(h2.data_ptr(), h_ld, rows, cols, ptr(mean), ptr(var), float(cfg["eps"]), ptr(gamma), ptr(beta), cfg["act"], ptr(act_param), float(cfg["dice_eps"]), ptr(mask), float(cfg["p_drop"]),
-                            g.data_ptr(), g_ld, int(bool(cfg["training"])), d_h.data_ptr(), cols, d_gamma.data_ptr(), d_beta.data_ptr(), d_alpha.data_ptr() if ctx.has_param else None, stream_ptr()), "rh_bn_act_bwd")
-        return d_h, (d_gamma if gamma is not None else None), (d_beta if beta is not None else None), (d_alpha.view_as(act_param) if ctx.has_param else None), None
+            L.rh_bn_act_bwd(h.data_ptr(), cols, rows, cols, ptr(mean), ptr(var), float(cfg["eps"]), ptr(gamma), ptr(beta), cfg["act"], ptr(act_param), float(cfg["dice_eps"]), float(cfg["p_drop"]), cfg["seed"],
+                            ptr(counter), g.data_ptr(), g_ld, int(training), d_h.data_ptr(), cols, d_gamma.data_ptr(), d_beta.data_ptr(), d_alpha.data_ptr() if ctx.has_param else None, stream_ptr()), "rh_bn_act_bwd")
+        d_W = torch.mm(d_h.t(), x2)
+        if not training and ctx.has_bias:  # eval: BN is affine, the Linear bias sees sum_rows d_h = d_beta * gamma * rstd
+            d_b = d_beta * (gamma if gamma is not None else 1.0) / torch.sqrt(var + cfg["eps"])
+        # training: the bias in front of a batch-statistics BN has a gradient of exactly 0 (BN removes any per-column
+        # shift); the reference's autograd produces rounding noise ~1e-8 there.  d_b stays the zero slice of gbuf.
+        d_x = None
+        if ctx.needs_input_grad[0]:
+            ld = _pad4(K)
+            buf = torch.empty((rows, ld), dtype=torch.float32, device=dev)
+            d_x = buf if ld == K else buf[:, :K]
+            torch.mm(d_h, W, out=d_x)
+        return (d_x, d_W, d_b if ctx.has_bias else None, d_gamma if gamma is not None else None, d_beta if beta is not None else None, d_alpha.view_as(act_param) if ctx.has_param else None, None)
 
 
-def bn_act(h, bn, act_code, act_param, dice_eps, p_drop, training):
-    """``dropout(act(bn(h)))`` for a 2-D ``h`` — one tower layer after its Linear (basic/layers.py:282-285)."""
+def tower_layer(x, linear, bn, act_code, act_param, dice_eps, p_drop, training):
+    """One ``Linear -> BatchNorm1d -> activation -> Dropout`` group of the reference's MLP on CUDA."""
     cfg = {
         "running_mean": bn.running_mean,
         "running_var": bn.running_var,
@@ -462,9 +499,10 @@ def bn_act(h, bn, act_code, act_param, dice_eps, p_drop, training):
         "training": bool(training),
         "act": act_code,
         "dice_eps": dice_eps,
-        "p_drop": p_drop,
+        "p_drop": float(p_drop),
+        "seed": _dropout_seed(bn) if p_drop > 0 else 0,
     }
-    return _BnAct.apply(h, bn.weight, bn.bias, act_param, cfg)
+    return _TowerLayer.apply(x, linear.weight, linear.bias, bn.weight, bn.bias, act_param, cfg)
 
 
 # =====================================================================================================

@@ -42,6 +42,7 @@ class RowwiseOptimizer(object):
         self._step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         self._lr_dev = torch.full((1,), self.lr, dtype=torch.float32, device=dev)
         self._lr_host = self.lr
+        self._bc_dev = torch.ones(2, dtype=torch.float32, device=dev)  # Adam bias corrections, refreshed by rh_opt_advance
 
     # -- state ---------------------------------------------------------------------------------------
     def _state(self, p):
@@ -65,11 +66,11 @@ class RowwiseOptimizer(object):
     def step(self):
         L = _lib.lib()
         st = stream_ptr()
-        check(L.rh_opt_advance(self._step_dev.data_ptr(), st), "rh_opt_advance")
+        check(L.rh_opt_advance(self._step_dev.data_ptr(), self._bc_dev.data_ptr(), self.betas[0], self.betas[1], st), "rh_opt_advance")
         # one (table, id-list) entry per lookup recorded by the backward kernels
         entries = []
         for p in self.params:
-            slot = _table._slots.get(p)
+            slot = _table.find_slot(p)
             if slot is None or slot.buffer is None or not slot.pending:
                 continue
             if slot.all_dirty or p.grad is None or p.grad.data_ptr() != slot.buffer.data_ptr():
@@ -108,7 +109,7 @@ class RowwiseOptimizer(object):
                     stamps.append(stt["stamp"])
                 check(
                     L.rh_fields_rowwise_update(arr, len(chunk), dim, batch, _ptrs(tables), _ptrs(s1) if self.kind != 0 else None, _ptrs(s2) if self.kind == 1 else None, _ptrs(stamps), self.kind,
-                                               self._step_dev.data_ptr(), self._lr_dev.data_ptr(), self.betas[0], self.betas[1], self.eps, self.weight_decay, st), "rh_fields_rowwise_update")
+                                               self._step_dev.data_ptr(), self._lr_dev.data_ptr(), self._bc_dev.data_ptr(), self.betas[0], self.betas[1], self.eps, self.weight_decay, st), "rh_fields_rowwise_update")
         for p in self.params:
             _table.mark_clean(p)
 
@@ -118,7 +119,7 @@ class RowwiseOptimizer(object):
         m, v = stt.get("m"), stt.get("v")
         check(
             L.rh_rowwise_update(p.data_ptr(), slot.buffer.data_ptr(), None if m is None else m.data_ptr(), None if v is None else v.data_ptr(), stt["stamp"].data_ptr(), p.shape[0], p.shape[1], idc.data_ptr(),
-                                int(idc.dtype == torch.int32), idc.numel(), self.kind, self._step_dev.data_ptr(), self._lr_dev.data_ptr(), self.betas[0], self.betas[1], self.eps, self.weight_decay, st),
+                                int(idc.dtype == torch.int32), idc.numel(), self.kind, self._step_dev.data_ptr(), self._lr_dev.data_ptr(), self._bc_dev.data_ptr(), self.betas[0], self.betas[1], self.eps, self.weight_decay, st),
             "rh_rowwise_update")
 
     def zero_grad(self, set_to_none=True):
@@ -129,6 +130,35 @@ class RowwiseOptimizer(object):
                 _table.clean(p)
 
 
+class DenseOptimizer(object):
+    """SGD / Adam / Adagrad over the small dense tensors in ONE launch (``rh_dense_update``), sharing the step counter,
+    learning-rate scalar and Adam bias corrections of the row-wise optimiser (all on the device: graph-replay safe)."""
+
+    def __init__(self, params, rowwise):
+        self.params = [p for p in params]
+        self.rw = rowwise
+        self.state = {}
+
+    def step(self):
+        L = _lib.lib()
+        rw = self.rw
+        ps = [p for p in self.params if p.grad is not None]
+        if not ps:
+            return
+        for p in ps:
+            if id(p) not in self.state:
+                self.state[id(p)] = (torch.zeros_like(p, memory_format=torch.contiguous_format) if rw.kind != 0 else None,
+                                     torch.zeros_like(p, memory_format=torch.contiguous_format) if rw.kind == 1 else None)
+        grads = [p.grad if p.grad.is_contiguous() else p.grad.contiguous() for p in ps]
+        n = len(ps)
+        numel = (ctypes.c_int64 * n)(*[p.numel() for p in ps])
+        s1 = _ptrs([self.state[id(p)][0] for p in ps]) if rw.kind != 0 else None
+        s2 = _ptrs([self.state[id(p)][1] for p in ps]) if rw.kind == 1 else None
+        check(
+            L.rh_dense_update(n, _ptrs(ps), _ptrs(grads), s1, s2, numel, rw.kind, rw._lr_dev.data_ptr(), rw._bc_dev.data_ptr(), rw.betas[0], rw.betas[1], rw.eps, rw.weight_decay, stream_ptr()),
+            "rh_dense_update")
+
+
 class HybridOptimizer(object):
     """Row-wise optimiser for the tables + the user's torch optimiser for everything else.
 
@@ -137,9 +167,10 @@ class HybridOptimizer(object):
     its learning rate.
     """
 
-    def __init__(self, rowwise, dense):
+    def __init__(self, rowwise, dense, dense_params):
         self.rowwise = rowwise
-        self.dense = dense
+        self.dense = dense  # a torch optimiser that only carries param_groups / lr for schedulers; never stepped
+        self.dense_engine = DenseOptimizer(dense_params, rowwise)
         self.scheduler_target = dense
 
     @classmethod
@@ -159,19 +190,15 @@ class HybridOptimizer(object):
         if not tables:
             return None
         tset = {id(p) for p in tables}
-        others = [p for p in model.parameters() if id(p) not in tset]
-        dense_kwargs = dict(optimizer_params)
-        if others:
-            if kind == 1:
-                dense_kwargs.setdefault("capturable", True)  # step counter on the device: CUDA-graph safe
-            dense = optimizer_fn(others, **dense_kwargs)
-        else:
+        others = [p for p in model.parameters() if id(p) not in tset and p.numel() > 0 and p.requires_grad]
+        if not others:
             return None
+        dense = optimizer_fn(others, **dict(optimizer_params))
         defaults = {0: dict(lr=1e-3), 1: dict(lr=1e-3, betas=(0.9, 0.999), eps=1e-8), 2: dict(lr=1e-2, eps=1e-10)}[kind]
         kw = dict(defaults)
         kw.update({k: v for k, v in optimizer_params.items()})
         rw = RowwiseOptimizer(tables, kind, **kw)
-        return cls(rw, dense)
+        return cls(rw, dense, others)
 
     @property
     def param_groups(self):
@@ -180,8 +207,8 @@ class HybridOptimizer(object):
     def step(self):
         lr = self.dense.param_groups[0]["lr"]
         self.rowwise.set_lr(float(lr) if not torch.is_tensor(lr) else float(lr.item()))
-        self.rowwise.step()
-        self.dense.step()
+        self.rowwise.step()  # advances the shared step counter / bias corrections first
+        self.dense_engine.step()
 
     def zero_grad(self, set_to_none=True):
         self.rowwise.zero_grad(set_to_none)

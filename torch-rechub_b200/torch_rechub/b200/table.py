@@ -29,24 +29,32 @@ class GradSlot(object):
         self.all_dirty = False  # a foreign dense gradient was accumulated into the buffer
 
 
-_slots = weakref.WeakKeyDictionary()  # weight Parameter -> GradSlot
+_slots = {}  # id(weight Parameter) -> (weakref to the Parameter, GradSlot); tensors cannot key a WeakKeyDictionary (== is elementwise)
+
+
+def find_slot(weight):
+    ent = _slots.get(id(weight))
+    if ent is not None and ent[0]() is weight:
+        return ent[1]
+    return None
 
 
 def slot_of(weight):
-    s = _slots.get(weight)
+    s = find_slot(weight)
     if s is None:
         s = GradSlot()
-        _slots[weight] = s
-        # a dense gradient arriving through autograd's AccumulateGrad (e.g. an L2 penalty on the table)
-        # may touch every row: remember to clean everything next time.
-        if hasattr(weight, "register_post_accumulate_grad_hook"):
+        key = id(weight)
+        _slots[key] = (weakref.ref(weight, lambda _r, _k=key: _slots.pop(_k, None)), s)
+        # A dense gradient reaching this weight through autograd (e.g. an L2 penalty on the table) is added IN PLACE to
+        # whatever .grad is — possibly our buffer — and may touch every row: remember to clean everything next time.
+        # (A tensor hook receives None when only the engine's kernels contributed, the summed gradient otherwise.)
+        def _mark(grad, _slot_ref=weakref.ref(s)):
+            sl = _slot_ref()
+            if grad is not None and sl is not None:
+                sl.all_dirty = True
 
-            def _mark(param, _slot_ref=weakref.ref(s)):
-                sl = _slot_ref()
-                if sl is not None and sl.buffer is not None and param.grad is not None and param.grad.data_ptr() == sl.buffer.data_ptr():
-                    sl.all_dirty = True
-
-            weight.register_post_accumulate_grad_hook(_mark)
+        if weight.requires_grad:
+            weight.register_hook(_mark)
     return s
 
 
@@ -109,7 +117,7 @@ def note_dirty(slot, ids):
 
 def mark_clean(weight):
     """Called by the row-wise optimiser: it consumed AND re-zeroed every pending row."""
-    slot = _slots.get(weight)
+    slot = find_slot(weight)
     if slot is not None:
         slot.pending = []
 

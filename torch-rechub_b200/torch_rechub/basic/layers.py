@@ -102,6 +102,7 @@ class EmbeddingLayer(nn.Module):
         self.embed_dict = nn.ModuleDict()
         self.n_dense = 0
         self.input_mask = InputMask()
+        self._dist = None  # b200.dist.ShardedFront when the tables are sharded by field over several GPUs
         for fea in features:
             if fea.name in self.embed_dict:
                 continue
@@ -213,6 +214,11 @@ class EmbeddingLayer(nn.Module):
         return plan
 
     def forward(self, x, features, squeeze_dim=False):
+        if self._dist is not None:
+            return self._dist.forward(x, features, squeeze_dim)
+        return self._forward_local(x, features, squeeze_dim)
+
+    def _forward_local(self, x, features, squeeze_dim=False):
         if not self._on_cuda(x, features):
             return self._forward_composite(x, features, squeeze_dim)
         from ..b200 import ops
@@ -296,10 +302,9 @@ class MLP(nn.Module):
             m = mods[i]
             if (isinstance(m, nn.Linear) and i + 3 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm1d) and isinstance(mods[i + 3], nn.Dropout) and self._fusable(mods[i + 1], mods[i + 2], x)):
                 bn, act, drop = mods[i + 1], mods[i + 2], mods[i + 3]
-                h = torch.nn.functional.linear(x, m.weight, m.bias)
                 name = _FUSED_ACTS[type(act)]
                 param = act.alpha if name == "dice" else (act.weight if name == "prelu" else None)
-                x = ops.bn_act(h, bn, ops.ACT_CODES[name], param, getattr(act, "epsilon", 0.0), drop.p if drop.training else 0.0, bn.training)
+                x = ops.tower_layer(x, m, bn, ops.ACT_CODES[name], param, getattr(act, "epsilon", 0.0), drop.p if drop.training else 0.0, bn.training)
                 i += 4
             else:
                 x = m(x)

@@ -62,7 +62,35 @@ class DeepFM(torch.nn.Module):
         plan.want_fm = plan.want_lr = True
         return plan
 
+    def _fm_from_deep(self, input_deep):
+        """(B, n_fm, D) view/gather of the deep tile's columns when every FM feature is also a deep feature
+        (sharded runs: ONE all-to-all exchange serves both uses)."""
+        from ...basic.features import DenseFeature
+        offsets, col = {}, 0
+        for fea in self.deep_features:
+            if not isinstance(fea, DenseFeature):
+                offsets.setdefault(fea.name, (col, fea.embed_dim))
+                col += fea.embed_dim
+        dim = self.fm_features[0].embed_dim
+        starts = []
+        for fea in self.fm_features:
+            if fea.name not in offsets or offsets[fea.name][1] != dim or fea.embed_dim != dim:
+                return None
+            starts.append(offsets[fea.name][0])
+        n = len(starts)
+        if all(starts[i] == starts[0] + i * dim for i in range(n)):
+            return input_deep[:, starts[0]:starts[0] + n * dim].unflatten(1, (n, dim))
+        idx = torch.tensor([c for s0 in starts for c in range(s0, s0 + dim)], device=input_deep.device)
+        return input_deep.index_select(1, idx).unflatten(1, (n, dim))
+
     def forward(self, x):
+        if self.embedding._dist is not None:
+            input_deep = self.embedding(x, self.deep_features, squeeze_dim=True)
+            input_fm = self._fm_from_deep(input_deep) if self.fm_features else None
+            if input_fm is None:
+                input_fm = self.embedding(x, self.fm_features, squeeze_dim=False)
+            y = self.linear(input_fm.flatten(start_dim=1)) + self.fm(input_fm) + self.mlp(input_deep)
+            return torch.sigmoid(y.squeeze(1))
         plan = self._fused_plan(x) if self.embedding._on_cuda(x, self.deep_features + self.fm_features) else None
         if plan is not None:
             from ...b200 import ops

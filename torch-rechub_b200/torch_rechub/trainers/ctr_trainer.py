@@ -75,7 +75,7 @@ class CTRTrainer(object):
                 self.model = torch.nn.DataParallel(self.model, device_ids=gpus)
         self.model.to(self.device)
         self._dist = None
-        if self.device.type == "cuda" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1 and (self.device.type == "cuda" or os.environ.get("RECHUB_B200_SHARD_ON_CPU") == "1"):
             from ..b200 import dist as _dist
             self._dist = _dist.attach(self.model, self.device)
         if optimizer_params is None:
@@ -104,7 +104,7 @@ class CTRTrainer(object):
                 hybrid = optim.HybridOptimizer.build(self.model, optimizer_fn, optimizer_params)
                 if hybrid is not None:
                     return hybrid
-        return optimizer_fn(self.model.parameters(), **optimizer_params)
+        return optimizer_fn([p for p in self.model.parameters() if p.numel() > 0], **optimizer_params)
 
     def _to_device(self, x_dict):
         if hasattr(x_dict, "copy_into"):  # b200.data.PackedColumns: <= 3 copies instead of one per column
@@ -128,7 +128,7 @@ class CTRTrainer(object):
         self.model.zero_grad()
         loss.backward()
         self.optimizer.step()
-        return loss
+        return loss.detach()  # callers only read the value; holding the graph alive would pin AccumulateGrad nodes
 
     def train_one_epoch(self, data_loader, log_interval=10):
         self.model.train()
@@ -140,7 +140,7 @@ class CTRTrainer(object):
             from ..b200 import _lib, config, graph
         tk0 = tqdm.tqdm(data_loader, desc="train", smoothing=0, mininterval=1.0)
         for i, (x_dict, y) in enumerate(tk0):
-            if on_cuda and config.cuda_graph and self._dist is None:
+            if on_cuda and config.cuda_graph and (self._dist is None or config.dist_cuda_graph):
                 if self._graph_step is None:
                     self._graph_step = graph.GraphedStep(self)
                 loss = self._graph_step(x_dict, y)  # copies the (host) batch straight into the graph's static inputs
@@ -185,8 +185,12 @@ class CTRTrainer(object):
                     self.model.load_state_dict(self.early_stopper.best_weights)
                     break
 
-        if self._dist is None or self._dist.rank == 0:
+        if self._dist is None:
             torch.save(self.model.state_dict(), os.path.join(self.model_path, "model.pth"))
+        else:  # every rank takes part in gathering the sharded tables; rank 0 writes the reference-layout checkpoint
+            full = self._dist.full_state_dict()
+            if self._dist.rank == 0:
+                torch.save(full, os.path.join(self.model_path, "model.pth"))
 
         for logger in self._iter_loggers():
             logger.finish()
