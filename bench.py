@@ -307,7 +307,8 @@ def run_b200_arm(args):
     # ---- roofline of the fused forward kernel -------------------------------------------------------------------
     roof = None
     if rank == 0:
-        avg_ms, med_ms = time_fused_forward_kernel(model, pool_dev)
+        kmodel = model if trainer._dist is None else build_model(device)[0]  # sharded run: time the kernel on a private full set of tables
+        avg_ms, med_ms = time_fused_forward_kernel(kmodel, pool_dev)
         peak, peak_src = peaks()
         algo = ALGO_BYTES_FWD_PER_SAMPLE * BATCH
         achieved = algo / (avg_ms * 1e-3) / 1e9
@@ -325,8 +326,7 @@ def run_b200_arm(args):
     if world > 1:
         dist.barrier()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _leave(world)
         return
 
     cpu = None
@@ -360,8 +360,18 @@ def run_b200_arm(args):
         "final_loss": final_loss,
     }
     print(json.dumps(line), flush=True)
+    _leave(world)
+
+
+def _leave(world):
+    """Multi-rank exit: NCCL communicators captured inside live CUDA graphs can hang destroy_process_group(); every rank has
+    passed the final barrier, so flush and leave without tearing the communicator down."""
     if world > 1:
-        dist.destroy_process_group()
+        import torch
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
