@@ -268,6 +268,20 @@ int rh_dense_update(int n_tensors, float* const* params, const float* const* gra
                     float beta1, float beta2, float eps, float weight_decay, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Tower GEMM on the tcgen05 tensor cores, fp32-accurate (3xTF32: hi*hi + hi*lo + lo*hi, fp32 accumulators in TMEM).
+ *   C[M, N] (+)= A[M, K] * B[N, K]^T (+ bias[N])          — the Linear layers of MLP.forward / backward
+ *   (reference basic/layers.py:281-292; ATen addmm / mm there).
+ *   a_mn_major == 0: A is stored row-major [M][lda] (K contiguous);  != 0: A is stored [K][lda] (M contiguous), i.e. the
+ *   caller passes the matrix whose TRANSPOSE is the operand (dW = dH^T X reads dH and X as stored).  Same for B.
+ *   lda, ldb must be multiples of 4 floats and A, B 16-byte aligned (TMA); C any ldc >= N.
+ *   split_k > 1: K is cut into split_k slices accumulated with red.global.add — C must be zero on entry.
+ * ------------------------------------------------------------------------------------------- */
+int rh_gemm_tf32x3(const float* A, int64_t lda, int a_mn_major,
+                   const float* B, int64_t ldb, int b_mn_major,
+                   float* C, int64_t ldc, int M, int N, int K,
+                   const float* bias, int split_k, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * DIN target attention (models/ranking/din.py:77-93, ActivationUnit.forward).
  * ------------------------------------------------------------------------------------------- */
 

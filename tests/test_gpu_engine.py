@@ -180,7 +180,7 @@ def test_full_size_properties():
     tile, y_fm, y_lr = ops.fused_tile(plan, lw, lb)
     assert torch.equal(y_fm, torch.full((B,), 5200.0, device=DEV))
     assert torch.equal(y_lr, torch.full((B,), 416.5, device=DEV))
-    assert tile.shape == (B, F * D) and float(tile.min()) == 1.0 and float(tile.max()) == 1.0
+    assert tile.shape == (B, F * D) and float(tile.detach().min()) == 1.0 and float(tile.detach().max()) == 1.0
     # (2) row r of table f holds the value r + f/32: the gathered tile reproduces (id + f/32) bit-exactly
     with torch.no_grad():
         base = torch.arange(V, dtype=torch.float32, device=DEV).unsqueeze(1)

@@ -1,0 +1,389 @@
+// rh_gemm.cu — fp32-accurate tower GEMM on the 5th-generation tensor cores: C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]).
+//
+// Why not TF32 straight: the parity bar is |d logit| <= 1e-4 |ref| + 1e-6 against an fp32 reference; one TF32 product
+// carries ~5e-4 relative error.  3xTF32 (split every fp32 operand x = hi + lo, hi = top 19 bits, and accumulate
+// hi*hi + hi*lo + lo*hi in fp32 TMEM accumulators) restores ~2^-22 per product — fp32-level — at 3 tensor-core MMAs
+// per k-step, still ~10x the fp32 SIMT rate the reference-equivalent cuBLAS sgemm runs at on this part.
+//
+// Structure (one 128x128 output tile per CTA, BLOCK_K = 32 floats = one 128-byte swizzle row, 3-stage ring):
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d of the raw fp32 A / B tiles (SWIZZLE_128B), mbarrier tx bytes
+//   warps 2..7  splitters: read the raw tiles, write hi (truncated) back in place and lo into the twin tiles,
+//               fence.proxy.async, arrive on `ready`
+//   warp 1      MMA issuer: one thread issues 12 tcgen05.mma.kind::tf32 (M128 N128 K8) per k-block, tcgen05.commit frees
+//               the stage; also owns the TMEM allocation (128 columns)
+//   warps 4..7  epilogue: tcgen05.ld 32x32b.x32 -> registers -> (+bias) -> st.global / red.global (split-K)
+// Operands may be K-major (row-major [rows, K]) or MN-major (row-major [K, rows], i.e. the transposed use of a stored
+// matrix): dX = dH * W and dW = dH^T * X read W, dH and X as stored — no transposed copies.
+//
+// Replaces the Linear GEMMs of MLP.forward/backward (reference basic/layers.py:281-292; cuBLAS sgemm via ATen there).
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "rh_common.cuh"
+
+namespace rh {
+
+constexpr int kBM = 128, kBN = 128, kBK = 32, kStages = 3;
+constexpr int kTileBytes = kBM * kBK * 4;         // 16 KB: one operand tile (hi or lo)
+constexpr int kStageBytes = 4 * kTileBytes;       // A_hi, B_hi, A_lo, B_lo
+constexpr int kSplitWarps = 6;                    // warps 2..7
+constexpr int kGemmThreads = 256;
+constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_c),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+        "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Shared-memory matrix descriptors (cute/arch/mma_sm100_desc.hpp: SmemDescriptor), version 1.
+//   K-major : SWIZZLE_128B (layout type 2): rows of 128 B, 8-row groups 1024 B apart (SBO); one MMA k-step (8 tf32) = +32 B
+//             on the start address inside the swizzle atom.
+//   MN-major: tf32 MN-major operands only exist with SWIZZLE_128B_BASE32B (layout type 1; TMA SWIZZLE_128B_ATOM_32B):
+//             atom = 32 MN elements (128 B) x 4 k rows (512 B), 32-B chunks XOR-ed with (row & 3).  Our tile = four TMA
+//             boxes {32 MN, 32 K} of 4096 B: MN groups LBO = 4096 B apart, 4-k groups SBO = 512 B apart; one MMA k-step
+//             (8 k rows) = +1024 B.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, bool mn_major, int variant = 0) {
+  uint64_t lbo = 1u, sbo = 1024u >> 4, type = 2;
+  if (mn_major) {
+    type = 1;
+    lbo = 4096u >> 4;
+    sbo = 512u >> 4;
+    if (variant == 1) {
+      lbo = 512u >> 4;
+      sbo = 4096u >> 4;
+    }
+  }
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (type << 61);
+}
+
+struct GemmP {
+  float* C;
+  int64_t ldc;
+  const float* bias;
+  int M, N, K;
+  int a_mn, b_mn;   // operand majors: 0 = K-major, 1 = MN-major
+  int kblocks_per_split;
+  int reduce;       // 1: red.global.add into C (split-K), 0: plain stores
+  int variant;      // debug: descriptor variant for MN-major operands
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmP p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kStageBytes);
+  uint64_t* full = bars;                 // [kStages]
+  uint64_t* ready = bars + kStages;      // [kStages]
+  uint64_t* empty = bars + 2 * kStages;  // [kStages]
+  uint64_t* tmem_full = bars + 3 * kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * kBN;
+  const int total_kb = (p.K + kBK - 1) / kBK;
+  const int kb0 = blockIdx.z * p.kblocks_per_split;
+  int kb1 = kb0 + p.kblocks_per_split;
+  if (kb1 > total_kb) kb1 = total_kb;
+  const int n_iter = kb1 - kb0;  // >= 1 by construction of the grid
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&ready[s], kSplitWarps);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM: 2 x 128 fp32 accumulator columns (main + cross terms)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* st = smem + (size_t)s * kStageBytes;
+        mbar_arrive_expect_tx(&full[s], 2 * kTileBytes);
+        const int k0 = (kb0 + it) * kBK;
+        if (p.a_mn) {
+          for (int i = 0; i < 4; ++i) tma_load_2d(st + i * 4096, &map_a, &full[s], m0 + 32 * i, k0);
+        } else {
+          tma_load_2d(st, &map_a, &full[s], k0, m0);
+        }
+        if (p.b_mn) {
+          for (int i = 0; i < 4; ++i) tma_load_2d(st + kTileBytes + i * 4096, &map_b, &full[s], n0 + 32 * i, k0);
+        } else {
+          tma_load_2d(st + kTileBytes, &map_b, &full[s], k0, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) | ((uint32_t)(kBN >> 3) << 17) |
+                           ((uint32_t)(kBM >> 4) << 24);
+    const uint32_t a_step = p.a_mn ? (1024u >> 4) : (32u >> 4);
+    const uint32_t b_step = p.b_mn ? (1024u >> 4) : (32u >> 4);
+    for (int it = 0; it < n_iter; ++it) {
+      const int s = it % kStages;
+      const uint32_t ph = (it / kStages) & 1;
+      mbar_wait(&ready[s], ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        const uint32_t base = smem_u32(smem + (size_t)s * kStageBytes);
+        const uint64_t a_hi = make_desc(base, p.a_mn != 0, p.variant), b_hi = make_desc(base + kTileBytes, p.b_mn != 0, p.variant);
+        const uint64_t a_lo = make_desc(base + 2 * kTileBytes, p.a_mn != 0, p.variant), b_lo = make_desc(base + 3 * kTileBytes, p.b_mn != 0, p.variant);
+#pragma unroll
+        for (int kk = 0; kk < kBK / 8; ++kk) {
+          const uint64_t da = (uint64_t)(kk * a_step), db = (uint64_t)(kk * b_step);
+          // The tensor core accumulates with round-toward-zero: every MMA into a large accumulator adds a -2^-24-relative
+          // bias (measured: 160 MMAs into one accumulator = 11x the fp32 error).  The small cross terms therefore get their
+          // OWN accumulator; the main one sees one MMA per k-step.  The epilogue adds the two in fp32.
+          const uint32_t first = (it > 0 || kk > 0) ? 1u : 0u;
+          umma_tf32(tmem_base, a_hi + da, b_hi + db, idesc, first);
+          umma_tf32(tmem_base + 128u, a_hi + da, b_lo + db, idesc, first);
+          umma_tf32(tmem_base + 128u, a_lo + da, b_hi + db, idesc, 1u);
+        }
+        umma_commit(&empty[s]);                       // stage free once these MMAs have read it
+        if (it == n_iter - 1) umma_commit(tmem_full);  // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== splitters (warps 2..7): hi = top 19 bits (in place), lo = x - hi (twin tile, same swizzled offsets) =====
+    const int t = threadIdx.x - 64;  // 0..191
+    for (int it = 0; it < n_iter; ++it) {
+      const int s = it % kStages;
+      const uint32_t ph = (it / kStages) & 1;
+      mbar_wait(&full[s], ph);
+      uint8_t* st = smem + (size_t)s * kStageBytes;
+      for (int i = t; i < 2 * kTileBytes / 16; i += kSplitWarps * 32) {
+        float4* src = reinterpret_cast<float4*>(st + (size_t)i * 16);
+        float4* dst = reinterpret_cast<float4*>(st + 2 * kTileBytes + (size_t)i * 16);
+        const float4 x = *src;
+        float4 h, l;
+        // hi = top 19 bits (what a tf32 operand keeps); lo = rn_tf32(x - hi): rounding lo to nearest keeps the second-order
+        // error unbiased (a truncated lo loses up to 2^-10 of itself ALWAYS toward zero: measured 6x the fp32 error at K = 512)
+        h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+        h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+        h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+        h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+        l.x = rna_tf32(x.x - h.x);
+        l.y = rna_tf32(x.y - h.y);
+        l.z = rna_tf32(x.z - h.z);
+        l.w = rna_tf32(x.w - h.w);
+        // the raw tile stays as it is: kind::tf32 reads only the top 19 bits of each word (verified: rewriting hi changes nothing)
+        *dst = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor-core (async) proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ready[s]);
+    }
+    // ===== epilogue (warps 4..7 own TMEM lane quadrants 0..3) =====
+    if (warp >= 4) {
+      const int q = warp - 4;
+      mbar_wait(tmem_full, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int m = m0 + q * 32 + lane;
+      const bool add_bias = p.bias != nullptr && blockIdx.z == 0;
+      const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15u) == 0);
+#pragma unroll 1
+      for (int c = 0; c < kBN / 32; ++c) {
+        uint32_t r[32], x[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
+        tmem_ld32(taddr, r);
+        tmem_ld32(taddr + 128u, x);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(x[j]));
+        if (m < p.M) {
+          const int nb = n0 + c * 32;
+          float* crow = p.C + (int64_t)m * p.ldc + nb;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            if (add_bias) {
+              if (nb + j < p.N) v.x += __ldg(p.bias + nb + j);
+              if (nb + j + 1 < p.N) v.y += __ldg(p.bias + nb + j + 1);
+              if (nb + j + 2 < p.N) v.z += __ldg(p.bias + nb + j + 2);
+              if (nb + j + 3 < p.N) v.w += __ldg(p.bias + nb + j + 3);
+            }
+            if (vec_ok && nb + j + 3 < p.N) {
+              if (p.reduce) red_add_row16(crow + j, v);
+              else *reinterpret_cast<float4*>(crow + j) = v;
+            } else {
+              const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (nb + j + e < p.N) {
+                  if (p.reduce) atomicAdd(crow + j + e, vv[e]);
+                  else crow[j + e] = vv[e];
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+// ---- host ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+  }
+  return fn;
+}
+
+// rows x K fp32 matrix used as a [rows, K] operand.  K-major: stored [rows][ld] -> box {32 (K), 128 (rows)}.
+// MN-major: stored [K][ld] with `rows` contiguous -> box {32 (rows), 32 (K)}.
+static int make_map(CUtensorMap* map, const float* base, int64_t ld, int rows, int K, bool mn_major) {
+  EncodeTiledFn fn = encode_fn();
+  RH_REQUIRE(fn != nullptr, RH_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t gdim[2], gstride[1];
+  cuuint32_t box[2], estr[2] = {1, 1};
+  if (mn_major) {
+    gdim[0] = (cuuint64_t)rows;
+    gdim[1] = (cuuint64_t)K;
+    box[0] = 32;
+    box[1] = 32;
+  } else {
+    gdim[0] = (cuuint64_t)K;
+    gdim[1] = (cuuint64_t)rows;
+    box[0] = 32;
+    box[1] = 128;
+  }
+  gstride[0] = (cuuint64_t)ld * sizeof(float);
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RH_REQUIRE(r == CUDA_SUCCESS, RH_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): base %p ld %lld rows %d K %d mn %d", (int)r, (const void*)base,
+             (long long)ld, rows, K, (int)mn_major);
+  return RH_OK;
+}
+
+}  // namespace rh
+
+using namespace rh;
+
+extern "C" int rh_gemm_tf32x3(const float* A, int64_t lda, int a_mn_major, const float* B, int64_t ldb, int b_mn_major, float* C, int64_t ldc,
+                              int M, int N, int K, const float* bias, int split_k, void* stream) {
+  RH_REQUIRE(A && B && C, RH_ERR_INVALID_ARG, "rh_gemm_tf32x3: NULL pointer");
+  RH_REQUIRE(M > 0 && N > 0 && K > 0 && ldc >= N, RH_ERR_INVALID_ARG, "rh_gemm_tf32x3: bad sizes");
+  RH_REQUIRE(lda % 4 == 0 && ldb % 4 == 0, RH_ERR_UNSUPPORTED, "rh_gemm_tf32x3: TMA needs 16-byte row strides (lda=%lld ldb=%lld)", (long long)lda,
+             (long long)ldb);
+  RH_REQUIRE(((uintptr_t)A & 15u) == 0 && ((uintptr_t)B & 15u) == 0, RH_ERR_UNSUPPORTED, "rh_gemm_tf32x3: operands must be 16-byte aligned");
+  RH_REQUIRE(lda >= (a_mn_major ? M : K) && ldb >= (b_mn_major ? N : K), RH_ERR_INVALID_ARG, "rh_gemm_tf32x3: leading dimension too small");
+  const int total_kb = (K + kBK - 1) / kBK;
+  if (split_k < 1) split_k = 1;
+  if (split_k > total_kb) split_k = total_kb;
+  const int per = (total_kb + split_k - 1) / split_k;
+  split_k = (total_kb + per - 1) / per;  // no empty splits
+
+  CUtensorMap map_a, map_b;
+  int rc = make_map(&map_a, A, lda, M, K, a_mn_major != 0);
+  if (rc != RH_OK) return rc;
+  rc = make_map(&map_b, B, ldb, N, K, b_mn_major != 0);
+  if (rc != RH_OK) return rc;
+
+  GemmP p;
+  p.C = C;
+  p.ldc = ldc;
+  p.bias = bias;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.a_mn = a_mn_major != 0;
+  p.b_mn = b_mn_major != 0;
+  p.kblocks_per_split = per;
+  p.reduce = split_k > 1 ? 1 : 0;
+  p.variant = getenv("RH_GEMM_VARIANT") ? atoi(getenv("RH_GEMM_VARIANT")) : 0;
+
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem);
+    RH_REQUIRE(e == cudaSuccess, RH_ERR_CUDA, "rh_gemm_tf32x3: cannot reserve %zu bytes of shared memory: %s", kGemmSmem, cudaGetErrorString(e));
+    configured = true;
+  }
+  dim3 grid((M + kBM - 1) / kBM, (N + kBN - 1) / kBN, split_k);
+  gemm_tf32x3_kernel<<<grid, kGemmThreads, kGemmSmem, (cudaStream_t)stream>>>(map_a, map_b, p);
+  RH_LAUNCH_CHECK();
+  return RH_OK;
+}

@@ -24,5 +24,8 @@ dist_cuda_graph = _flag("RECHUB_B200_DIST_CUDA_GRAPH", True)
 # flag is checked at the trainer's existing sync points (``loss.item()``) and by ``check_errors()``.
 eager_bounds_check = _flag("RECHUB_B200_EAGER_BOUNDS_CHECK", False)
 
+# Tower GEMMs on the tcgen05 tensor cores with the fp32-accurate 3xTF32 kernel (rh_gemm_tf32x3); off = cuBLAS fp32 (torch.mm).
+tensor_core_gemm = _flag("RECHUB_B200_TC_GEMM", True)
+
 # Set by the graph runner while inputs live in static buffers that the next batch overwrites.
 static_inputs = False

@@ -400,6 +400,53 @@ def _colstats_scratch(device, cols):
     return t
 
 
+def gemm3x(A, a_mn, B, b_mn, M, N, K, bias=None, split_k=1, out=None, out_cols=None):
+    """C[M, N] = op(A) @ op(B)^T (+ bias) on the tensor cores, fp32-accurate (rh_gemm_tf32x3).
+    ``A``: (M, K) row-major when ``a_mn`` is False, else the stored (K, M) matrix whose transpose is the operand; same for B.
+    ``out``: optional (M, >= N) buffer with unit inner stride; with ``split_k > 1`` it must be zero."""
+    L = _lib.lib()
+    if out is None:
+        ld = _pad4(N) if out_cols is None else out_cols
+        out = torch.zeros((M, ld), dtype=torch.float32, device=A.device) if split_k > 1 else torch.empty((M, ld), dtype=torch.float32, device=A.device)
+    check(
+        L.rh_gemm_tf32x3(A.data_ptr(), A.stride(0), int(a_mn), B.data_ptr(), B.stride(0), int(b_mn), out.data_ptr(), out.stride(0), M, N, K, ptr(bias), int(split_k), stream_ptr()),
+        "rh_gemm_tf32x3")
+    return out if out.shape[1] == N else out[:, :N]
+
+
+def _tc_ok(rows, *mats):
+    """Shapes/strides the TMA-fed kernel accepts; tiny problems stay on the library GEMM."""
+    from . import config
+    if not config.tensor_core_gemm or rows < 128:
+        return False
+    return all(m.dtype == torch.float32 and m.dim() == 2 and m.stride(1) == 1 and m.stride(0) % 4 == 0 and m.data_ptr() % 16 == 0 for m in mats)
+
+
+_padded_weights = {}
+
+
+def _padded_weight(W):
+    """W (N, K) with a row stride that is a multiple of 4 floats (TMA): W itself, or a refreshed padded copy."""
+    if W.stride(1) == 1 and W.stride(0) % 4 == 0 and W.data_ptr() % 16 == 0:
+        return W
+    key = id(W)
+    ent = _padded_weights.get(key)
+    N, K = W.shape
+    if ent is None or ent[0]() is not W or ent[1].device != W.device:
+        import weakref
+        buf = torch.zeros((N, _pad4(K)), dtype=torch.float32, device=W.device)
+        _padded_weights[key] = (weakref.ref(W, lambda _r, _k=key: _padded_weights.pop(_k, None)), buf)
+        ent = _padded_weights[key]
+    ent[1][:, :K].copy_(W.detach())
+    return ent[1][:, :K]
+
+
+def _split_k_for(m_tiles, n_tiles, k_blocks):
+    """Enough K slices to put ~128 CTAs on the 148 SMs when the output has few tiles (weight gradients)."""
+    tiles = max(1, m_tiles * n_tiles)
+    return max(1, min(k_blocks, 128 // tiles))
+
+
 _salt_counter = [0]
 
 
@@ -428,7 +475,12 @@ class _TowerLayer(torch.autograd.Function):
         dev = x2.device
         st = stream_ptr()
         h = torch.empty((rows, cols), dtype=torch.float32, device=dev)
-        if b is not None:
+        Wp = None
+        use_tc = cols % 4 == 0 and _tc_ok(rows, x2)
+        if use_tc:
+            Wp = _padded_weight(W)  # (cols, K) view with a 16-byte row stride
+            gemm3x(x2, False, Wp, False, rows, cols, K, bias=b, out=h)
+        elif b is not None:
             torch.addmm(b, x2, W.t(), out=h)
         else:
             torch.mm(x2, W.t(), out=h)
@@ -450,6 +502,8 @@ class _TowerLayer(torch.autograd.Function):
         ctx.cfg = cfg
         ctx.has_param = act_param is not None
         ctx.has_bias = b is not None
+        ctx.use_tc = use_tc
+        ctx.Wp = Wp
         ctx.save_for_backward(x2, W, h, stats, mean if stats is None else None, var if stats is None else None, gamma, beta, act_param)
         return y
 
@@ -474,7 +528,10 @@ class _TowerLayer(torch.autograd.Function):
         check(
             L.rh_bn_act_bwd(h.data_ptr(), cols, rows, cols, ptr(mean), ptr(var), float(cfg["eps"]), ptr(gamma), ptr(beta), cfg["act"], ptr(act_param), float(cfg["dice_eps"]), float(cfg["p_drop"]), cfg["seed"],
                             ptr(counter), g.data_ptr(), g_ld, int(training), d_h.data_ptr(), cols, d_gamma.data_ptr(), d_beta.data_ptr(), d_alpha.data_ptr() if ctx.has_param else None, stream_ptr()), "rh_bn_act_bwd")
-        d_W = torch.mm(d_h.t(), x2)
+        if ctx.use_tc:  # dW[cols, K] = d_h^T x: both operands read as stored (MN-major), K = rows split over CTAs
+            d_W = gemm3x(d_h, True, x2, True, cols, K, rows, split_k=_split_k_for((cols + 127) // 128, (K + 127) // 128, (rows + 31) // 32), out_cols=K)
+        else:
+            d_W = torch.mm(d_h.t(), x2)
         if not training and ctx.has_bias:  # eval: BN is affine, the Linear bias sees sum_rows d_h = d_beta * gamma * rstd
             d_b = d_beta * (gamma if gamma is not None else 1.0) / torch.sqrt(var + cfg["eps"])
         # training: the bias in front of a batch-statistics BN has a gradient of exactly 0 (BN removes any per-column
@@ -484,7 +541,10 @@ class _TowerLayer(torch.autograd.Function):
             ld = _pad4(K)
             buf = torch.empty((rows, ld), dtype=torch.float32, device=dev)
             d_x = buf if ld == K else buf[:, :K]
-            torch.mm(d_h, W, out=d_x)
+            if ctx.use_tc:  # dX[rows, K] = d_h W: W (cols, K) is the MN-major B operand as stored
+                gemm3x(d_h, False, ctx.Wp, True, rows, K, cols, out=buf)
+            else:
+                torch.mm(d_h, W, out=d_x)
         return (d_x, d_W, d_b if ctx.has_bias else None, d_gamma if gamma is not None else None, d_beta if beta is not None else None, d_alpha.view_as(act_param) if ctx.has_param else None, None)
 
 
