@@ -93,6 +93,23 @@ int rh_fields_fwd(const rh_field* fields, int n_fields, int dim,
                   float* y_fm, float* y_lr, float* field_sum,
                   int32_t* err_flag, void* stream);
 
+/* Fused gather + all-to-all over peer memory (multi-GPU field sharding): the owner of the tables gathers
+ * its fields for the GLOBAL batch and writes each sample's rows STRAIGHT into the tile of the GPU that holds that sample
+ * (NVLink peer stores from inside the gather kernel) — no local staging buffer, no NCCL all-to-all.
+ *   dest_tiles[d]  device pointer (peer-mapped) of destination d's tile block; sample i goes to dest i / rows_per_dest,
+ *                  row i % rows_per_dest, row stride tile_ld; field f fills columns [tile_col, tile_col + dim)
+ * Callers order the exchange with cross-GPU barriers.  The backward direction needs no new entry point: rh_fields_bwd's
+ * rh_field.table_grad may be a peer pointer (vector RED over NVLink). */
+int rh_fields_fwd_p2p(const rh_field* fields, int n_fields, int dim, int batch,
+                      float* const* dest_tiles, int n_dest, int rows_per_dest, int64_t tile_ld,
+                      int32_t* err_flag, void* stream);
+
+/* ids of my samples -> the owners' id buffers (peer memory).  cols[c] (ids / id_stride / ids_are_i32 are read) is the c-th id
+ * column, col_dest[c] its destination GPU (columns sorted by destination; the order inside a destination is the slot order);
+ * dest_base[d] points at MY (batch, fmax) block of destination d's id buffer:  dest_base[d][j * fmax + slot] = ids[j]. */
+int rh_ids_scatter(const rh_field* cols, int n_cols, const int32_t* col_dest, int batch,
+                   int64_t* const* dest_base, int n_dest, int fmax, void* stream);
+
 /* Backward of rh_fields_fwd: the sparse-gradient scatter-add into the tables' gradient buffers.
  *
  * Replaces autograd's aten::embedding_dense_backward per lookup (reference: implicit in
@@ -198,6 +215,20 @@ int rh_fm_fwd(const float* x, int batch, int n_fields, int dim, int reduce_sum,
               float* y, void* stream);
 int rh_fm_bwd(const float* x, const float* d_y, int batch, int n_fields, int dim, int reduce_sum,
               float* d_x, void* stream);
+
+/* FM + LR on an already materialised tile (batch, n_fields*dim) — the sharded multi-GPU front end, where rows arrive
+ * over NVLink instead of being gathered locally.  Same arithmetic as the FM/LR part of rh_fields_fwd / rh_fields_bwd:
+ *   y_fm = FM(tile) (basic/layers.py:313-319), y_lr = tile . lr_weight + lr_bias (layers.py:183-189), field_sum = sum_f e.
+ * Backward: d_tile[b, f] (= or +=, `accumulate`) d_y_fm[b] (field_sum[b] - e) + d_y_lr[b] lr_weight[f];
+ * d_lr_weight / d_lr_bias are accumulated into (caller zeroes). */
+int rh_tile_fm_lr_fwd(const float* tile, int64_t tile_ld, int batch, int n_fields, int dim,
+                      const float* lr_weight, const float* lr_bias,
+                      float* y_fm, float* y_lr, float* field_sum, void* stream);
+int rh_tile_fm_lr_bwd(const float* tile, int64_t tile_ld, int batch, int n_fields, int dim,
+                      const float* lr_weight, const float* field_sum,
+                      const float* d_y_fm, const float* d_y_lr,
+                      float* d_tile, int64_t d_tile_ld, int accumulate,
+                      float* d_lr_weight, float* d_lr_bias, void* stream);
 
 /* CrossNetwork.forward (basic/layers.py:412-420): x_{l+1} = x0 * <w_l, x_l> + b_l + x_l for
  * l < n_layers (<= 16), all layers in one launch, the row held in registers throughout.

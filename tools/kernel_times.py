@@ -16,15 +16,22 @@ import bench  # noqa: E402
 def main():
     steps = int(os.environ.get("PROF_STEPS", "20"))
     use_graph = os.environ.get("PROF_GRAPH", "1") == "1"
-    dev = torch.device("cuda", 0)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
     from torch_rechub.b200 import config
     from torch_rechub.b200.graph import GraphedStep
     from torch_rechub.trainers import CTRTrainer
     config.rowwise_optimizer = True
     config.cuda_graph = use_graph
     model, dense, sparse = bench.build_model(dev)
-    trainer = CTRTrainer(model, device="cuda:0", n_epoch=1)
-    pool = bench.make_pool(16, seed=1)
+    trainer = CTRTrainer(model, device=str(dev), n_epoch=1)
+    pool = bench.make_pool(16, seed=1 + rank)
     pool_dev = [(x.to(dev), y.to(dev)) for x, y in pool]
     model.train()
     step = GraphedStep(trainer) if use_graph else (lambda x, y: trainer._train_step(x, y))
@@ -35,6 +42,9 @@ def main():
         for i in range(steps):
             step(*pool_dev[i % 16])
         torch.cuda.synchronize()
+    if rank != 0:
+        torch.distributed.barrier()
+        os._exit(0)
     agg = defaultdict(lambda: [0, 0.0])
     for ev in prof.events():
         if ev.device_type == torch.autograd.DeviceType.CUDA:
@@ -44,6 +54,10 @@ def main():
     print("graph=%s steps=%d  sum of kernel time per step: %.1f us" % (use_graph, steps, total / steps))
     for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print("%6.2f/step %8.2f us avg %5.1f%%  %s" % (n / steps, t / n, 100 * t / total, name[:110]))
+    sys.stdout.flush()
+    if world > 1:
+        torch.distributed.barrier()
+        os._exit(0)
 
 
 if __name__ == "__main__":

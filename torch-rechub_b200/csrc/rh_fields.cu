@@ -40,7 +40,8 @@ struct FwdParams {
   FieldDev f[RH_MAX_FIELDS];
   DenseDev d[RH_MAX_DENSE];
   int32_t n_fields, n_dense, batch, dim;
-  int32_t tile_vec, pad0_;  // 1: tile rows/columns are 16-byte aligned -> vector stores
+  int32_t tile_vec, dest_rows;  // tile_vec: 16-byte aligned tile rows -> vector stores; dest_rows > 0: rows go to dest[b / dest_rows]
+  float* dest[8];               // peer-memory tiles (one per destination GPU) for the fused gather + all-to-all
   float* tile;
   int64_t tile_ld;
   const float* lrw;
@@ -149,7 +150,8 @@ __global__ void __launch_bounds__(NG * 32) fields_fwd_v4(const __grid_constant__
       if (f < p.n_fields && lane_on) {
         const FieldDev& fd = p.f[f];
         if (fd.tile_col >= 0 && p.tile != nullptr) {
-          st_tile4(p.tile + (int64_t)b * p.tile_ld + fd.tile_col + 4 * q, v[j], p.tile_vec != 0);
+          float* trow = p.dest_rows > 0 ? p.dest[b / p.dest_rows] + (int64_t)(b % p.dest_rows) * p.tile_ld : p.tile + (int64_t)b * p.tile_ld;
+          st_tile4(trow + fd.tile_col + 4 * q, v[j], p.tile_vec != 0);
         }
         if (fd.fm_slot >= 0 && want_fm) {
           s = f4_add(s, v[j]);
@@ -431,9 +433,9 @@ static void launch_bwd_v4(const BwdParams& p, cudaStream_t st) {
 
 using namespace rh;
 
-extern "C" int rh_fields_fwd(const rh_field* fields, int n_fields, int dim, const rh_dense* dense, int n_dense, int batch,
-                             float* tile, int64_t tile_ld, const float* lr_weight, const float* lr_bias, float* y_fm,
-                             float* y_lr, float* field_sum, int32_t* err_flag, void* stream) {
+static int fields_fwd_impl(const rh_field* fields, int n_fields, int dim, const rh_dense* dense, int n_dense, int batch, float* tile,
+                           int64_t tile_ld, const float* lr_weight, const float* lr_bias, float* y_fm, float* y_lr, float* field_sum,
+                           int32_t* err_flag, void* stream, float* const* dest, int n_dest, int dest_rows) {
   RH_REQUIRE(n_fields >= 0 && n_fields <= RH_MAX_FIELDS, RH_ERR_INVALID_ARG, "n_fields %d not in [0,%d]", n_fields, RH_MAX_FIELDS);
   RH_REQUIRE(n_dense >= 0 && n_dense <= RH_MAX_DENSE, RH_ERR_INVALID_ARG, "n_dense %d not in [0,%d]", n_dense, RH_MAX_DENSE);
   RH_REQUIRE(n_fields == 0 || fields != nullptr, RH_ERR_INVALID_ARG, "fields is NULL");
@@ -481,6 +483,17 @@ extern "C" int rh_fields_fwd(const rh_field* fields, int n_fields, int dim, cons
   p.tile = tile;
   p.tile_ld = tile_ld;
   p.tile_vec = tile_vec ? 1 : 0;
+  p.dest_rows = 0;
+  if (n_dest > 0) {
+    RH_REQUIRE(vec_ok && n_dense == 0 && n_dest <= 8 && dest_rows > 0 && dest != nullptr, RH_ERR_UNSUPPORTED,
+               "peer-tile gather needs the 16-byte-lane kernel, no dense columns and <= 8 destinations");
+    for (int i = 0; i < n_dest; ++i) {
+      RH_REQUIRE(dest[i] != nullptr && aligned16(dest[i]), RH_ERR_INVALID_ARG, "peer tile %d NULL or misaligned", i);
+      p.dest[i] = dest[i];
+    }
+    RH_REQUIRE((int64_t)n_dest * dest_rows >= batch, RH_ERR_INVALID_ARG, "peer tiles cover %d x %d rows < batch %d", n_dest, dest_rows, batch);
+    p.dest_rows = dest_rows;
+  }
   p.lrw = want_fm ? lr_weight : nullptr;
   p.lrb = want_fm ? lr_bias : nullptr;
   p.yfm = want_fm ? y_fm : nullptr;
@@ -575,6 +588,73 @@ extern "C" int rh_fields_bwd(const rh_field* fields, int n_fields, int dim, int 
     if (grid > cap) grid = cap;
     fields_bwd_scalar<<<grid, 256, 0, st>>>(p);
   }
+  RH_LAUNCH_CHECK();
+  return RH_OK;
+}
+
+extern "C" int rh_fields_fwd(const rh_field* fields, int n_fields, int dim, const rh_dense* dense, int n_dense, int batch, float* tile,
+                             int64_t tile_ld, const float* lr_weight, const float* lr_bias, float* y_fm, float* y_lr, float* field_sum,
+                             int32_t* err_flag, void* stream) {
+  return fields_fwd_impl(fields, n_fields, dim, dense, n_dense, batch, tile, tile_ld, lr_weight, lr_bias, y_fm, y_lr, field_sum, err_flag, stream,
+                         nullptr, 0, 0);
+}
+
+extern "C" int rh_fields_fwd_p2p(const rh_field* fields, int n_fields, int dim, int batch, float* const* dest_tiles, int n_dest,
+                                 int rows_per_dest, int64_t tile_ld, int32_t* err_flag, void* stream) {
+  RH_REQUIRE(dest_tiles != nullptr && n_dest > 0, RH_ERR_INVALID_ARG, "rh_fields_fwd_p2p: no destinations");
+  return fields_fwd_impl(fields, n_fields, dim, nullptr, 0, batch, dest_tiles[0], tile_ld, nullptr, nullptr, nullptr, nullptr, nullptr, err_flag, stream,
+                         dest_tiles, n_dest, rows_per_dest);
+}
+
+// ids of my samples -> the owners' id buffers (peer memory).  One thread per (destination, sample) writes that sample's ids for
+// ALL of the destination's fields contiguously (24-104 B), so a warp's stores to a peer coalesce into full NVLink packets.
+namespace rh {
+struct IdScatterP {
+  const void* src[RH_MAX_FIELDS];   // columns sorted by (destination, slot)
+  int32_t stride[RH_MAX_FIELDS];
+  uint8_t is_i32[RH_MAX_FIELDS];
+  long long* dst[8];                 // per destination: base of MY block in its (W, b, fmax) id buffer
+  int32_t first[8], count[8];        // columns of destination d: [first[d], first[d] + count[d])
+  int32_t batch, fmax;
+};
+__global__ void __launch_bounds__(256) ids_scatter_kernel(const __grid_constant__ IdScatterP p) {
+  const int d = blockIdx.y;
+  const int first = p.first[d], count = p.count[d];
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < p.batch; j += gridDim.x * blockDim.x) {
+    long long* out = p.dst[d] + (int64_t)j * p.fmax;
+    for (int k = 0; k < count; ++k) out[k] = (long long)load_id(p.src[first + k], (int64_t)j * p.stride[first + k], p.is_i32[first + k] != 0);
+  }
+}
+}  // namespace rh
+
+extern "C" int rh_ids_scatter(const rh_field* cols, int n_cols, const int32_t* col_dest, int batch, int64_t* const* dest_base, int n_dest, int fmax,
+                              void* stream) {
+  RH_REQUIRE(cols != nullptr && col_dest != nullptr && dest_base != nullptr && n_cols > 0 && n_cols <= RH_MAX_FIELDS && batch >= 0 && fmax > 0 &&
+                 n_dest > 0 && n_dest <= 8,
+             RH_ERR_INVALID_ARG, "rh_ids_scatter: bad arguments");
+  if (batch == 0) return RH_OK;
+  static thread_local rh::IdScatterP p;
+  memset(&p, 0, sizeof(p));
+  int prev = -1;
+  for (int i = 0; i < n_cols; ++i) {
+    const int d = col_dest[i];
+    RH_REQUIRE(cols[i].ids != nullptr && d >= 0 && d < n_dest && d >= prev, RH_ERR_INVALID_ARG, "rh_ids_scatter: column %d (columns must be sorted by destination)", i);
+    RH_REQUIRE(cols[i].id_stride >= 0 && cols[i].id_stride < ((int64_t)1 << 31), RH_ERR_INVALID_ARG, "rh_ids_scatter: stride out of range");
+    if (d != prev) p.first[d] = i;
+    p.count[d] += 1;
+    prev = d;
+    p.src[i] = cols[i].ids;
+    p.stride[i] = (int32_t)cols[i].id_stride;
+    p.is_i32[i] = (uint8_t)(cols[i].ids_are_i32 != 0);
+  }
+  for (int d = 0; d < n_dest; ++d) {
+    RH_REQUIRE(dest_base[d] != nullptr && p.count[d] <= fmax, RH_ERR_INVALID_ARG, "rh_ids_scatter: destination %d", d);
+    p.dst[d] = reinterpret_cast<long long*>(dest_base[d]);
+  }
+  p.batch = batch;
+  p.fmax = fmax;
+  dim3 grid((batch + 255) / 256, n_dest);
+  rh::ids_scatter_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
   RH_LAUNCH_CHECK();
   return RH_OK;
 }

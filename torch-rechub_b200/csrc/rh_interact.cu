@@ -56,6 +56,114 @@ __global__ void __launch_bounds__(256) fm_bwd_kernel(const float* __restrict__ x
   }
 }
 
+// ---- FM + LR on an already materialised tile ------------------------------------------------------
+// The sharded (multi-GPU) front end receives its rows over NVLink instead of gathering them, so FM / LR run on the
+// (batch, n_fields*dim) tile: same arithmetic as the fused gather kernel (rh_fields_fwd), rows read from the tile.
+// lane = (sample, 16-byte quarter); each lane walks the fields of its sample.
+template <int LPR>
+__global__ void __launch_bounds__(128) tile_fm_lr_fwd_kernel(const float* __restrict__ tile, int64_t ld, int batch, int n_fields, int dim,
+                                                             const float* __restrict__ lrw, const float* __restrict__ lrb,
+                                                             float* __restrict__ yfm, float* __restrict__ ylr, float* __restrict__ fsum) {
+  const int spb = blockDim.x / LPR;
+  const int b = blockIdx.x * spb + (int)threadIdx.x / LPR;
+  const int q = (int)threadIdx.x % LPR;
+  const bool live = b < batch, lane_on = live && 4 * q < dim;
+  float4 s = f4_zero();
+  float ss = 0.f, lr = 0.f;
+  if (lane_on) {
+    const float* row = tile + (int64_t)b * ld + 4 * q;
+#pragma unroll 4
+    for (int f = 0; f < n_fields; ++f) {
+      const float4 v = ldg_row16(row + (int64_t)f * dim);
+      s = f4_add(s, v);
+      ss += f4_dot(v, v);
+      if (lrw != nullptr) lr += f4_dot(v, __ldg(reinterpret_cast<const float4*>(lrw + (int64_t)f * dim + 4 * q)));
+    }
+  }
+  float t = (s.x * s.x + s.y * s.y) + (s.z * s.z + s.w * s.w) - ss;
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) {
+    t += __shfl_xor_sync(0xffffffffu, t, o);
+    lr += __shfl_xor_sync(0xffffffffu, lr, o);
+  }
+  if (live && q == 0) {
+    if (yfm != nullptr) yfm[b] = 0.5f * t;
+    if (ylr != nullptr) ylr[b] = lr + (lrb != nullptr ? __ldg(lrb) : 0.f);
+  }
+  if (fsum != nullptr && lane_on) *reinterpret_cast<float4*>(fsum + (int64_t)b * dim + 4 * q) = s;
+}
+
+// d_tile[b, f] (+)= d_yfm[b] * (S[b] - e) + d_ylr[b] * w[f];   d_lrw[f] += sum_b d_ylr[b] * e;   d_lrb += sum_b d_ylr[b]
+// grid = (sample chunks, fields): the LR weight gradient of a field reduces inside the block.
+template <int LPR>
+__global__ void __launch_bounds__(128) tile_fm_lr_bwd_kernel(const float* __restrict__ tile, int64_t ld, int batch, int n_fields, int dim,
+                                                             const float* __restrict__ lrw, const float* __restrict__ fsum,
+                                                             const float* __restrict__ dyfm, const float* __restrict__ dylr,
+                                                             float* __restrict__ d_tile, int64_t d_ld, int accumulate,
+                                                             float* __restrict__ d_lrw, float* __restrict__ d_lrb) {
+  __shared__ float4 sm_dw[4][32];
+  __shared__ float sm_db[4];
+  constexpr int ITER = 4;
+  const int f = blockIdx.y;
+  const int spi = blockDim.x / LPR;
+  const int q = (int)threadIdx.x % LPR, sl = (int)threadIdx.x / LPR;
+  const bool lane_on = 4 * q < dim;
+  const int base = blockIdx.x * spi * ITER;
+  float4 w = f4_zero();
+  if (lrw != nullptr && dylr != nullptr && lane_on) w = __ldg(reinterpret_cast<const float4*>(lrw + (int64_t)f * dim + 4 * q));
+  float4 dw = f4_zero();
+  float db = 0.f;
+#pragma unroll
+  for (int i = 0; i < ITER; ++i) {
+    const int b = base + i * spi + sl;
+    if (b < batch && lane_on) {
+      const float4 e = ldg_row16(tile + (int64_t)b * ld + (int64_t)f * dim + 4 * q);
+      const float gf = dyfm != nullptr ? __ldg(dyfm + b) : 0.f;
+      const float gl = dylr != nullptr ? __ldg(dylr + b) : 0.f;
+      float4 g = f4_zero();
+      if (dyfm != nullptr) {
+        const float4 S = ldg_row16(fsum + (int64_t)b * dim + 4 * q);
+        g = make_float4(gf * (S.x - e.x), gf * (S.y - e.y), gf * (S.z - e.z), gf * (S.w - e.w));
+      }
+      g = f4_fma(w, make_float4(gl, gl, gl, gl), g);
+      float* dst = d_tile + (int64_t)b * d_ld + (int64_t)f * dim + 4 * q;
+      if (accumulate) g = f4_add(g, *reinterpret_cast<const float4*>(dst));
+      *reinterpret_cast<float4*>(dst) = g;
+      dw = f4_fma(e, make_float4(gl, gl, gl, gl), dw);
+      if (q == 0) db += gl;
+    }
+  }
+  const bool want_dw = d_lrw != nullptr && dylr != nullptr;
+  const bool want_db = f == 0 && d_lrb != nullptr && dylr != nullptr;
+  if (want_dw || want_db) {
+#pragma unroll
+    for (int o = 16; o >= LPR; o >>= 1) {
+      dw.x += __shfl_xor_sync(0xffffffffu, dw.x, o);
+      dw.y += __shfl_xor_sync(0xffffffffu, dw.y, o);
+      dw.z += __shfl_xor_sync(0xffffffffu, dw.z, o);
+      dw.w += __shfl_xor_sync(0xffffffffu, dw.w, o);
+    }
+    db = warp_sum(db);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane < LPR) sm_dw[warp][lane] = dw;
+    if (lane == 0) sm_db[warp] = db;
+    __syncthreads();
+    const int nwarp = blockDim.x >> 5;
+    if (warp == 0) {
+      if (want_dw && lane < LPR && 4 * lane < dim) {
+        float4 t = sm_dw[0][lane];
+        for (int k = 1; k < nwarp; ++k) t = f4_add(t, sm_dw[k][lane]);
+        red_add_row16(d_lrw + (int64_t)f * dim + 4 * lane, t);
+      }
+      if (want_db && lane == 0) {
+        float t = sm_db[0];
+        for (int k = 1; k < nwarp; ++k) t += sm_db[k];
+        atomicAdd(d_lrb, t);
+      }
+    }
+  }
+}
+
 // ---- CrossNetwork ------------------------------------------------------------------------------
 // Per-layer parameters stay where the reference keeps them (one Linear(width,1) weight and one bias
 // vector per layer, basic/layers.py:409-410): the kernels take pointer tables, not stacked copies.
@@ -327,4 +435,59 @@ extern "C" int rh_cross_bwd(const float* x0, int64_t x_ld, int batch, int width,
   }
   return dispatch_cross(false, x0, x_ld, batch, width, n_layers, cp, nullptr, 0, const_cast<float*>(xw_saved), d_out, d_out_ld, d_x0,
                         d_x0_ld, (cudaStream_t)stream);
+}
+
+static bool al16i(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+extern "C" int rh_tile_fm_lr_fwd(const float* tile, int64_t tile_ld, int batch, int n_fields, int dim, const float* lr_weight,
+                                 const float* lr_bias, float* y_fm, float* y_lr, float* field_sum, void* stream) {
+  RH_REQUIRE(tile != nullptr && batch >= 0 && n_fields > 0 && dim > 0, RH_ERR_INVALID_ARG, "rh_tile_fm_lr_fwd: bad arguments");
+  RH_REQUIRE(dim % 4 == 0 && dim <= 128 && tile_ld % 4 == 0 && al16i(tile) && al16i(lr_weight) && al16i(field_sum), RH_ERR_UNSUPPORTED,
+             "rh_tile_fm_lr_fwd needs dim %% 4 == 0 (<= 128) and 16-byte aligned rows (dim=%d ld=%lld)", dim, (long long)tile_ld);
+  if (batch == 0) return RH_OK;
+  const int lpr = pow2_ceil(dim / 4), threads = 128;
+  const int grid = (batch + threads / lpr - 1) / (threads / lpr);
+  cudaStream_t st = (cudaStream_t)stream;
+#define RH_TF(L) tile_fm_lr_fwd_kernel<L><<<grid, threads, 0, st>>>(tile, tile_ld, batch, n_fields, dim, lr_weight, lr_bias, y_fm, y_lr, field_sum)
+  switch (lpr) {
+    case 1: RH_TF(1); break;
+    case 2: RH_TF(2); break;
+    case 4: RH_TF(4); break;
+    case 8: RH_TF(8); break;
+    case 16: RH_TF(16); break;
+    default: RH_TF(32); break;
+  }
+#undef RH_TF
+  RH_LAUNCH_CHECK();
+  return RH_OK;
+}
+
+extern "C" int rh_tile_fm_lr_bwd(const float* tile, int64_t tile_ld, int batch, int n_fields, int dim, const float* lr_weight,
+                                 const float* field_sum, const float* d_y_fm, const float* d_y_lr, float* d_tile, int64_t d_tile_ld,
+                                 int accumulate, float* d_lr_weight, float* d_lr_bias, void* stream) {
+  RH_REQUIRE(tile != nullptr && d_tile != nullptr && batch >= 0 && n_fields > 0 && dim > 0, RH_ERR_INVALID_ARG, "rh_tile_fm_lr_bwd: bad arguments");
+  RH_REQUIRE(d_y_fm == nullptr || field_sum != nullptr, RH_ERR_INVALID_ARG, "rh_tile_fm_lr_bwd: d_y_fm needs field_sum");
+  RH_REQUIRE(d_y_lr == nullptr || lr_weight != nullptr, RH_ERR_INVALID_ARG, "rh_tile_fm_lr_bwd: d_y_lr needs lr_weight");
+  RH_REQUIRE(dim % 4 == 0 && dim <= 128 && tile_ld % 4 == 0 && d_tile_ld % 4 == 0 && al16i(tile) && al16i(d_tile) && al16i(lr_weight) &&
+                 al16i(field_sum) && al16i(d_lr_weight),
+             RH_ERR_UNSUPPORTED, "rh_tile_fm_lr_bwd needs dim %% 4 == 0 (<= 128) and 16-byte aligned rows");
+  if (batch == 0) return RH_OK;
+  const int lpr = pow2_ceil(dim / 4), threads = 128;
+  const int spb = threads / lpr * 4;
+  dim3 grid((batch + spb - 1) / spb, n_fields);
+  cudaStream_t st = (cudaStream_t)stream;
+#define RH_TB(L)                                                                                                                      \
+  tile_fm_lr_bwd_kernel<L><<<grid, threads, 0, st>>>(tile, tile_ld, batch, n_fields, dim, lr_weight, field_sum, d_y_fm, d_y_lr, d_tile, \
+                                                     d_tile_ld, accumulate, d_lr_weight, d_lr_bias)
+  switch (lpr) {
+    case 1: RH_TB(1); break;
+    case 2: RH_TB(2); break;
+    case 4: RH_TB(4); break;
+    case 8: RH_TB(8); break;
+    case 16: RH_TB(16); break;
+    default: RH_TB(32); break;
+  }
+#undef RH_TB
+  RH_LAUNCH_CHECK();
+  return RH_OK;
 }

@@ -36,6 +36,8 @@ PROTOTYPES = {
     "rh_last_error": [],
     "rh_launch_count": [],
     "rh_fields_fwd": [c_p, c_i, c_i, c_p, c_i, c_i, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
+    "rh_fields_fwd_p2p": [c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_i64, c_p, c_p],
+    "rh_ids_scatter": [c_p, c_i, c_p, c_i, c_p, c_i, c_i, c_p],
     "rh_fields_bwd": [c_p, c_i, c_i, c_i, c_p, c_i64, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "rh_rows_gather": [c_p, c_i, c_i, c_p, c_i, c_i64, c_p, c_p, c_p],
     "rh_rows_scatter_add": [c_p, c_i, c_i, c_i, c_p, c_i, c_i64, c_p, c_p, c_p],
@@ -48,6 +50,8 @@ PROTOTYPES = {
     "rh_fields_zero": [c_p, c_i, c_i, c_i, c_p],
     "rh_fm_fwd": [c_p, c_i, c_i, c_i, c_i, c_p, c_p],
     "rh_fm_bwd": [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p],
+    "rh_tile_fm_lr_fwd": [c_p, c_i64, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p],
+    "rh_tile_fm_lr_bwd": [c_p, c_i64, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_i64, c_i, c_p, c_p, c_p],
     "rh_cross_fwd": [c_p, c_i64, c_i, c_i, c_i, c_p, c_p, c_p, c_i64, c_p, c_p],
     "rh_cross_bwd": [c_p, c_i64, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_i64, c_p, c_i64, c_p, c_p, c_p],
     "rh_colstats": [c_p, c_i64, c_i64, c_i, c_p, c_p, c_p, c_p, c_p, c_f, c_p],

@@ -20,6 +20,10 @@ cuda_graph = _flag("RECHUB_B200_CUDA_GRAPH", False)
 # Also capture the sharded (multi-GPU) step, NCCL collectives included, into the graph.
 dist_cuda_graph = _flag("RECHUB_B200_DIST_CUDA_GRAPH", True)
 
+# Sharded front end: exchange ids / rows / row-gradients with the engine's own kernels over NVLink peer memory
+# (torch symmetric memory) instead of NCCL all-to-alls.
+p2p_exchange = _flag("RECHUB_B200_P2P", True)
+
 # Check the device-side out-of-range-id flag after every forward (one D2H sync per step).  When off the
 # flag is checked at the trainer's existing sync points (``loss.item()``) and by ``check_errors()``.
 eager_bounds_check = _flag("RECHUB_B200_EAGER_BOUNDS_CHECK", False)

@@ -45,8 +45,166 @@ class _AllToAllRows(torch.autograd.Function):
         return out, None
 
 
+class P2PExchange(object):
+    """Peer-mapped (symmetric-memory) buffers of one sharded front-end plan + the cross-GPU barrier that orders them.
+
+    ids   (W, b, fmax) int64   on owner r: block s = ids of rank s's samples for r's fields      (written by rank s)
+    rows  (W, b, fmax*dim) f32 on rank s : block r = rows of owner r's fields for s's samples     (written by owner r's gather kernel)
+    drows (W, b, fmax*dim) f32 on owner r: block s = gradients of those rows from rank s          (RED by rank s's backward kernel)
+    """
+
+    def __init__(self, group, device, W, b, fmax, dim):
+        import torch.distributed._symmetric_memory as symm
+        self.ids = symm.empty(W * b * fmax, dtype=torch.int64, device=device)
+        self.rows = symm.empty(W * b * fmax * dim, dtype=torch.float32, device=device)
+        self.drows = symm.empty(W * b * fmax * dim, dtype=torch.float32, device=device)
+        self.h_ids = symm.rendezvous(self.ids, group)
+        self.h_rows = symm.rendezvous(self.rows, group)
+        self.h_drows = symm.rendezvous(self.drows, group)
+        self.ids_ptrs = [int(p) for p in self.h_ids.buffer_ptrs]
+        self.rows_ptrs = [int(p) for p in self.h_rows.buffer_ptrs]
+        self.drows_ptrs = [int(p) for p in self.h_drows.buffer_ptrs]
+        self.drows.zero_()
+        self.ids_local = torch.zeros_like(self.ids)
+
+    def barrier(self):
+        self.h_rows.barrier(channel=0)
+
+
+class _ShardedP2P(torch.autograd.Function):
+    """The sharded front end as ONE autograd node, all exchanges done by the engine's own kernels over NVLink peer memory:
+
+      forward   rh_ids_scatter (ids -> owners)  | barrier | rh_fields_fwd_p2p (owner gathers, rows land in the samples' GPUs)
+                | barrier | rh_fields_fwd on the received rows (unpack + dense columns + FM + LR)
+      backward  rh_fields_bwd with peer table_grad pointers (row gradients RED into the owners' buffers over NVLink)
+                | barrier | rh_fields_bwd on the owner (scatter-add into its tables) | barrier
+    """
+
+    @staticmethod
+    def forward(ctx, front, p, x, fm_features, lr_w, lr_b, *owned_weights):
+        from . import _lib, ops, table as _table
+        L = _lib.lib()
+        ex, W, me = p["ex"], front.world, front.rank
+        sparse, dense, fmax, dim = p["sparse"], p["dense"], p["fmax"], p["dim"]
+        b = p["batch"]
+        dev = front.device
+        st = ops.stream_ptr()
+        err = _lib.err_flag(dev).data_ptr()
+        import ctypes
+        # F1: my samples' ids -> the owners
+        cols = (ops.RhField * len(p["slots"]))()  # slots are sorted by (owner, slot)
+        col_dest = (ctypes.c_int32 * len(p["slots"]))()
+        for n, (r, k, f) in enumerate(p["slots"]):
+            ids = ops._as_ids(x[f.name])
+            cols[n].ids = ids.data_ptr()
+            cols[n].id_stride = ids.stride(0) if ids.shape[0] > 1 else 1
+            cols[n].ids_are_i32 = int(ids.dtype == torch.int32)
+            col_dest[n] = r
+        bases = (ctypes.c_void_p * W)(*[ex.ids_ptrs[r] + me * b * fmax * 8 for r in range(W)])
+        ops.check(L.rh_ids_scatter(cols, len(p["slots"]), col_dest, b, bases, W, fmax, st), "rh_ids_scatter")
+        ex.barrier()
+        # F3: owner-side gather over the global batch, rows stored straight into the destination GPUs' tiles.  The ids are
+        # snapshotted locally first: peers may refill ex.ids for the next step while this rank's backward still needs them.
+        mine = p["by_owner"][me]
+        ex.ids_local.copy_(ex.ids)
+        ids_g = ex.ids_local.view(W * b, fmax)
+        orefs = []
+        for k, f in enumerate(mine):
+            tbl = front.layer.table_of(f)
+            orefs.append(ops.FieldRef(tbl.weight, ids_g[:, k], tbl.padding_idx, k * dim, -1))
+        if orefs:
+            dest = (ctypes.c_void_p * W)(*[ex.rows_ptrs[s] + me * b * fmax * dim * 4 for s in range(W)])
+            ops.check(L.rh_fields_fwd_p2p(ops._field_array(orefs), len(orefs), dim, W * b, dest, W, b, fmax * dim, err, st), "rh_fields_fwd_p2p")
+        ex.barrier()
+        # F5: sample side — the received rows are the "table"
+        table = ex.rows.view(W * b * fmax, dim)
+        fm_slot = {f.name: j for j, f in enumerate(fm_features)} if fm_features else {}
+        srefs, col = [], 0
+        for f, rid in zip(sparse, p["row_ids"]):
+            srefs.append(ops.FieldRef(table, rid, None, col, fm_slot.get(f.name, -1), is_act=True))
+            col += dim
+        drefs = []
+        for f in dense:
+            v = x[f.name]
+            if v.dtype not in ops._DENSE_CODES:
+                v = v.float()
+            width = 1 if v.dim() == 1 else v.shape[1]
+            drefs.append(ops.DenseRef(v, width, col))
+            col += width
+        width_total = col
+        ld = ops._pad4(width_total)
+        tile = torch.empty((b, ld), dtype=torch.float32, device=dev)
+        want_fm = bool(fm_features)
+        y_fm = torch.empty(b, dtype=torch.float32, device=dev) if want_fm else None
+        y_lr = torch.empty(b, dtype=torch.float32, device=dev) if (want_fm and lr_w is not None) else None
+        fsum = torch.empty((b, dim), dtype=torch.float32, device=dev) if want_fm else None
+        ops.check(
+            L.rh_fields_fwd(ops._field_array(srefs), len(srefs), dim, ops._dense_array(drefs) if drefs else None, len(drefs), b, tile.data_ptr(), ld, ops.ptr(lr_w) if y_lr is not None else None,
+                            ops.ptr(lr_b) if y_lr is not None else None, ops.ptr(y_fm), ops.ptr(y_lr), ops.ptr(fsum), err, st), "rh_fields_fwd")
+        ctx.front, ctx.p, ctx.srefs, ctx.orefs, ctx.ld, ctx.want_lr = front, p, srefs, orefs, ld, y_lr is not None
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(tile, fsum, lr_w)
+        return (tile if ld == width_total else tile[:, :width_total]), y_fm, y_lr
+
+    @staticmethod
+    def backward(ctx, d_tile, d_yfm, d_ylr):
+        from . import _lib, ops, table as _table
+        L = _lib.lib()
+        front, p = ctx.front, ctx.p
+        ex, W, me = p["ex"], front.world, front.rank
+        fmax, dim, b = p["fmax"], p["dim"], p["batch"]
+        tile, fsum, lr_w = ctx.saved_tensors
+        dev = front.device
+        st = ops.stream_ptr()
+        err = _lib.err_flag(dev).data_ptr()
+        d_ld = 0
+        if d_tile is not None:
+            d_tile = ops._rowmajor(d_tile)
+            d_ld = d_tile.stride(0) if b > 1 else d_tile.shape[1]
+        d_yfm = d_yfm.contiguous() if d_yfm is not None else None
+        d_ylr = d_ylr.contiguous() if d_ylr is not None else None
+        d_lrw = d_lrb = None
+        if d_ylr is not None and lr_w is not None:
+            n = lr_w.numel()
+            buf = torch.zeros(ops._pad4(n) + 1, dtype=torch.float32, device=dev)
+            d_lrw, d_lrb = buf[:n].view_as(lr_w), buf[ops._pad4(n):ops._pad4(n) + 1]
+        # B1: gradients of the received rows go straight to their owners (vector RED over NVLink into drows[owner][me])
+        arr = ops._field_array(ctx.srefs)
+        owners = [front.owner_of(f) for f in p["sparse"]]
+        for n, r in enumerate(owners):
+            # the kernel indexes the gradient buffer with the FORWARD row id (r*b + i)*fmax + k; the owner's block for my
+            # samples starts at row me*b*fmax: shift the base so that both agree
+            arr[n].table_grad = ex.drows_ptrs[r] + (me - r) * b * fmax * dim * 4
+        has_fm = (d_yfm is not None or d_ylr is not None) and any(s.fm_slot >= 0 for s in ctx.srefs)
+        ops.check(
+            L.rh_fields_bwd(arr, len(ctx.srefs), dim, b, tile.data_ptr(), ctx.ld, ops.ptr(d_tile), d_ld, ops.ptr(d_yfm) if has_fm else None, ops.ptr(d_ylr) if has_fm else None,
+                            ops.ptr(lr_w) if has_fm else None, ops.ptr(fsum) if has_fm else None, ops.ptr(d_lrw) if has_fm else None, ops.ptr(d_lrb) if has_fm else None, err, st), "rh_fields_bwd")
+        ex.barrier()
+        # B3: the owner scatter-adds what every rank sent into its tables
+        if ctx.orefs:
+            targets = [_table.grad_target(r.weight) for r in ctx.orefs]
+            ops.check(
+                L.rh_fields_bwd(ops._field_array(ctx.orefs, [t[0] for t in targets]), len(ctx.orefs), dim, W * b, None, 0, ex.drows.data_ptr(), fmax * dim, None, None, None, None, None, None, err, st),
+                "rh_fields_bwd")
+            for r, (g, slot) in zip(ctx.orefs, targets):
+                if g is not None:
+                    _table.note_dirty(slot, r.ids)
+        ex.drows.zero_()  # ready for the next step's REDs: they can only start after the next forward's two barriers
+        return (None, None, None, None, d_lrw, d_lrb) + (None,) * len(ctx.orefs)
+
+
 class ShardedFront(object):
-    """Field-sharded replacement for ``EmbeddingLayer.forward`` (installed by :func:`attach`)."""
+    """Field-sharded replacement for ``EmbeddingLayer.forward`` (installed by :func:`attach`).
+
+    CUDA route per call (all launches static-shaped, graph-capturable):
+      1 kernel    pack my samples' ids per owner                       (index_select / stack)
+      NCCL        ids all-to-all
+      1 launch    owner-side ``rh_fields_fwd`` over the global batch   -> rows (W*b, fmax*dim)
+      NCCL        rows all-to-all (autograd Function; backward = the reverse exchange)
+      1 launch    sample-side ``rh_fields_fwd`` reading the RECEIVED rows as its table: unpacks them into the model's
+                  column order, appends the dense columns and (DeepFM) reduces FM + LR in the same pass
+    CPU route (gloo tests): the same data flow with stock torch ops.
+    """
 
     def __init__(self, layer, group, device):
         self.layer = layer
@@ -56,12 +214,14 @@ class ShardedFront(object):
         self.rank = dist.get_rank(group)
         self.owner = field_owners(list(layer.embed_dict.keys()), self.world)
         self._plans = {}
+        from . import config
+        self.use_p2p = device.type == "cuda" and config.p2p_exchange
 
     def owner_of(self, fea):
         return self.owner[fea.name if fea.shared_with is None else fea.shared_with]
 
-    def _plan(self, features):
-        key = tuple(id(f) for f in features)
+    def _plan(self, features, batch):
+        key = (tuple(id(f) for f in features), batch)
         p = self._plans.get(key)
         if p is None:
             sparse = [f for f in features if isinstance(f, (SparseFeature, SequenceFeature))]
@@ -72,56 +232,117 @@ class ShardedFront(object):
             dims = {f.embed_dim for f in sparse}
             if len(dims) > 1:
                 raise NotImplementedError("field sharding needs one embed_dim across the sharded features")
-            by_owner = [[f for f in sparse if self.owner_of(f) == r] for r in range(self.world)]
+            W = self.world
+            by_owner = [[f for f in sparse if self.owner_of(f) == r] for r in range(W)]
             fmax = max(len(b) for b in by_owner) if sparse else 0
-            # column permutation: position of each feature's block in the owner-grouped (padded) receive buffer
             dim = sparse[0].embed_dim if sparse else 0
-            cols = []
+            # received-row index of (sample i, feature f): rows are laid out (owner, sample, slot)
+            row_ids, cols = [], []
+            ar = torch.arange(batch, dtype=torch.int32, device=self.device)
             for f in sparse:
                 r = self.owner_of(f)
                 k = by_owner[r].index(f)
+                row_ids.append((r * batch + ar) * fmax + k)
                 base = (r * fmax + k) * dim
                 cols.extend(range(base, base + dim))
-            p = {"sparse": sparse, "dense": dense, "by_owner": by_owner, "fmax": fmax, "dim": dim, "cols": torch.tensor(cols, dtype=torch.long, device=self.device)}
+            p = {"sparse": sparse, "dense": dense, "by_owner": by_owner, "fmax": fmax, "dim": dim, "row_ids": row_ids, "batch": batch, "ex": None,
+                 "cols": torch.tensor(cols, dtype=torch.long, device=self.device), "slots": [(r, k, f) for r in range(W) for k, f in enumerate(by_owner[r])]}
             self._plans[key] = p
         return p
 
-    def forward(self, x, features, squeeze_dim):
-        p = self._plan(features)
+    def _pack_ids(self, x, p, b):
+        """(W, fmax, b) int64: chunk r = my samples' ids of the fields rank r owns (unused slots hold id 0)."""
+        W, fmax = self.world, p["fmax"]
+        ids = getattr(x, "ids", None)
+        if ids is not None and ids.dim() == 2 and ids.dtype == torch.int64:  # PackedColumns: one gather of the transposed block
+            sel = p.get("sel")
+            if sel is None:
+                pos = {n: j for j, n in enumerate(x.id_names)}
+                sel_list = [0] * (W * fmax)
+                for r, k, f in p["slots"]:
+                    sel_list[r * fmax + k] = pos[f.name]
+                sel = p["sel"] = torch.tensor(sel_list, dtype=torch.long, device=ids.device)
+            return ids.t().index_select(0, sel).view(W, fmax, b)
+        cols = [None] * (W * fmax)
+        for r, k, f in p["slots"]:
+            cols[r * fmax + k] = x[f.name].long()
+        filler = next(c for c in cols if c is not None)
+        return torch.stack([c if c is not None else filler for c in cols], dim=0).view(W, fmax, b)
+
+    def run(self, x, features, fm_features=None, lr=None):
+        """-> (tile (b, width) with sparse block first and dense appended, y_fm, y_lr)."""
+        first = next(f for f in features if not isinstance(f, DenseFeature)) if any(not isinstance(f, DenseFeature) for f in features) else None
+        if first is None:
+            return self.layer._forward_local(x, features, squeeze_dim=True), None, None
+        b = x[first.name].shape[0]
+        p = self._plan(features, b)
         sparse, dense, W, fmax, dim = p["sparse"], p["dense"], self.world, p["fmax"], p["dim"]
-        parts = []
-        if sparse:
-            b = x[sparse[0].name].shape[0]
-            # 1) ids all-to-all: chunk r = my samples' ids of the fields rank r owns, padded to fmax columns
-            send = torch.zeros((W, fmax, b), dtype=torch.long, device=self.device)
-            for r in range(W):
-                for k, f in enumerate(p["by_owner"][r]):
-                    send[r, k] = x[f.name].long()
-            recv = torch.empty_like(send)
-            dist.all_to_all_single(recv, send, group=self.group)  # recv[s, k, i] = id of sample i of rank s for my k-th field
+        cuda = self.device.type == "cuda"
+        if cuda and self.use_p2p and dim % 4 == 0 and W <= 8:
+            if p["ex"] is None:
+                p["ex"] = P2PExchange(self.group, self.device, W, b, fmax, dim)
             mine = p["by_owner"][self.rank]
-            # 2) owner-local fused gather over the global batch (W*b samples) of my fields only
+            owned = [self.layer.table_of(f).weight for f in mine]
+            return _ShardedP2P.apply(self, p, x, fm_features, lr[0] if lr else None, lr[1] if lr else None, *owned)
+        send = self._pack_ids(x, p, b)
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=self.group)  # recv[s, k, i] = id of sample i of rank s for my k-th field
+        mine = p["by_owner"][self.rank]
+        # owner side: fused gather of MY fields over the global batch (W*b samples)
+        ids_g = recv.permute(0, 2, 1).contiguous().view(W * b, fmax)  # [global sample, my k-th field]: one strided column per field
+        xg = {f.name: ids_g[:, k] for k, f in enumerate(mine)}
+        if cuda:
+            from . import ops
+            rows = torch.empty((W * b, fmax * dim), dtype=torch.float32, device=self.device)
             if mine:
-                xg = {f.name: recv[:, k, :].reshape(W * b) for k, f in enumerate(mine)}
-                rows = self.layer._forward_local(xg, mine, squeeze_dim=True)  # (W*b, len(mine)*dim)
-                if len(mine) < fmax:
-                    rows = torch.nn.functional.pad(rows, (0, (fmax - len(mine)) * dim))
-            else:
-                rows = torch.zeros((W * b, fmax * dim), dtype=torch.float32, device=self.device)
-            # 3) rows all-to-all back to the samples' ranks (backward: tile gradients travel the other way)
-            got = _AllToAllRows.apply(rows.view(W, b, fmax * dim), self.group)  # got[r] = rank r's fields for MY samples
-            grouped = got.permute(1, 0, 2).reshape(b, W * fmax * dim)
-            parts.append(grouped.index_select(1, p["cols"]))  # the model's column order
-        if squeeze_dim:
+                oplan = self.layer.build_plan(xg, mine, with_dense=False)
+                oplan.out_tile = rows
+                oplan.tile_width = fmax * dim  # the whole buffer travels; slots >= len(mine) are never read on the other side
+                rows = ops.fused_tile(oplan)[0]
+        else:
+            rows = self.layer._forward_local(xg, mine, squeeze_dim=True) if mine else torch.zeros((W * b, 0))
+            if len(mine) < fmax:
+                rows = torch.nn.functional.pad(rows, (0, (fmax - len(mine)) * dim))
+        got = _AllToAllRows.apply(rows.view(W, b, fmax * dim), self.group)  # got[r] = rank r's fields for MY samples
+        if cuda:
+            from . import ops
+            table = got.view(W * b * fmax, dim)
+            plan = ops.TilePlan(b, self.device)
+            fm_slot = {f.name: j for j, f in enumerate(fm_features)} if fm_features else {}
+            col = 0
+            for f, rid in zip(sparse, p["row_ids"]):
+                plan.fields.append(ops.FieldRef(table, rid, None, col, fm_slot.get(f.name, -1), is_act=True))
+                col += dim
             for f in dense:
-                v = x[f.name].float()
-                parts.append(v if v.dim() > 1 else v.unsqueeze(1))
-            if not parts:
+                v = x[f.name]
+                if v.dtype not in ops._DENSE_CODES:
+                    v = v.float()
+                width = 1 if v.dim() == 1 else v.shape[1]
+                plan.dense.append(ops.DenseRef(v, width, col))
+                col += width
+            plan.tile_width = col
+            plan.act_table = table
+            if fm_features:
+                plan.n_fm, plan.fm_dim, plan.want_fm, plan.want_lr = len(fm_features), dim, True, lr is not None
+            return ops.fused_tile(plan, lr[0] if lr else None, lr[1] if lr else None)
+        grouped = got.permute(1, 0, 2).reshape(b, W * fmax * dim)
+        parts = [grouped.index_select(1, p["cols"])]
+        for f in dense:
+            v = x[f.name].float()
+            parts.append(v if v.dim() > 1 else v.unsqueeze(1))
+        return (torch.cat(parts, dim=1) if len(parts) > 1 else parts[0]), None, None
+
+    def forward(self, x, features, squeeze_dim):
+        n_sparse = sum(1 for f in features if not isinstance(f, DenseFeature))
+        if squeeze_dim:
+            if not features:
                 raise ValueError("The input features can note be empty")
-            return torch.cat(parts, dim=1) if len(parts) > 1 else parts[0]
-        if not sparse:
+            return self.run(x, features)[0]
+        if n_sparse == 0:
             raise ValueError("If keep the original shape:[batch_size, num_features, embed_dim], expected %s in feature list, got %s" % ("SparseFeatures", features))
-        return parts[0].unflatten(1, (len(sparse), dim))
+        only_sparse = [f for f in features if not isinstance(f, DenseFeature)]
+        tile = self.run(x, only_sparse)[0]
+        return tile.unflatten(1, (n_sparse, only_sparse[0].embed_dim))
 
 
 class DistEngine(object):
@@ -159,22 +380,38 @@ class DistEngine(object):
             if b.dtype.is_floating_point:
                 dist.broadcast(b.data, src=0, group=self.group)
         n = sum(p.numel() for p in self.dense_params)
+        self.n_dense = n
         self.flat = torch.zeros(n + 1, dtype=torch.float32, device=self.device)  # [+1]: the loss rides along
-        off = 0
+        self.views, off = [], 0
         for p in self.dense_params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
 
     # -- one training step -------------------------------------------------------------------------------------
     def train_step(self, trainer, x_dict, y):
         loss = trainer._loss(x_dict, y)
-        self.flat.zero_()  # dense grads are views of this bucket
         for p in self.owned:
             p.grad = None
+        for p in self.dense_params:
+            p.grad = None  # autograd then hands over fresh gradient tensors (no accumulate kernels)
         (loss / self.world).backward()
-        self.flat[-1] = loss.detach() / self.world
-        dist.all_reduce(self.flat, group=self.group)  # SUM over ranks of (local grad / world) = gradient of the global-batch mean
-        trainer.optimizer.step()
+        # ONE bucket: [dense gradients ..., loss]; a parameter that got no gradient contributes zeros
+        pieces = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in self.dense_params]
+        pieces.append((loss.detach() / self.world).reshape(1))
+        torch.cat(pieces, out=self.flat)
+        work = dist.all_reduce(self.flat, group=self.group, async_op=True)  # SUM of (local grad / world) = grad of the global-batch mean
+        opt = trainer.optimizer
+        split = hasattr(opt, "rowwise") and hasattr(opt, "dense_engine")
+        if split:
+            opt.rowwise.set_lr(float(opt.dense.param_groups[0]["lr"]))
+            opt.rowwise.step()  # the owned tables' update does not need the all-reduce: it overlaps with it
+        work.wait()
+        for p, v in zip(self.dense_params, self.views):
+            p.grad = v
+        if split:
+            opt.dense_engine.step()
+        else:
+            opt.step()
         return self.flat[-1]  # global mean loss
 
     def full_state_dict(self):

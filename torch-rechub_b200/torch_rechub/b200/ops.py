@@ -81,9 +81,10 @@ def table_lookup(tbl, ids):
 # =====================================================================================================
 class FieldRef(object):
     """One SparseFeature column of a plan."""
-    __slots__ = ("weight", "ids", "vocab", "dim", "padding_idx", "tile_col", "fm_slot")
+    __slots__ = ("weight", "ids", "vocab", "dim", "padding_idx", "tile_col", "fm_slot", "is_act")
 
-    def __init__(self, weight, ids, padding_idx, tile_col, fm_slot):
+    def __init__(self, weight, ids, padding_idx, tile_col, fm_slot, is_act=False):
+        self.is_act = is_act  # the "table" is an activation (rows received from peer GPUs): its gradient is returned, not stored
         self.weight = weight
         self.ids = ids
         self.vocab, self.dim = weight.shape
@@ -130,10 +131,14 @@ class TilePlan(object):
         self.want_fm = False
         self.want_lr = False
         self.by_name = {}
+        self.act_table = None  # (rows, dim) activation used as the table of every field flagged is_act
+        self.out_tile = None  # optional preallocated (batch, ld) output buffer
 
     def weights(self):
         seen, out = set(), []
         for r in list(self.fields) + list(self.seqs):
+            if getattr(r, "is_act", False):
+                continue
             if id(r.weight) not in seen:
                 seen.add(id(r.weight))
                 out.append(r.weight)
@@ -186,7 +191,7 @@ class _FusedTile(torch.autograd.Function):
     """tile, y_fm, y_lr = front(plan).  Inputs carried for autograd connectivity only: lr weight/bias, table weights."""
 
     @staticmethod
-    def forward(ctx, plan, lr_weight, lr_bias, *weights):
+    def forward(ctx, plan, lr_weight, lr_bias, act_table, *weights):
         L = _lib.lib()
         dev = plan.device
         B = plan.batch
@@ -195,8 +200,12 @@ class _FusedTile(torch.autograd.Function):
         tile = None
         ld = 0
         if plan.tile_width > 0:
-            ld = _pad4(plan.tile_width)
-            tile = torch.empty((B, ld), dtype=torch.float32, device=dev)  # columns >= tile_width are padding, never read
+            if plan.out_tile is not None:
+                tile = plan.out_tile
+                ld = tile.stride(0)
+            else:
+                ld = _pad4(plan.tile_width)
+                tile = torch.empty((B, ld), dtype=torch.float32, device=dev)  # columns >= tile_width are padding, never read
         y_fm = torch.empty(B, dtype=torch.float32, device=dev) if plan.want_fm else None
         y_lr = torch.empty(B, dtype=torch.float32, device=dev) if plan.want_lr else None
         fsum = torch.empty((B, plan.fm_dim), dtype=torch.float32, device=dev) if plan.want_fm else None
@@ -230,7 +239,7 @@ class _FusedTile(torch.autograd.Function):
         ctx.save_for_backward(tile, fsum, lr_weight)
         tile_view = None
         if tile is not None:
-            tile_view = tile if ld == plan.tile_width else tile[:, :plan.tile_width]
+            tile_view = tile if tile.shape[1] == plan.tile_width else tile[:, :plan.tile_width]
         return tile_view, y_fm, y_lr
 
     @staticmethod
@@ -256,8 +265,11 @@ class _FusedTile(torch.autograd.Function):
             d_lrw = buf[:n].view_as(lr_weight)
             d_lrb = buf[_pad4(n):_pad4(n) + 1]
 
+        d_act = None
+        if plan.act_table is not None:
+            d_act = torch.zeros_like(plan.act_table)  # every received row is written once by the scatter below
         for dim, refs in plan.field_groups():
-            targets = [_table.grad_target(r.weight) for r in refs]
+            targets = [(d_act, None) if r.is_act else _table.grad_target(r.weight) for r in refs]
             grads = [t[0] for t in targets]
             has_fm = any(r.fm_slot >= 0 for r in refs) and (d_yfm is not None or d_ylr is not None)
             if d_tile is None and not has_fm:
@@ -267,7 +279,7 @@ class _FusedTile(torch.autograd.Function):
                                 ptr(d_ylr) if has_fm else None, ptr(lr_weight) if has_fm else None, ptr(fsum) if has_fm else None, ptr(d_lrw) if has_fm else None,
                                 ptr(d_lrb) if has_fm else None, err, st), "rh_fields_bwd")
             for r, (g, slot) in zip(refs, targets):
-                if g is not None:
+                if g is not None and not r.is_act:
                     _table.note_dirty(slot, r.ids)
         if d_tile is not None:
             for s in plan.seqs:
@@ -279,7 +291,7 @@ class _FusedTile(torch.autograd.Function):
                     L.rh_seq_pool_bwd(g.data_ptr(), s.vocab, s.dim, s.padding_idx, ids.data_ptr(), int(ids.dtype == torch.int32), B, ids.shape[1], s.mode, s.mask_id, d_tile.data_ptr() + 4 * s.tile_col, d_ld, err, st),
                     "rh_seq_pool_bwd")
                 _table.note_dirty(slot, ids)
-        return (None, d_lrw, d_lrb) + (None,) * len(plan.weights())
+        return (None, d_lrw, d_lrb, d_act) + (None,) * len(plan.weights())
 
 
 def fused_tile(plan, lr_weight=None, lr_bias=None):
@@ -288,7 +300,7 @@ def fused_tile(plan, lr_weight=None, lr_bias=None):
     for w in ws:
         if w.dtype != torch.float32:
             raise NotImplementedError("the sm_100a engine keeps tables in fp32 (got %s)" % w.dtype)
-    return _FusedTile.apply(plan, lr_weight, lr_bias, *ws)
+    return _FusedTile.apply(plan, lr_weight, lr_bias, plan.act_table, *ws)
 
 
 # =====================================================================================================

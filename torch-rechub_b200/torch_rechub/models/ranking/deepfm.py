@@ -84,7 +84,17 @@ class DeepFM(torch.nn.Module):
         return input_deep.index_select(1, idx).unflatten(1, (n, dim))
 
     def forward(self, x):
-        if self.embedding._dist is not None:
+        front = self.embedding._dist
+        if front is not None:
+            from ...basic.features import DenseFeature
+            deep_names = {f.name for f in self.deep_features if not isinstance(f, DenseFeature)}
+            dim = self.fm_features[0].embed_dim if self.fm_features else 0
+            fusable = (front.device.type == "cuda" and self.fm_features and all(f.name in deep_names and f.embed_dim == dim for f in self.fm_features) and dim % 4 == 0 and
+                       len({f.name for f in self.fm_features}) == len(self.fm_features) <= 64)
+            if fusable:  # ONE exchange; the receiving kernel unpacks the rows and reduces FM + LR in the same pass
+                input_deep, y_fm, y_linear = front.run(x, self.deep_features, fm_features=self.fm_features, lr=(self.linear.fc.weight, self.linear.fc.bias))
+                y = y_linear.unsqueeze(1) + y_fm.unsqueeze(1) + self.mlp(input_deep)
+                return torch.sigmoid(y.squeeze(1))
             input_deep = self.embedding(x, self.deep_features, squeeze_dim=True)
             input_fm = self._fm_from_deep(input_deep) if self.fm_features else None
             if input_fm is None:
