@@ -187,6 +187,7 @@ int rh_rowwise_update(float* table, float* table_grad, float* state1, float* sta
                       int32_t* stamp, int vocab, int dim,
                       const void* ids, int ids_are_i32, int64_t n,
                       int kind, const int32_t* step_dev, const float* lr_dev, const float* bias_corr_dev,
+                      int64_t state_row_stride,
                       float beta1, float beta2, float eps, float weight_decay, void* stream);
 /* ++*step_dev, and (Adam) bias_corr_dev[0] = 1 - beta1^step, bias_corr_dev[1] = sqrt(1 - beta2^step) in fp64, once
  * per optimiser step instead of once per thread.  bias_corr_dev: device float[2], may be NULL for SGD/Adagrad. */
@@ -194,12 +195,14 @@ int rh_opt_advance(int32_t* step_dev, float* bias_corr_dev, float beta1, float b
 
 /* The same update for ALL tables of one batch in a single launch (grid.y = field): fields[i] gives
  * table_grad / ids / id_stride / vocab of table i; tables / state1 / state2 / stamp are host arrays
- * of n_fields device pointers.  Needs dim % 4 == 0.  This is the optimiser half of the
+ * of n_fields device pointers.  Needs dim % 4 == 0.  state_row_stride: floats between consecutive rows of state1 / state2
+ * (2*dim when m and v are interleaved as one 128-byte record per row — one DRAM burst instead of two random ones).  This is the optimiser half of the
  * "backward sparse-grad scatter-add into the tables" (BASELINE.json north_star). */
 int rh_fields_rowwise_update(const rh_field* fields, int n_fields, int dim, int batch,
                              float* const* tables, float* const* state1, float* const* state2,
                              int32_t* const* stamp, int kind,
                              const int32_t* step_dev, const float* lr_dev, const float* bias_corr_dev,
+                             int64_t state_row_stride,
                              float beta1, float beta2, float eps, float weight_decay, void* stream);
 
 /* table_grad[ids] = 0 for all tables of one batch in a single launch (sparse zero_grad). */

@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(256) rowwise_update_kernel(float* __restrict__
                                                              float* __restrict__ st2, int32_t* __restrict__ stamp, int vocab, int dim,
                                                              const void* __restrict__ ids, bool is_i32, int64_t n, OptArgs a,
                                                              const int32_t* __restrict__ step_dev, const float* __restrict__ lr_dev,
-                                                             const float* __restrict__ bc_dev, bool vec, int G) {
+                                                             const float* __restrict__ bc_dev, bool vec, int G, int64_t sstride) {
   // G (power of two <= 32) consecutive threads own one entry of `ids`.  The group's lane 0 claims
   // the row through stamp[id] (first claimant of this step wins: duplicates of an id are skipped)
   // and broadcasts the verdict; the owner group then updates the row's `lanes` 16-byte (or scalar) slots.
@@ -295,24 +295,24 @@ __global__ void __launch_bounds__(256) rowwise_update_kernel(float* __restrict__
         *reinterpret_cast<float4*>(gp) = f4_zero();
         float4 w = *reinterpret_cast<float4*>(wp);
         float4 m = f4_zero(), v = f4_zero();
-        if (a.kind != 0) m = *reinterpret_cast<float4*>(st1 + id * dim + 4 * q);
-        if (a.kind == 1) v = *reinterpret_cast<float4*>(st2 + id * dim + 4 * q);
+        if (a.kind != 0) m = *reinterpret_cast<float4*>(st1 + id * sstride + 4 * q);
+        if (a.kind == 1) v = *reinterpret_cast<float4*>(st2 + id * sstride + 4 * q);
         w.x = opt_update(w.x, gr.x, &m.x, &v.x, a, lr, bc1, bc2s);
         w.y = opt_update(w.y, gr.y, &m.y, &v.y, a, lr, bc1, bc2s);
         w.z = opt_update(w.z, gr.z, &m.z, &v.z, a, lr, bc1, bc2s);
         w.w = opt_update(w.w, gr.w, &m.w, &v.w, a, lr, bc1, bc2s);
         *reinterpret_cast<float4*>(wp) = w;
-        if (a.kind != 0) *reinterpret_cast<float4*>(st1 + id * dim + 4 * q) = m;
-        if (a.kind == 1) *reinterpret_cast<float4*>(st2 + id * dim + 4 * q) = v;
+        if (a.kind != 0) *reinterpret_cast<float4*>(st1 + id * sstride + 4 * q) = m;
+        if (a.kind == 1) *reinterpret_cast<float4*>(st2 + id * sstride + 4 * q) = v;
       } else {
-        const int64_t o = id * dim + q;
+        const int64_t o = id * dim + q, so = id * sstride + q;
         const float gr = grad[o];
         grad[o] = 0.f;
-        float m = a.kind != 0 ? st1[o] : 0.f;
-        float v = a.kind == 1 ? st2[o] : 0.f;
+        float m = a.kind != 0 ? st1[so] : 0.f;
+        float v = a.kind == 1 ? st2[so] : 0.f;
         table[o] = opt_update(table[o], gr, &m, &v, a, lr, bc1, bc2s);
-        if (a.kind != 0) st1[o] = m;
-        if (a.kind == 1) st2[o] = v;
+        if (a.kind != 0) st1[so] = m;
+        if (a.kind == 1) st2[so] = v;
       }
     }
   }
@@ -335,8 +335,10 @@ struct MultiP {
 __global__ void __launch_bounds__(128) fields_rowwise_update_kernel(const __grid_constant__ MultiP p, OptArgs a,
                                                                     const int32_t* __restrict__ step_dev,
                                                                     const float* __restrict__ lr_dev,
-                                                                    const float* __restrict__ bc_dev, int G) {
-  // same claim protocol as rowwise_update_kernel; 16-byte lanes only (dim % 4 == 0)
+                                                                    const float* __restrict__ bc_dev, int G, int64_t state_stride) {
+  // same claim protocol as rowwise_update_kernel; 16-byte lanes only (dim % 4 == 0).
+  // Latency shape: ids -> {claim atomic, g, w, m, v loads} -> stores.  The row loads are issued BEFORE the claim's verdict
+  // is known (duplicates are rare and a wasted read is harmless), which removes one dependent DRAM round trip.
   const int f = blockIdx.y;
   const int step = *step_dev;
   const float lr = *lr_dev;
@@ -349,29 +351,30 @@ __global__ void __launch_bounds__(128) fields_rowwise_update_kernel(const __grid
   int64_t id = -1;
   if (r < p.batch) id = load_id(p.ids[f], r * p.id_stride[f], p.is_i32[f] != 0);
   const bool valid = (uint64_t)id < (uint64_t)p.vocab[f];
+  const bool lane_on = valid && g < lanes;  // G == pow2_ceil(lanes) <= 32: one 16-byte slot per lane
+  float* gp = p.grad[f] + id * dim + 4 * g;
+  float* wp = p.table[f] + id * dim + 4 * g;
+  float* s1p = a.kind != 0 ? p.st1[f] + id * state_stride + 4 * g : nullptr;
+  float* s2p = a.kind == 1 ? p.st2[f] + id * state_stride + 4 * g : nullptr;
+  float4 gr = f4_zero(), w = f4_zero(), m = f4_zero(), v = f4_zero();
+  if (lane_on) {
+    gr = *reinterpret_cast<const float4*>(gp);
+    w = *reinterpret_cast<const float4*>(wp);
+    if (a.kind != 0) m = *reinterpret_cast<const float4*>(s1p);
+    if (a.kind == 1) v = *reinterpret_cast<const float4*>(s2p);
+  }
   int old = step;
   if (valid && g == 0) old = atomicExch(p.stamp[f] + id, step);
   old = __shfl_sync(0xffffffffu, old, lane & ~(G - 1));
-  if (!valid || old == step) return;
-  float* table = p.table[f];
-  float* grad = p.grad[f];
-  for (int q = g; q < lanes; q += G) {
-    float* gp = grad + id * dim + 4 * q;
-    float* wp = table + id * dim + 4 * q;
-    float4 gr = *reinterpret_cast<float4*>(gp);
-    *reinterpret_cast<float4*>(gp) = f4_zero();
-    float4 w = *reinterpret_cast<float4*>(wp);
-    float4 m = f4_zero(), v = f4_zero();
-    if (a.kind != 0) m = *reinterpret_cast<float4*>(p.st1[f] + id * dim + 4 * q);
-    if (a.kind == 1) v = *reinterpret_cast<float4*>(p.st2[f] + id * dim + 4 * q);
-    w.x = opt_update(w.x, gr.x, &m.x, &v.x, a, lr, bc1, bc2s);
-    w.y = opt_update(w.y, gr.y, &m.y, &v.y, a, lr, bc1, bc2s);
-    w.z = opt_update(w.z, gr.z, &m.z, &v.z, a, lr, bc1, bc2s);
-    w.w = opt_update(w.w, gr.w, &m.w, &v.w, a, lr, bc1, bc2s);
-    *reinterpret_cast<float4*>(wp) = w;
-    if (a.kind != 0) *reinterpret_cast<float4*>(p.st1[f] + id * dim + 4 * q) = m;
-    if (a.kind == 1) *reinterpret_cast<float4*>(p.st2[f] + id * dim + 4 * q) = v;
-  }
+  if (!lane_on || old == step) return;
+  *reinterpret_cast<float4*>(gp) = f4_zero();
+  w.x = opt_update(w.x, gr.x, &m.x, &v.x, a, lr, bc1, bc2s);
+  w.y = opt_update(w.y, gr.y, &m.y, &v.y, a, lr, bc1, bc2s);
+  w.z = opt_update(w.z, gr.z, &m.z, &v.z, a, lr, bc1, bc2s);
+  w.w = opt_update(w.w, gr.w, &m.w, &v.w, a, lr, bc1, bc2s);
+  *reinterpret_cast<float4*>(wp) = w;
+  if (a.kind != 0) *reinterpret_cast<float4*>(s1p) = m;
+  if (a.kind == 1) *reinterpret_cast<float4*>(s2p) = v;
 }
 
 __global__ void __launch_bounds__(128) fields_zero_kernel(const __grid_constant__ MultiP p) {
@@ -493,21 +496,23 @@ extern "C" int rh_seq_pool_bwd(float* table_grad, int vocab, int dim, int paddin
 
 extern "C" int rh_rowwise_update(float* table, float* table_grad, float* state1, float* state2, int32_t* stamp, int vocab, int dim,
                                  const void* ids, int ids_are_i32, int64_t n, int kind, const int32_t* step_dev, const float* lr_dev,
-                                 const float* bias_corr_dev, float beta1, float beta2, float eps, float weight_decay, void* stream) {
+                                 const float* bias_corr_dev, int64_t state_row_stride, float beta1, float beta2, float eps, float weight_decay,
+                                 void* stream) {
   RH_REQUIRE(table && table_grad && stamp && ids && step_dev && lr_dev, RH_ERR_INVALID_ARG, "rh_rowwise_update: NULL pointer");
+  RH_REQUIRE(state_row_stride >= dim, RH_ERR_INVALID_ARG, "rh_rowwise_update: state_row_stride < dim");
   RH_REQUIRE(kind != 1 || bias_corr_dev != nullptr, RH_ERR_INVALID_ARG, "rh_rowwise_update: Adam needs bias_corr_dev");
   RH_REQUIRE(kind >= 0 && kind <= 2, RH_ERR_INVALID_ARG, "rh_rowwise_update: kind %d unknown", kind);
   RH_REQUIRE(kind == 0 || state1 != nullptr, RH_ERR_INVALID_ARG, "rh_rowwise_update: state1 required");
   RH_REQUIRE(kind != 1 || state2 != nullptr, RH_ERR_INVALID_ARG, "rh_rowwise_update: state2 required for Adam");
   RH_REQUIRE(vocab > 0 && dim > 0 && n >= 0, RH_ERR_INVALID_ARG, "rh_rowwise_update: bad sizes");
   if (n == 0) return RH_OK;
-  const bool vec = dim % 4 == 0 && aligned16r(table) && aligned16r(table_grad) && (state1 == nullptr || aligned16r(state1)) &&
-                   (state2 == nullptr || aligned16r(state2));
+  const bool vec = dim % 4 == 0 && state_row_stride % 4 == 0 && aligned16r(table) && aligned16r(table_grad) &&
+                   (state1 == nullptr || aligned16r(state1)) && (state2 == nullptr || aligned16r(state2));
   OptArgs a{kind, beta1, beta2, eps, weight_decay};
   int G = pow2_ceil(vec ? dim / 4 : dim);
   if (G > 32) G = 32;
   rowwise_update_kernel<<<grid_for(n * G, 256), 256, 0, (cudaStream_t)stream>>>(table, table_grad, state1, state2, stamp, vocab, dim, ids,
-                                                                                ids_are_i32 != 0, n, a, step_dev, lr_dev, bias_corr_dev, vec, G);
+                                                                                ids_are_i32 != 0, n, a, step_dev, lr_dev, bias_corr_dev, vec, G, state_row_stride);
   RH_LAUNCH_CHECK();
   return RH_OK;
 }
@@ -551,8 +556,9 @@ static int pack_multi(rh::MultiP& p, const rh_field* fields, int n_fields, int d
 
 extern "C" int rh_fields_rowwise_update(const rh_field* fields, int n_fields, int dim, int batch, float* const* tables,
                                         float* const* state1, float* const* state2, int32_t* const* stamp, int kind,
-                                        const int32_t* step_dev, const float* lr_dev, const float* bias_corr_dev, float beta1,
-                                        float beta2, float eps, float weight_decay, void* stream) {
+                                        const int32_t* step_dev, const float* lr_dev, const float* bias_corr_dev, int64_t state_row_stride,
+                                        float beta1, float beta2, float eps, float weight_decay, void* stream) {
+  RH_REQUIRE(state_row_stride >= dim && state_row_stride % 4 == 0, RH_ERR_INVALID_ARG, "rh_fields_rowwise_update: state_row_stride %lld", (long long)state_row_stride);
   RH_REQUIRE(kind != 1 || bias_corr_dev != nullptr, RH_ERR_INVALID_ARG, "rh_fields_rowwise_update: Adam needs bias_corr_dev");
   RH_REQUIRE(kind >= 0 && kind <= 2, RH_ERR_INVALID_ARG, "rh_fields_rowwise_update: kind %d unknown", kind);
   RH_REQUIRE(step_dev && lr_dev, RH_ERR_INVALID_ARG, "rh_fields_rowwise_update: step/lr NULL");
@@ -571,7 +577,7 @@ extern "C" int rh_fields_rowwise_update(const rh_field* fields, int n_fields, in
   OptArgs a{kind, beta1, beta2, eps, weight_decay};
   const int threads = 128;
   dim3 grid((unsigned)(((int64_t)batch * G + threads - 1) / threads), n_fields);
-  fields_rowwise_update_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(p, a, step_dev, lr_dev, bias_corr_dev, G);
+  fields_rowwise_update_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(p, a, step_dev, lr_dev, bias_corr_dev, G, state_row_stride);
   RH_LAUNCH_CHECK();
   return RH_OK;
 }

@@ -49,10 +49,16 @@ class RowwiseOptimizer(object):
         st = self.state.get(id(p))
         if st is None:
             st = {"stamp": torch.zeros(p.shape[0], dtype=torch.int32, device=p.device)}
-            if self.kind in (1, 2):
-                st["m"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-            if self.kind == 1:
-                st["v"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+            V, D = p.shape
+            if self.kind == 1 and D % 4 == 0:  # Adam: m and v interleaved, one (m | v) record of 2*D floats per row
+                mv = torch.zeros((V, 2 * D), dtype=torch.float32, device=p.device)
+                st["m"], st["v"], st["stride"] = mv[:, :D], mv[:, D:], 2 * D
+            else:
+                if self.kind in (1, 2):
+                    st["m"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                if self.kind == 1:
+                    st["v"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                st["stride"] = D
             self.state[id(p)] = st
         return st
 
@@ -109,7 +115,7 @@ class RowwiseOptimizer(object):
                     stamps.append(stt["stamp"])
                 check(
                     L.rh_fields_rowwise_update(arr, len(chunk), dim, batch, _ptrs(tables), _ptrs(s1) if self.kind != 0 else None, _ptrs(s2) if self.kind == 1 else None, _ptrs(stamps), self.kind,
-                                               self._step_dev.data_ptr(), self._lr_dev.data_ptr(), self._bc_dev.data_ptr(), self.betas[0], self.betas[1], self.eps, self.weight_decay, st), "rh_fields_rowwise_update")
+                                               self._step_dev.data_ptr(), self._lr_dev.data_ptr(), self._bc_dev.data_ptr(), self._state(chunk[0][0])["stride"], self.betas[0], self.betas[1], self.eps, self.weight_decay, st), "rh_fields_rowwise_update")
         for p in self.params:
             _table.mark_clean(p)
 
@@ -119,7 +125,7 @@ class RowwiseOptimizer(object):
         m, v = stt.get("m"), stt.get("v")
         check(
             L.rh_rowwise_update(p.data_ptr(), slot.buffer.data_ptr(), None if m is None else m.data_ptr(), None if v is None else v.data_ptr(), stt["stamp"].data_ptr(), p.shape[0], p.shape[1], idc.data_ptr(),
-                                int(idc.dtype == torch.int32), idc.numel(), self.kind, self._step_dev.data_ptr(), self._lr_dev.data_ptr(), self._bc_dev.data_ptr(), self.betas[0], self.betas[1], self.eps, self.weight_decay, st),
+                                int(idc.dtype == torch.int32), idc.numel(), self.kind, self._step_dev.data_ptr(), self._lr_dev.data_ptr(), self._bc_dev.data_ptr(), stt["stride"], self.betas[0], self.betas[1], self.eps, self.weight_decay, st),
             "rh_rowwise_update")
 
     def zero_grad(self, set_to_none=True):
