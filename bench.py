@@ -123,18 +123,18 @@ def run_reference_arm(args):
         "vs_baseline": None,
         "dtype": "fp32",
         "data": "synthetic",
-        "config": workload_config("cpu"),
+        "config": workload_config("cpu", step="reference CTRTrainer step on CPU: fwd + BCE + zero_grad + bwd (dense per-lookup table gradients) + dense Adam over all 416 M parameters"),
         "cpu_baseline": {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": r["samples_per_s"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(parallelism):
+def workload_config(parallelism, step="zero_grad + fwd + BCE + bwd (scatter-add into tables) + optimiser (row-wise Adam on touched rows, Adam on the tower); tower GEMMs on tcgen05 (3xTF32, fp32-accurate); whole step replayed as one CUDA graph"):
     return {
         "workload": "DeepFM synthetic Criteo-shape: 13 dense + 26 sparse x 1M vocab x dim 16, batch 4096 per GPU, tutorial wiring (deep = dense + sparse), MLP 429-256-128-1 relu dropout 0.2",
         "global_batch_per_gpu": BATCH,
-        "step": "zero_grad + fwd + BCE + bwd (scatter-add into tables) + optimiser (row-wise Adam on touched rows, Adam on the tower)",
+        "step": step,
         "ids": "uniform int64, %d distinct batches cycled" % N_POOL,
         "l2": "inputs larger than L2: tables 1.66 GB and %d x 6.8 MB of distinct rows per cycle vs 126 MB L2" % N_POOL,
         "parallelism": parallelism,
@@ -208,6 +208,43 @@ def time_fused_forward_kernel(model, pool_dev, reps=20):
         del keep
     ms.sort()
     return sum(ms) / len(ms), ms[len(ms) // 2]
+
+
+TOWER_GEMMS = [("fwd1", 4096, 256, 429, False, False, 1), ("fwd2", 4096, 128, 256, False, False, 1), ("dX1", 4096, 429, 256, False, True, 1), ("dX2", 4096, 256, 128, False, True, 1),
+               ("dW1", 256, 429, 4096, True, True, 16), ("dW2", 128, 256, 4096, True, True, 32)]
+
+
+def time_tower_gemms(device):
+    """The six tower GEMMs of one step (rh_gemm_tf32x3, tcgen05) replayed from a CUDA graph: (sum of fp32-equivalent FLOPs, us)."""
+    import torch
+    from torch_rechub.b200 import ops
+    calls, flops = [], 0
+    for name, M, N, K, am, bm, sk in TOWER_GEMMS:
+        def mk(rows, cols, mn):
+            r, c = (cols, rows) if mn else (rows, cols)
+            return torch.randn(r, (c + 3) // 4 * 4, device=device)[:, :c]
+        A, B = mk(M, K, am), mk(N, K, bm)
+        out = torch.zeros(M, (N + 3) // 4 * 4, device=device)
+        calls.append((A, am, B, bm, M, N, K, sk, out))
+        flops += 2 * M * N * K
+    run = lambda: [ops.gemm3x(A, am, B, bm, M, N, K, split_k=sk, out=out) for (A, am, B, bm, M, N, K, sk, out) in calls]
+    run()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(10):
+            run()
+    g.replay()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3 / 10)
+    return flops, sorted(ts)[len(ts) // 2]
 
 
 def run_b200_arm(args):
@@ -305,7 +342,7 @@ def run_b200_arm(args):
     h2d = pool[0][0].h2d_bytes() + pool[0][1].numel() * 4
 
     # ---- roofline of the fused forward kernel -------------------------------------------------------------------
-    roof = None
+    roof = gemm_roof = None
     if rank == 0:
         kmodel = model if trainer._dist is None else build_model(device)[0]  # sharded run: time the kernel on a private full set of tables
         avg_ms, med_ms = time_fused_forward_kernel(kmodel, pool_dev)
@@ -319,9 +356,17 @@ def run_b200_arm(args):
                 traffic = json.load(open(tf)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        roof = {"bound": "hbm", "kernel": "rh::fields_fwd_v4<4,32> (fused 26-field gather + FM + LR + tile)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "algorithmic_bytes_per_launch": algo, "avg_us": avg_ms * 1e3, "median_us": med_ms * 1e3, "peak_source": peak_src,
-                "note": "B=4096 moves 14.5 MB: at 6.5 TB/s that is 2.2 us, i.e. the launch is latency-bound (two dependent DRAM round trips); see profiles/ for the batch sweep"}
+        roof = {"bound": "hbm", "kernel": "rh::fields_fwd_v4<4,8> (fused 26-field gather + FM + LR + tile, the north_star kernel)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "algorithmic_bytes_per_launch": algo, "avg_us": avg_ms * 1e3, "median_us": med_ms * 1e3, "peak_source": peak_src,
+                "note": "latency floor, not bandwidth: 106 k random 64-B rows cost 8.8 us at any footprint (profiles/r01_microbench_gather.csv); the same kernel reaches 3.16 TB/s at B=262144 = the random-gather ceiling of this part (profiles/r01_sweep_fields_fwd.csv)"}
+        gflops, gus = time_tower_gemms(device)
+        try:
+            tpeak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+        except Exception:
+            tpeak = 1590.0
+        gemm_roof = {"bound": "tensor", "kernel": "rh::gemm_tf32x3_kernel x6 (tower fwd/dX/dW; largest share of the step)", "achieved": gflops / gus / 1e6, "peak": tpeak, "unit": "TFLOP/s",
+                     "frac": gflops / gus / 1e6 / tpeak, "us_per_step": gus, "fp32_flops_per_step": gflops,
+                     "note": "fp32-accurate 3xTF32: 3 tensor-core MMAs per fp32 product and TF32 peak is half the bf16 peak, so 1/6 of the bf16 peak is the ceiling of this scheme; ncu tensor-pipe 10-29 % (profiles/r01b_ncu_full_summary.json)"}
 
     if world > 1:
         dist.barrier()
@@ -356,6 +401,7 @@ def run_b200_arm(args):
         "gpu_launches": per_step_launches * args.steps,
         "gpu_launches_per_step": per_step_launches,
         "roofline": roof,
+        "roofline_gemm": gemm_roof if rank == 0 else None,
         "cpu_baseline": cpu,
         "final_loss": final_loss,
     }
