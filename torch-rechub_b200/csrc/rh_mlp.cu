@@ -721,8 +721,8 @@ extern "C" int rh_dense_update(int n_tensors, float* const* params, const float*
       t.n[i] = (int32_t)numel[i0 + i];
       if (numel[i0 + i] > biggest) biggest = numel[i0 + i];
     }
-    int gx = (int)((biggest + 255) / 256);
-    if (gx > 64) gx = 64;
+    int gx = (int)((biggest + 255) / 256);  // one element per thread for tower-sized tensors: the update is a latency chain, not a stream
+    if (gx > 1024) gx = 1024;
     if (gx < 1) gx = 1;
     dense_update_kernel<<<dim3(gx, cnt), 256, 0, (cudaStream_t)stream>>>(t, kind, beta1, beta2, eps, weight_decay, lr_dev, bias_corr_dev);
     RH_LAUNCH_CHECK();
