@@ -9,7 +9,8 @@ the tables, and the optimiser (row-wise Adam on touched table rows + Adam on the
 
   value     whole-job samples/s with the batch already resident in HBM (CUDA events, max over ranks)
   e2e       the same step through the public API (CTRTrainer.train_one_epoch over a host loader): every step copies
-            its batch from pinned host memory and reads the loss back (loss.item())
+            its batch from pinned host memory (copy stream -> staging -> static inputs) and reads its loss + the
+            out-of-range-id flag back to the host (async D2H, consumed by the loop one step later)
   roofline  the fused gather+FM+LR+tile forward kernel (rh_fields_fwd) timed alone with CUDA events:
             algorithmic bytes (3544 B/sample with the tile) / duration vs MEASURED_PEAKS.json hbm_gbs
   cpu_baseline / --impl reference   the reference's own CPU training step (oracle/ref_port.py: stock torch modules
@@ -396,7 +397,7 @@ def run_b200_arm(args):
         "data": "synthetic",
         "config": workload_config("single GPU" if world == 1 else "tables sharded by field over %d ranks + dp tower" % world),
         "clocks": clocks,
-        "e2e": {"value": total_samples / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": e2e_s / args.steps * 1e3,
+        "e2e": {"value": total_samples / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8, "ms_per_step": e2e_s / args.steps * 1e3,
                 "api": "CTRTrainer.train_one_epoch(loader of pinned PackedColumns batches)"},
         "gpu_launches": per_step_launches * args.steps,
         "gpu_launches_per_step": per_step_launches,

@@ -106,9 +106,14 @@ int rh_fields_fwd_p2p(const rh_field* fields, int n_fields, int dim, int batch,
 
 /* ids of my samples -> the owners' id buffers (peer memory).  cols[c] (ids / id_stride / ids_are_i32 are read) is the c-th id
  * column, col_dest[c] its destination GPU (columns sorted by destination; the order inside a destination is the slot order);
- * dest_base[d] points at MY (batch, fmax) block of destination d's id buffer:  dest_base[d][j * fmax + slot] = ids[j]. */
+ * dest_base[d] points at MY block of destination d's id buffer:  dest_base[d][slot * slot_stride + j * sample_stride] = ids[j]
+ * (field-major buffers, sample_stride 1, give contiguous NVLink stores and unit-stride ids for the owner's gather;
+ * sample-major is slot_stride 1, sample_stride fmax).  At most fmax columns per destination.
+ * rh_field.table_grad may equally be a peer pointer in rh_fields_bwd: the sample's GPU then REDs row gradients straight
+ * into the owner's gradient buffer at the row id (no staging buffer, no owner-side scatter pass). */
 int rh_ids_scatter(const rh_field* cols, int n_cols, const int32_t* col_dest, int batch,
-                   int64_t* const* dest_base, int n_dest, int fmax, void* stream);
+                   int64_t* const* dest_base, int n_dest, int fmax, int64_t slot_stride, int64_t sample_stride,
+                   void* stream);
 
 /* Backward of rh_fields_fwd: the sparse-gradient scatter-add into the tables' gradient buffers.
  *

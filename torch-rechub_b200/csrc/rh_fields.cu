@@ -606,8 +606,9 @@ extern "C" int rh_fields_fwd_p2p(const rh_field* fields, int n_fields, int dim, 
                          dest_tiles, n_dest, rows_per_dest);
 }
 
-// ids of my samples -> the owners' id buffers (peer memory).  One thread per (destination, sample) writes that sample's ids for
-// ALL of the destination's fields contiguously (24-104 B), so a warp's stores to a peer coalesce into full NVLink packets.
+// ids of my samples -> the owners' id buffers (peer memory).  One thread per (destination, sample); the id of the
+// destination's k-th field lands at  dst[k * slot_stride + sample * sample_stride].  Field-major buffers
+// (sample_stride 1) make every warp store one contiguous 256-byte run over NVLink, and give the owner's gather unit-stride ids.
 namespace rh {
 struct IdScatterP {
   const void* src[RH_MAX_FIELDS];   // columns sorted by (destination, slot)
@@ -616,21 +617,24 @@ struct IdScatterP {
   long long* dst[8];                 // per destination: base of MY block in its (W, b, fmax) id buffer
   int32_t first[8], count[8];        // columns of destination d: [first[d], first[d] + count[d])
   int32_t batch, fmax;
+  long long slot_stride, sample_stride;
 };
 __global__ void __launch_bounds__(256) ids_scatter_kernel(const __grid_constant__ IdScatterP p) {
   const int d = blockIdx.y;
   const int first = p.first[d], count = p.count[d];
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < p.batch; j += gridDim.x * blockDim.x) {
-    long long* out = p.dst[d] + (int64_t)j * p.fmax;
-    for (int k = 0; k < count; ++k) out[k] = (long long)load_id(p.src[first + k], (int64_t)j * p.stride[first + k], p.is_i32[first + k] != 0);
+    long long* out = p.dst[d] + (int64_t)j * p.sample_stride;
+#pragma unroll 4
+    for (int k = 0; k < count; ++k)
+      out[(int64_t)k * p.slot_stride] = (long long)load_id(p.src[first + k], (int64_t)j * p.stride[first + k], p.is_i32[first + k] != 0);
   }
 }
 }  // namespace rh
 
 extern "C" int rh_ids_scatter(const rh_field* cols, int n_cols, const int32_t* col_dest, int batch, int64_t* const* dest_base, int n_dest, int fmax,
-                              void* stream) {
+                              int64_t slot_stride, int64_t sample_stride, void* stream) {
   RH_REQUIRE(cols != nullptr && col_dest != nullptr && dest_base != nullptr && n_cols > 0 && n_cols <= RH_MAX_FIELDS && batch >= 0 && fmax > 0 &&
-                 n_dest > 0 && n_dest <= 8,
+                 n_dest > 0 && n_dest <= 8 && slot_stride > 0 && sample_stride > 0,
              RH_ERR_INVALID_ARG, "rh_ids_scatter: bad arguments");
   if (batch == 0) return RH_OK;
   static thread_local rh::IdScatterP p;
@@ -653,6 +657,8 @@ extern "C" int rh_ids_scatter(const rh_field* cols, int n_cols, const int32_t* c
   }
   p.batch = batch;
   p.fmax = fmax;
+  p.slot_stride = slot_stride;
+  p.sample_stride = sample_stride;
   dim3 grid((batch + 255) / 256, n_dest);
   rh::ids_scatter_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
   RH_LAUNCH_CHECK();

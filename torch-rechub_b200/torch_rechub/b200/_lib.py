@@ -37,7 +37,7 @@ PROTOTYPES = {
     "rh_launch_count": [],
     "rh_fields_fwd": [c_p, c_i, c_i, c_p, c_i, c_i, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "rh_fields_fwd_p2p": [c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_i64, c_p, c_p],
-    "rh_ids_scatter": [c_p, c_i, c_p, c_i, c_p, c_i, c_i, c_p],
+    "rh_ids_scatter": [c_p, c_i, c_p, c_i, c_p, c_i, c_i, c_i64, c_i64, c_p],
     "rh_fields_bwd": [c_p, c_i, c_i, c_i, c_p, c_i64, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "rh_rows_gather": [c_p, c_i, c_i, c_p, c_i, c_i64, c_p, c_p, c_p],
     "rh_rows_scatter_add": [c_p, c_i, c_i, c_i, c_p, c_i, c_i64, c_p, c_p, c_p],

@@ -24,12 +24,27 @@ dist_cuda_graph = _flag("RECHUB_B200_DIST_CUDA_GRAPH", True)
 # (torch symmetric memory) instead of NCCL all-to-alls.
 p2p_exchange = _flag("RECHUB_B200_P2P", True)
 
+# Peer-memory exchange details.  Field-major id buffers: contiguous NVLink stores from rh_ids_scatter and unit-stride ids for the
+# owner's gather (off = sample-major, the first layout).  Direct gradients: the sample's GPU REDs each row gradient straight into
+# the OWNER's persistent gradient buffer at the row id (the buffers live in one symmetric-memory pool per rank); off = RED into a
+# staging buffer on the owner + an owner-side scatter-add pass.
+p2p_field_major_ids = _flag("RECHUB_B200_P2P_FIELD_MAJOR", True)
+p2p_direct_grads = _flag("RECHUB_B200_P2P_DIRECT_GRADS", True)
+
 # Check the device-side out-of-range-id flag after every forward (one D2H sync per step).  When off the
 # flag is checked at the trainer's existing sync points (``loss.item()``) and by ``check_errors()``.
 eager_bounds_check = _flag("RECHUB_B200_EAGER_BOUNDS_CHECK", False)
 
 # Tower GEMMs on the tcgen05 tensor cores with the fp32-accurate 3xTF32 kernel (rh_gemm_tf32x3); off = cuBLAS fp32 (torch.mm).
 tensor_core_gemm = _flag("RECHUB_B200_TC_GEMM", True)
+
+# Graph-replayed training loop: ship host batches over PCIe on a copy stream while the previous step computes
+# (staging buffers + D2D into the graph's static inputs) ...
+pipelined_inputs = _flag("RECHUB_B200_PIPELINED_INPUTS", True)
+
+# ... and read each step's loss / out-of-range-id flag one step late (async D2H into pinned slots), so the training
+# loop never drains the GPU.  Epoch statistics are unchanged; an IndexError surfaces one batch later than in the reference.
+lagged_loss = _flag("RECHUB_B200_LAGGED_LOSS", True)
 
 # Set by the graph runner while inputs live in static buffers that the next batch overwrites.
 static_inputs = False

@@ -48,23 +48,29 @@ class _AllToAllRows(torch.autograd.Function):
 class P2PExchange(object):
     """Peer-mapped (symmetric-memory) buffers of one sharded front-end plan + the cross-GPU barrier that orders them.
 
-    ids   (W, b, fmax) int64   on owner r: block s = ids of rank s's samples for r's fields      (written by rank s)
+    ids   (fmax, W, b) int64   on owner r: [k, s, :] = ids of rank s's samples for r's k-th field (written by rank s;
+                               sample-major (W, b, fmax) when config.p2p_field_major_ids is off)
     rows  (W, b, fmax*dim) f32 on rank s : block r = rows of owner r's fields for s's samples     (written by owner r's gather kernel)
-    drows (W, b, fmax*dim) f32 on owner r: block s = gradients of those rows from rank s          (RED by rank s's backward kernel)
+    drows (W, b, fmax*dim) f32 on owner r: block s = gradients of those rows from rank s          (RED by rank s's backward kernel;
+                               absent with direct gradients: the REDs then target the owner's table gradient buffers)
     """
 
-    def __init__(self, group, device, W, b, fmax, dim):
+    def __init__(self, group, device, W, b, fmax, dim, with_drows=True):
         import torch.distributed._symmetric_memory as symm
+        from . import config
+        self.field_major = bool(config.p2p_field_major_ids)
         self.ids = symm.empty(W * b * fmax, dtype=torch.int64, device=device)
         self.rows = symm.empty(W * b * fmax * dim, dtype=torch.float32, device=device)
-        self.drows = symm.empty(W * b * fmax * dim, dtype=torch.float32, device=device)
         self.h_ids = symm.rendezvous(self.ids, group)
         self.h_rows = symm.rendezvous(self.rows, group)
-        self.h_drows = symm.rendezvous(self.drows, group)
         self.ids_ptrs = [int(p) for p in self.h_ids.buffer_ptrs]
         self.rows_ptrs = [int(p) for p in self.h_rows.buffer_ptrs]
-        self.drows_ptrs = [int(p) for p in self.h_drows.buffer_ptrs]
-        self.drows.zero_()
+        self.drows = self.drows_ptrs = None
+        if with_drows:
+            self.drows = symm.empty(W * b * fmax * dim, dtype=torch.float32, device=device)
+            self.h_drows = symm.rendezvous(self.drows, group)
+            self.drows_ptrs = [int(p) for p in self.h_drows.buffer_ptrs]
+            self.drows.zero_()
         self.ids_local = torch.zeros_like(self.ids)
 
     def barrier(self):
@@ -94,24 +100,35 @@ class _ShardedP2P(torch.autograd.Function):
         # F1: my samples' ids -> the owners
         cols = (ops.RhField * len(p["slots"]))()  # slots are sorted by (owner, slot)
         col_dest = (ctypes.c_int32 * len(p["slots"]))()
+        my_ids = {}
         for n, (r, k, f) in enumerate(p["slots"]):
-            ids = ops._as_ids(x[f.name])
+            ids = my_ids[f.name] = ops._as_ids(x[f.name])
             cols[n].ids = ids.data_ptr()
             cols[n].id_stride = ids.stride(0) if ids.shape[0] > 1 else 1
             cols[n].ids_are_i32 = int(ids.dtype == torch.int32)
             col_dest[n] = r
-        bases = (ctypes.c_void_p * W)(*[ex.ids_ptrs[r] + me * b * fmax * 8 for r in range(W)])
-        ops.check(L.rh_ids_scatter(cols, len(p["slots"]), col_dest, b, bases, W, fmax, st), "rh_ids_scatter")
+        direct = front.direct if torch.is_grad_enabled() else None  # peer-mapped gradient buffers of every table (or None)
+        if direct is not None:
+            # my own tables' buffers must be attached and clean BEFORE any peer's backward REDs into them: do it ahead of the
+            # forward barriers (the staged route does this in its owner-side backward pass)
+            for f in p["by_owner"][me]:
+                _table.grad_target(front.layer.table_of(f).weight)
+        if ex.field_major:  # [slot, source rank, sample]
+            bases = (ctypes.c_void_p * W)(*[ex.ids_ptrs[r] + me * b * 8 for r in range(W)])
+            ops.check(L.rh_ids_scatter(cols, len(p["slots"]), col_dest, b, bases, W, fmax, W * b, 1, st), "rh_ids_scatter")
+        else:  # [source rank, sample, slot]
+            bases = (ctypes.c_void_p * W)(*[ex.ids_ptrs[r] + me * b * fmax * 8 for r in range(W)])
+            ops.check(L.rh_ids_scatter(cols, len(p["slots"]), col_dest, b, bases, W, fmax, 1, fmax, st), "rh_ids_scatter")
         ex.barrier()
         # F3: owner-side gather over the global batch, rows stored straight into the destination GPUs' tiles.  The ids are
         # snapshotted locally first: peers may refill ex.ids for the next step while this rank's backward still needs them.
         mine = p["by_owner"][me]
         ex.ids_local.copy_(ex.ids)
-        ids_g = ex.ids_local.view(W * b, fmax)
+        ids_g = ex.ids_local.view(fmax, W * b) if ex.field_major else ex.ids_local.view(W * b, fmax).t()
         orefs = []
         for k, f in enumerate(mine):
             tbl = front.layer.table_of(f)
-            orefs.append(ops.FieldRef(tbl.weight, ids_g[:, k], tbl.padding_idx, k * dim, -1))
+            orefs.append(ops.FieldRef(tbl.weight, ids_g[k], tbl.padding_idx, k * dim, -1))
         if orefs:
             dest = (ctypes.c_void_p * W)(*[ex.rows_ptrs[s] + me * b * fmax * dim * 4 for s in range(W)])
             ops.check(L.rh_fields_fwd_p2p(ops._field_array(orefs), len(orefs), dim, W * b, dest, W, b, fmax * dim, err, st), "rh_fields_fwd_p2p")
@@ -142,6 +159,7 @@ class _ShardedP2P(torch.autograd.Function):
             L.rh_fields_fwd(ops._field_array(srefs), len(srefs), dim, ops._dense_array(drefs) if drefs else None, len(drefs), b, tile.data_ptr(), ld, ops.ptr(lr_w) if y_lr is not None else None,
                             ops.ptr(lr_b) if y_lr is not None else None, ops.ptr(y_fm), ops.ptr(y_lr), ops.ptr(fsum), err, st), "rh_fields_fwd")
         ctx.front, ctx.p, ctx.srefs, ctx.orefs, ctx.ld, ctx.want_lr = front, p, srefs, orefs, ld, y_lr is not None
+        ctx.direct, ctx.my_ids = direct, my_ids
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(tile, fsum, lr_w)
         return (tile if ld == width_total else tile[:, :width_total]), y_fm, y_lr
@@ -168,18 +186,39 @@ class _ShardedP2P(torch.autograd.Function):
             n = lr_w.numel()
             buf = torch.zeros(ops._pad4(n) + 1, dtype=torch.float32, device=dev)
             d_lrw, d_lrb = buf[:n].view_as(lr_w), buf[ops._pad4(n):ops._pad4(n) + 1]
-        # B1: gradients of the received rows go straight to their owners (vector RED over NVLink into drows[owner][me])
         arr = ops._field_array(ctx.srefs)
-        owners = [front.owner_of(f) for f in p["sparse"]]
-        for n, r in enumerate(owners):
-            # the kernel indexes the gradient buffer with the FORWARD row id (r*b + i)*fmax + k; the owner's block for my
-            # samples starts at row me*b*fmax: shift the base so that both agree
-            arr[n].table_grad = ex.drows_ptrs[r] + (me - r) * b * fmax * dim * 4
+        if ctx.direct is not None:
+            # B1 (direct): row gradients go over NVLink straight into the OWNER's gradient buffer, at the row the id names.
+            # The rows themselves come from the saved tile, so `table` is never dereferenced here.
+            for n, f in enumerate(p["sparse"]):
+                ids = ctx.my_ids[f.name]
+                ptr_, vocab, pad = ctx.direct[f.name if f.shared_with is None else f.shared_with]
+                arr[n].table = tile.data_ptr()
+                arr[n].table_grad = ptr_
+                arr[n].ids = ids.data_ptr()
+                arr[n].id_stride = ids.stride(0) if ids.shape[0] > 1 else 1
+                arr[n].ids_are_i32 = int(ids.dtype == torch.int32)
+                arr[n].vocab = vocab
+                arr[n].padding_idx = pad
+        else:
+            # B1 (staged): gradients of the received rows go to their owners' staging buffers (vector RED into drows[owner][me])
+            owners = [front.owner_of(f) for f in p["sparse"]]
+            for n, r in enumerate(owners):
+                # the kernel indexes the gradient buffer with the FORWARD row id (r*b + i)*fmax + k; the owner's block for my
+                # samples starts at row me*b*fmax: shift the base so that both agree
+                arr[n].table_grad = ex.drows_ptrs[r] + (me - r) * b * fmax * dim * 4
         has_fm = (d_yfm is not None or d_ylr is not None) and any(s.fm_slot >= 0 for s in ctx.srefs)
         ops.check(
             L.rh_fields_bwd(arr, len(ctx.srefs), dim, b, tile.data_ptr(), ctx.ld, ops.ptr(d_tile), d_ld, ops.ptr(d_yfm) if has_fm else None, ops.ptr(d_ylr) if has_fm else None,
                             ops.ptr(lr_w) if has_fm else None, ops.ptr(fsum) if has_fm else None, ops.ptr(d_lrw) if has_fm else None, ops.ptr(d_lrb) if has_fm else None, err, st), "rh_fields_bwd")
         ex.barrier()
+        if ctx.direct is not None:
+            # every rank's REDs have landed in my buffers: only the bookkeeping of which rows are dirty is left
+            for r in ctx.orefs:
+                g, slot = _table.grad_target(r.weight)
+                if g is not None:
+                    _table.note_dirty(slot, r.ids)
+            return (None, None, None, None, d_lrw, d_lrb) + (None,) * len(ctx.orefs)
         # B3: the owner scatter-adds what every rank sent into its tables
         if ctx.orefs:
             targets = [_table.grad_target(r.weight) for r in ctx.orefs]
@@ -216,6 +255,7 @@ class ShardedFront(object):
         self._plans = {}
         from . import config
         self.use_p2p = device.type == "cuda" and config.p2p_exchange
+        self.direct = None  # table name -> (peer-mapped gradient buffer pointer, vocab, padding_idx); set by DistEngine
 
     def owner_of(self, fea):
         return self.owner[fea.name if fea.shared_with is None else fea.shared_with]
@@ -280,7 +320,7 @@ class ShardedFront(object):
         cuda = self.device.type == "cuda"
         if cuda and self.use_p2p and dim % 4 == 0 and W <= 8:
             if p["ex"] is None:
-                p["ex"] = P2PExchange(self.group, self.device, W, b, fmax, dim)
+                p["ex"] = P2PExchange(self.group, self.device, W, b, fmax, dim, with_drows=self.direct is None)
             mine = p["by_owner"][self.rank]
             owned = [self.layer.table_of(f).weight for f in mine]
             return _ShardedP2P.apply(self, p, x, fm_features, lr[0] if lr else None, lr[1] if lr else None, *owned)
@@ -363,6 +403,7 @@ class DistEngine(object):
                 front = ShardedFront(mod, self.group, self.device)
                 mod._dist = front
                 self.fronts.append(front)
+                front._tables = [(name, front.owner[name], tuple(tbl.weight.shape), bool(tbl.weight.requires_grad), tbl.padding_idx) for name, tbl in mod.embed_dict.items()]
                 for name, tbl in mod.embed_dict.items():
                     if front.owner[name] == self.rank:
                         self.owned.append(tbl.weight)
@@ -371,6 +412,8 @@ class DistEngine(object):
                         tbl._dist_shape = tuple(tbl.weight.shape)
                         tbl.weight.data = torch.empty((0, tbl.weight.shape[1]), dtype=tbl.weight.dtype, device=tbl.weight.device)  # free it
                         tbl.weight.requires_grad_(False)
+        self.grad_pool = None
+        self._map_gradient_buffers()
         skip = {id(p) for p in self.owned} | {id(p) for p in self.foreign}
         self.dense_params = [p for p in model.parameters() if id(p) not in skip and p.requires_grad]
         # replicated parameters start identical on every rank
@@ -386,6 +429,41 @@ class DistEngine(object):
         for p in self.dense_params:
             self.views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
+
+    def _map_gradient_buffers(self):
+        """Direct gradients: carve every owned table's persistent gradient buffer out of ONE symmetric-memory pool per rank, so
+        that the peers' backward kernels can RED row gradients straight into it.  Every rank derives the same layout from the
+        model description (no communication besides the rendezvous)."""
+        from . import config, table as _table
+        fronts = [f for f in self.fronts if f.use_p2p]
+        if self.device.type != "cuda" or not config.p2p_direct_grads or not fronts or self.world > 8:
+            return
+        layout, totals = [], [0] * self.world  # (front, name, owner, offset in floats, shape, trainable, padding_idx)
+        for front in fronts:
+            for name, owner, shape, trainable, pad in front._tables:
+                if len(shape) != 2 or shape[1] % 4 != 0:
+                    return  # the vector RED needs 16-byte rows; keep the staged route
+                n = (shape[0] * shape[1] + 63) // 64 * 64
+                layout.append((front, name, owner, totals[owner], shape, trainable, pad))
+                totals[owner] += n
+        import torch.distributed._symmetric_memory as symm
+        self.grad_pool = symm.empty(max(max(totals), 64), dtype=torch.float32, device=self.device)
+        self.grad_pool.zero_()
+        handle = symm.rendezvous(self.grad_pool, self.group)
+        ptrs = [int(p) for p in handle.buffer_ptrs]
+        self._grad_pool_handle = handle
+        for front in fronts:
+            front.direct = {}
+        for front, name, owner, off, shape, trainable, pad in layout:
+            front.direct[name] = (ptrs[owner] + 4 * off if trainable else None, shape[0], -1 if pad is None else int(pad))
+            if owner == self.rank and trainable:
+                w = front.layer.embed_dict[name].weight
+                slot = _table.slot_of(w)
+                slot.buffer = self.grad_pool[off:off + shape[0] * shape[1]].view(shape)
+                slot.pending, slot.all_dirty = [], False
+                w.grad = None
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)  # nobody REDs into a pool that is still being zeroed
 
     # -- one training step -------------------------------------------------------------------------------------
     def train_step(self, trainer, x_dict, y):

@@ -5,15 +5,61 @@ eager loop by an order of magnitude.  ``GraphedStep`` captures ``trainer._train_
 BCE, backward with the scatter-add, optimiser) once and replays it per batch; the batch is copied into static
 input buffers first (one async H2D/D2D copy per column).
 
+Host batches are software-pipelined: batch t+1 travels over PCIe on a copy stream into staging buffers while step t
+computes; the step's own stream only pays three small D2D copies.  ``LaggedReader`` completes the pipeline on the
+result side: the loss (and the out-of-range-id flag) of step t are read while step t+1 is already queued, so the
+trainer's per-step ``loss.item()`` no longer drains the GPU.
+
 Constraints: static shapes (a ragged last batch runs eagerly), the hybrid row-wise optimiser (its step
 re-zeroes the gradient rows it consumed, so no per-step host bookkeeping is left), single process.
 """
+import collections
+
 import torch
 
 from . import optim as _optim
 from .data import PackedColumns
 
 _WARMUP_STEPS = 3
+
+
+class LaggedReader(object):
+    """Device scalars -> host one step late.  ``push(loss)`` queues an async D2H of the loss and of the engine's error flag
+    into pinned slots; ``pop()`` returns the oldest loss as a float (raising the reference's ``IndexError`` if that step
+    saw an out-of-range id).  With one step of lag the host never waits for the step it has just launched."""
+
+    def __init__(self, device, depth=4):
+        self.device = torch.device(device)
+        self.loss = torch.zeros(depth, dtype=torch.float32).pin_memory()
+        self.flag = torch.zeros(depth, dtype=torch.int32).pin_memory()
+        self.events = [torch.cuda.Event() for _ in range(depth)]
+        self.depth, self.head = depth, 0
+        self.queue = collections.deque()
+
+    def pending(self):
+        return len(self.queue)
+
+    def push(self, loss):
+        from . import _lib
+        if len(self.queue) == self.depth:
+            raise RuntimeError("LaggedReader: %d results outstanding; pop() before pushing more" % self.depth)
+        i = self.head
+        self.head = (self.head + 1) % self.depth
+        self.loss[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        self.flag[i:i + 1].copy_(_lib.err_flag(self.device), non_blocking=True)
+        self.events[i].record()
+        self.queue.append(i)
+
+    def pop(self):
+        from . import _lib
+        i = self.queue.popleft()
+        self.events[i].synchronize()
+        v = int(self.flag[i])
+        if v != 0:
+            _lib.err_flag(self.device).zero_()
+            self.queue.clear()
+            raise IndexError("index out of range in self (embedding lookup, field #%d of the launch)" % (v - 1))
+        return float(self.loss[i])
 
 
 class GraphedStep(object):
@@ -24,6 +70,9 @@ class GraphedStep(object):
         self.static_x = None
         self.static_y = None
         self.loss = None
+        self.staging_x = self.staging_y = None  # landing buffers of the copy stream (host batches only)
+        self.copy_stream = None
+        self.ev_h2d = self.ev_consumed = None
         self.calls = 0
         self.stream = None  # warm-up AND capture run on this side stream (autograd binds AccumulateGrad nodes to the stream
         # they were first used on; a default-stream node inside a capture invalidates it)
@@ -47,14 +96,37 @@ class GraphedStep(object):
         with torch.cuda.graph(self.graph, stream=self._side_stream()):
             self.loss = self.trainer._train_step(self.static_x, self.static_y).detach()
 
-    def load_inputs(self, x_dict, y):
-        """Batch -> static buffers (straight from pinned host memory when the batch is still on the host)."""
-        if isinstance(x_dict, PackedColumns) and isinstance(self.static_x, PackedColumns):
-            x_dict.copy_into(self.static_x)
+    @staticmethod
+    def _copy_batch(src_x, src_y, dst_x, dst_y):
+        if isinstance(src_x, PackedColumns) and isinstance(dst_x, PackedColumns):
+            src_x.copy_into(dst_x)
         else:
-            for k, v in x_dict.items():
-                self.static_x[k].copy_(v, non_blocking=True)
-        self.static_y.copy_(y, non_blocking=True)
+            for k, v in src_x.items():
+                dst_x[k].copy_(v, non_blocking=True)
+        dst_y.copy_(src_y, non_blocking=True)
+
+    def load_inputs(self, x_dict, y):
+        """Batch -> static buffers.  Device batches are copied directly.  Host batches go over PCIe on the copy stream into
+        staging buffers — overlapping the step that is still running — and reach the static buffers by D2D copies."""
+        from . import config
+        probe = x_dict.ids if isinstance(x_dict, PackedColumns) and x_dict.ids is not None else next(iter(x_dict.values()))
+        if probe.is_cuda or not config.pipelined_inputs:
+            self._copy_batch(x_dict, y, self.static_x, self.static_y)
+            return
+        if self.staging_x is None:
+            self.staging_x = self.static_x.clone() if isinstance(self.static_x, PackedColumns) else {k: v.clone() for k, v in self.static_x.items()}
+            self.staging_y = self.static_y.clone()
+            self.copy_stream = torch.cuda.Stream(device=self.trainer.device)
+            self.ev_h2d, self.ev_consumed = torch.cuda.Event(), torch.cuda.Event()
+            self.ev_consumed.record()
+        cur, cs = torch.cuda.current_stream(), self.copy_stream
+        cs.wait_event(self.ev_consumed)  # the previous batch has left the staging buffers
+        with torch.cuda.stream(cs):
+            self._copy_batch(x_dict, y, self.staging_x, self.staging_y)
+            self.ev_h2d.record(cs)
+        cur.wait_event(self.ev_h2d)
+        self._copy_batch(self.staging_x, self.staging_y, self.static_x, self.static_y)
+        self.ev_consumed.record(cur)
 
     def _side_stream(self):
         if self.stream is None:

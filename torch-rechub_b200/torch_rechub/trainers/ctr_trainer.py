@@ -132,32 +132,46 @@ class CTRTrainer(object):
 
     def train_one_epoch(self, data_loader, log_interval=10):
         self.model.train()
-        total_loss = 0
-        epoch_loss = 0
-        batch_count = 0
+        stats = {"total": 0.0, "epoch": 0.0, "count": 0}
         on_cuda = self.device.type == "cuda"
+        lagged = None
         if on_cuda:
             from ..b200 import _lib, config, graph
+            if config.lagged_loss:
+                lagged = graph.LaggedReader(self.device)
         tk0 = tqdm.tqdm(data_loader, desc="train", smoothing=0, mininterval=1.0)
-        for i, (x_dict, y) in enumerate(tk0):
+
+        def account(loss_value):
+            stats["total"] += loss_value
+            stats["epoch"] += loss_value
+            stats["count"] += 1
+            if stats["count"] % log_interval == 0:
+                tk0.set_postfix(loss=stats["total"] / log_interval)
+                stats["total"] = 0.0
+
+        for x_dict, y in tk0:
             if on_cuda and config.cuda_graph and (self._dist is None or config.dist_cuda_graph):
                 if self._graph_step is None:
                     self._graph_step = graph.GraphedStep(self)
-                loss = self._graph_step(x_dict, y)  # copies the (host) batch straight into the graph's static inputs
+                loss = self._graph_step(x_dict, y)  # copies the (host) batch into the graph's static inputs
             else:
                 x_dict = self._to_device(x_dict)
                 y = y.to(self.device).float()
                 loss = self._train_step(x_dict, y)
+            if lagged is not None:
+                # the reference syncs on loss.item() every step (ctr_trainer.py:100); here step t's loss is read while step
+                # t+1 is already queued, so the device never waits for the host
+                lagged.push(loss)
+                if lagged.pending() > 1:
+                    account(lagged.pop())
+                continue
             loss_value = loss.item()
             if on_cuda:
                 _lib.check_errors(self.device)  # out-of-range ids -> IndexError, at the reference's own sync point
-            total_loss += loss_value
-            epoch_loss += loss_value
-            batch_count += 1
-            if (i + 1) % log_interval == 0:
-                tk0.set_postfix(loss=total_loss / log_interval)
-                total_loss = 0
-        return epoch_loss / batch_count if batch_count > 0 else 0
+            account(loss_value)
+        while lagged is not None and lagged.pending():
+            account(lagged.pop())
+        return stats["epoch"] / stats["count"] if stats["count"] > 0 else 0
 
     def fit(self, train_dataloader, val_dataloader=None):
         for logger in self._iter_loggers():
