@@ -1,5 +1,8 @@
-"""2-GPU NCCL test of the field-sharded CUDA route (fused owner-side gather -> all-to-all -> fused receive/unpack+FM+LR)
-against a single-GPU emulation of the DataParallel semantics.  Needs >= 2 GPUs (skipped on a 1-GPU box)."""
+"""2-GPU test of the field-sharded CUDA route (ids to the owners, fused owner-side gather storing rows into the samples'
+GPUs, fused receive/unpack+FM+LR, row gradients RED back to the owners) against a single-GPU emulation of the
+DataParallel semantics, over TWO consecutive steps (the second one exercises the sparse re-zeroing of the gradient buffers
+under peer writes).  Both peer-memory variants are covered: field-major ids + direct gradients, and sample-major ids +
+staged gradients.  Needs >= 2 GPUs (skipped on a 1-GPU box)."""
 import copy
 import os
 import socket
@@ -36,17 +39,21 @@ def _make(kind):
     return DCN(dense + sparse, n_cross_layers=2, mlp_params={"dims": [32, 16]})
 
 
-def _batch(rank, b=256):
-    g = torch.Generator().manual_seed(100 + rank)
+N_STEPS = 2
+
+
+def _batch(rank, step=0, b=256):
+    g = torch.Generator().manual_seed(100 + rank + 10 * step)
     x = {"I%d" % i: torch.rand(b, generator=g) for i in range(3)}
     x.update({"C%d" % i: torch.randint(0, 301, (b,), generator=g) for i in range(7)})
     return x, torch.randint(0, 2, (b,), generator=g).float()
 
 
-def _worker(rank, world, port, kind, out):
+def _worker(rank, world, port, kind, variant, out):
     if PKG not in sys.path:
         sys.path.insert(0, PKG)
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      RECHUB_B200_P2P_DIRECT_GRADS=variant, RECHUB_B200_P2P_FIELD_MAJOR=variant)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -56,47 +63,50 @@ def _worker(rank, world, port, kind, out):
     full_sd = copy.deepcopy(model.state_dict())
     trainer = CTRTrainer(model, optimizer_fn=torch.optim.SGD, optimizer_params={"lr": 0.1}, device=str(dev))
     assert trainer._dist is not None
-    x, y = _batch(rank)
+    assert (trainer._dist.grad_pool is not None) == (variant == "1")
     model.train()
-    loss = trainer._train_step({k: v.to(dev) for k, v in x.items()}, y.to(dev))
+    for step in range(N_STEPS):
+        x, y = _batch(rank, step)
+        loss = trainer._train_step({k: v.to(dev) for k, v in x.items()}, y.to(dev))
     _lib.check_errors(dev)
     sd = trainer._dist.full_state_dict()
     out[rank] = {"loss": float(loss), "sd": {k: v.detach().cpu().clone() for k, v in sd.items()}, "init": full_sd}
     dist.barrier()
     torch.cuda.synchronize()
-    os._exit(0) if False else None
     dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("variant", ["1", "0"])
 @pytest.mark.parametrize("kind", ["deepfm", "dcn"])
-def test_two_gpu_sharded_step(kind):
+def test_two_gpu_sharded_step(kind, variant):
     world = 2
     out = mp.get_context("spawn").Manager().dict()
-    mp.spawn(_worker, args=(world, _free_port(), kind, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), kind, variant, out), nprocs=world, join=True)
     ref = _make(kind)
     ref.load_state_dict(out[0]["init"])
     ref = ref.to("cuda:0").train()
     opt = torch.optim.SGD(ref.parameters(), lr=0.1)
-    opt.zero_grad()
-    total = 0.0
-    bn_mods = [m for m in ref.modules() if isinstance(m, torch.nn.BatchNorm1d)]
-    saved = [(m.running_mean.clone(), m.running_var.clone()) for m in bn_mods]
-    for r in range(world):
-        for m, (rm, rv) in zip(bn_mods, saved):
-            m.running_mean.copy_(rm)
-            m.running_var.copy_(rv)
-        x, y = _batch(r)
-        loss = torch.nn.BCELoss()(ref({k: v.to("cuda:0") for k, v in x.items()}), y.to("cuda:0")) / world
-        loss.backward()
-        total += float(loss.detach())
-    opt.step()
+    for step in range(N_STEPS):
+        opt.zero_grad()
+        total = 0.0
+        for r in range(world):  # training-mode BatchNorm normalises with each replica's own batch statistics
+            x, y = _batch(r, step)
+            loss = torch.nn.BCELoss()(ref({k: v.to("cuda:0") for k, v in x.items()}), y.to("cuda:0")) / world
+            loss.backward()
+            total += float(loss.detach())
+        opt.step()
     assert abs(out[0]["loss"] - total) < 1e-5 and abs(out[1]["loss"] - total) < 1e-5
     want = {k: v.detach().cpu() for k, v in ref.state_dict().items()}
+    bad = []
     for k, v in out[0]["sd"].items():
         if "running_" in k or "num_batches" in k or k.endswith("mlp.0.bias") or k.endswith("mlp.4.bias"):
             continue
-        assert torch.allclose(v, want[k], rtol=2e-4, atol=2e-6), (k, (v - want[k]).abs().max())
+        moved = (want[k] - out[0]["init"][k].cpu()).abs().max().item()  # size of the two SGD updates: the error scale that matters
+        err = (v - want[k]).abs().max().item()
+        if err > 2e-3 * moved + 2e-6:
+            bad.append((k, err, moved))
+    assert not bad, bad
     for k, v in out[1]["sd"].items():
         if "running_" in k or "num_batches" in k:
             continue

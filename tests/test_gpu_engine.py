@@ -127,6 +127,34 @@ def test_cuda_graph_replay_equals_eager_steps():
             assert torch.allclose(p, q, rtol=1e-4, atol=1e-6), n
 
 
+def test_dense_optimizer_steps_on_packed_columns_match_the_cpu_route():
+    """Default (reference-semantics) optimiser over several steps with PACKED id columns: the sparse re-zeroing of the persistent
+    gradient buffers must follow the strided column views, or stale rows would be applied twice."""
+    from torch_rechub.b200.data import PackedColumns
+    from torch_rechub.trainers import CTRTrainer
+    torch.manual_seed(4)
+    m_c, dense, sparse = small_deepfm()
+    m_g = copy.deepcopy(m_c)
+    t_c = CTRTrainer(m_c, optimizer_fn=torch.optim.SGD, optimizer_params={"lr": 0.1}, device="cpu")
+    t_g = CTRTrainer(m_g, optimizer_fn=torch.optim.SGD, optimizer_params={"lr": 0.1}, device=DEV)
+    m_c.train()
+    m_g.train()
+    init = {n: p.detach().clone() for n, p in m_c.named_parameters()}
+    for i in range(4):
+        x, y = batch(128, seed=20 + i)
+        ids = torch.stack([x["C%d" % j] for j in range(4)], dim=1)
+        nums = torch.stack([x["I%d" % j] for j in range(3)], dim=1)
+        packed = PackedColumns(["C%d" % j for j in range(4)], ids.to(DEV), ["I%d" % j for j in range(3)], nums.to(DEV))
+        lc = float(t_c._train_step(x, y))
+        lg = float(t_g._train_step(packed, y.to(DEV)))
+        assert abs(lc - lg) < 1e-5, (i, lc, lg)
+    for (n, p), q in zip(m_g.named_parameters(), m_c.parameters()):
+        if n.endswith("mlp.0.bias") or n.endswith("mlp.4.bias"):
+            continue
+        moved = (q - init[n]).abs().max().item()
+        assert (p.cpu() - q).abs().max().item() <= 2e-3 * moved + 2e-6, n
+
+
 def test_trainer_with_packed_loader_and_graph(tmp_path):
     from torch_rechub.b200 import config
     from torch_rechub.b200.data import PackedLoader

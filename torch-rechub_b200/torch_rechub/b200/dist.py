@@ -77,6 +77,13 @@ class P2PExchange(object):
         self.h_rows.barrier(channel=0)
 
 
+def _snapshot(ids):
+    """The owner's id views alias the exchange's id buffer, which the NEXT forward overwrites before a dense optimiser's lazy
+    sparse clean reads it: record a copy (note_dirty already copies when the inputs are static graph buffers)."""
+    from . import config
+    return ids if config.static_inputs else ids.clone()
+
+
 class _ShardedP2P(torch.autograd.Function):
     """The sharded front end as ONE autograd node, all exchanges done by the engine's own kernels over NVLink peer memory:
 
@@ -107,7 +114,7 @@ class _ShardedP2P(torch.autograd.Function):
             cols[n].id_stride = ids.stride(0) if ids.shape[0] > 1 else 1
             cols[n].ids_are_i32 = int(ids.dtype == torch.int32)
             col_dest[n] = r
-        direct = front.direct if torch.is_grad_enabled() else None  # peer-mapped gradient buffers of every table (or None)
+        direct = front.direct if any(ctx.needs_input_grad) else None  # peer-mapped gradient buffers of every table (None: staged route / no backward)
         if direct is not None:
             # my own tables' buffers must be attached and clean BEFORE any peer's backward REDs into them: do it ahead of the
             # forward barriers (the staged route does this in its owner-side backward pass)
@@ -217,7 +224,7 @@ class _ShardedP2P(torch.autograd.Function):
             for r in ctx.orefs:
                 g, slot = _table.grad_target(r.weight)
                 if g is not None:
-                    _table.note_dirty(slot, r.ids)
+                    _table.note_dirty(slot, _snapshot(r.ids))
             return (None, None, None, None, d_lrw, d_lrb) + (None,) * len(ctx.orefs)
         # B3: the owner scatter-adds what every rank sent into its tables
         if ctx.orefs:
@@ -227,7 +234,7 @@ class _ShardedP2P(torch.autograd.Function):
                 "rh_fields_bwd")
             for r, (g, slot) in zip(ctx.orefs, targets):
                 if g is not None:
-                    _table.note_dirty(slot, r.ids)
+                    _table.note_dirty(slot, _snapshot(r.ids))
         ex.drows.zero_()  # ready for the next step's REDs: they can only start after the next forward's two barriers
         return (None, None, None, None, d_lrw, d_lrb) + (None,) * len(ctx.orefs)
 
@@ -467,11 +474,13 @@ class DistEngine(object):
 
     # -- one training step -------------------------------------------------------------------------------------
     def train_step(self, trainer, x_dict, y):
-        loss = trainer._loss(x_dict, y)
+        # zero_grad BEFORE the forward: with direct gradients the owned buffers are cleaned and re-attached ahead of the forward
+        # barriers, i.e. before any peer's backward can RED into them
         for p in self.owned:
             p.grad = None
         for p in self.dense_params:
             p.grad = None  # autograd then hands over fresh gradient tensors (no accumulate kernels)
+        loss = trainer._loss(x_dict, y)
         (loss / self.world).backward()
         # ONE bucket: [dense gradients ..., loss]; a parameter that got no gradient contributes zeros
         pieces = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in self.dense_params]

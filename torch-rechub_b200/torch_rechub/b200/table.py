@@ -78,6 +78,8 @@ def clean(weight, slot=None):
         L = _lib.lib()
         vocab, dim = slot.buffer.shape
         for ids, _ in slot.pending:
+            if not ids.is_contiguous():
+                ids = ids.contiguous()  # a column view of a packed (B, F) id block: rh_rows_zero takes a dense id list
             _lib.check(L.rh_rows_zero(slot.buffer.data_ptr(), vocab, dim, ids.data_ptr(), int(ids.dtype == torch.int32), ids.numel(), _lib.stream_ptr()), "rh_rows_zero")
     slot.pending = []
     slot.all_dirty = False
