@@ -46,5 +46,9 @@ pipelined_inputs = _flag("RECHUB_B200_PIPELINED_INPUTS", True)
 # loop never drains the GPU.  Epoch statistics are unchanged; an IndexError surfaces one batch later than in the reference.
 lagged_loss = _flag("RECHUB_B200_LAGGED_LOSS", True)
 
+# Tower backward: run a layer's weight-gradient GEMM on a second stream next to its input-gradient GEMM (they only share
+# d_h, and each fills about half of the 148 SMs at batch 4096).
+concurrent_tower_bwd = _flag("RECHUB_B200_CONCURRENT_BWD", True)
+
 # Set by the graph runner while inputs live in static buffers that the next batch overwrites.
 static_inputs = False

@@ -77,11 +77,10 @@ class P2PExchange(object):
         self.h_rows.barrier(channel=0)
 
 
-def _snapshot(ids):
+def _snapshot(front, ids):
     """The owner's id views alias the exchange's id buffer, which the NEXT forward overwrites before a dense optimiser's lazy
-    sparse clean reads it: record a copy (note_dirty already copies when the inputs are static graph buffers)."""
-    from . import config
-    return ids if config.static_inputs else ids.clone()
+    sparse clean reads it: record a copy then.  The row-wise optimiser consumes (and re-zeroes) the rows inside the same step."""
+    return ids.clone() if front.lazy_clean else ids
 
 
 class _ShardedP2P(torch.autograd.Function):
@@ -218,13 +217,16 @@ class _ShardedP2P(torch.autograd.Function):
         ops.check(
             L.rh_fields_bwd(arr, len(ctx.srefs), dim, b, tile.data_ptr(), ctx.ld, ops.ptr(d_tile), d_ld, ops.ptr(d_yfm) if has_fm else None, ops.ptr(d_ylr) if has_fm else None,
                             ops.ptr(lr_w) if has_fm else None, ops.ptr(fsum) if has_fm else None, ops.ptr(d_lrw) if has_fm else None, ops.ptr(d_lrb) if has_fm else None, err, st), "rh_fields_bwd")
-        ex.barrier()
+        if ctx.direct is not None and front.defer_barrier:
+            front.deferred = ex  # the step runs this barrier after launching the dense all-reduce, next to the row-wise update
+        else:
+            ex.barrier()
         if ctx.direct is not None:
-            # every rank's REDs have landed in my buffers: only the bookkeeping of which rows are dirty is left
+            # once every rank's REDs have landed in my buffers only the bookkeeping of which rows are dirty is left
             for r in ctx.orefs:
                 g, slot = _table.grad_target(r.weight)
                 if g is not None:
-                    _table.note_dirty(slot, _snapshot(r.ids))
+                    _table.note_dirty(slot, _snapshot(front, r.ids))
             return (None, None, None, None, d_lrw, d_lrb) + (None,) * len(ctx.orefs)
         # B3: the owner scatter-adds what every rank sent into its tables
         if ctx.orefs:
@@ -234,7 +236,7 @@ class _ShardedP2P(torch.autograd.Function):
                 "rh_fields_bwd")
             for r, (g, slot) in zip(ctx.orefs, targets):
                 if g is not None:
-                    _table.note_dirty(slot, _snapshot(r.ids))
+                    _table.note_dirty(slot, _snapshot(front, r.ids))
         ex.drows.zero_()  # ready for the next step's REDs: they can only start after the next forward's two barriers
         return (None, None, None, None, d_lrw, d_lrb) + (None,) * len(ctx.orefs)
 
@@ -262,6 +264,9 @@ class ShardedFront(object):
         self._plans = {}
         from . import config
         self.use_p2p = device.type == "cuda" and config.p2p_exchange
+        self.lazy_clean = True  # a dense optimiser cleans the gradient rows lazily, in the next step (set per step by DistEngine)
+        self.defer_barrier = False  # DistEngine.train_step issues the post-backward barrier itself, after launching the all-reduce
+        self.deferred = None
         self.direct = None  # table name -> (peer-mapped gradient buffer pointer, vocab, padding_idx); set by DistEngine
 
     def owner_of(self, fea):
@@ -420,6 +425,7 @@ class DistEngine(object):
                         tbl.weight.data = torch.empty((0, tbl.weight.shape[1]), dtype=tbl.weight.dtype, device=tbl.weight.device)  # free it
                         tbl.weight.requires_grad_(False)
         self.grad_pool = None
+        self._inv_world = torch.full((), 1.0 / self.world, dtype=torch.float32, device=self.device)
         self._map_gradient_buffers()
         skip = {id(p) for p in self.owned} | {id(p) for p in self.foreign}
         self.dense_params = [p for p in model.parameters() if id(p) not in skip and p.requires_grad]
@@ -480,15 +486,26 @@ class DistEngine(object):
             p.grad = None
         for p in self.dense_params:
             p.grad = None  # autograd then hands over fresh gradient tensors (no accumulate kernels)
+        opt = trainer.optimizer
+        split = hasattr(opt, "rowwise") and hasattr(opt, "dense_engine")
+        for f in self.fronts:
+            f.lazy_clean, f.defer_barrier, f.deferred = not split, True, None
         loss = trainer._loss(x_dict, y)
-        (loss / self.world).backward()
+        loss.backward(self._inv_world)  # d(loss / world): the all-reduce SUM then yields the gradient of the global-batch mean
+        for f in self.fronts:
+            f.defer_barrier = False
         # ONE bucket: [dense gradients ..., loss]; a parameter that got no gradient contributes zeros
         pieces = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in self.dense_params]
         pieces.append((loss.detach() / self.world).reshape(1))
         torch.cat(pieces, out=self.flat)
         work = dist.all_reduce(self.flat, group=self.group, async_op=True)  # SUM of (local grad / world) = grad of the global-batch mean
-        opt = trainer.optimizer
-        split = hasattr(opt, "rowwise") and hasattr(opt, "dense_engine")
+        for f in self.fronts:  # every rank's row-gradient REDs must have landed before the owners consume their buffers
+            if f.deferred is not None:
+                f.deferred.barrier()
+                f.deferred = None
+                break  # one barrier orders all exchanges: every backward kernel of every rank precedes it
+        for f in self.fronts:
+            f.deferred = None
         if split:
             opt.rowwise.set_lr(float(opt.dense.param_groups[0]["lr"]))
             opt.rowwise.step()  # the owned tables' update does not need the all-reduce: it overlaps with it

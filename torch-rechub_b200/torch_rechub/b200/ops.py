@@ -453,10 +453,22 @@ def _padded_weight(W):
     return ent[1][:, :K]
 
 
-def _split_k_for(m_tiles, n_tiles, k_blocks):
-    """Enough K slices to put ~128 CTAs on the 148 SMs when the output has few tiles (weight gradients)."""
+def _split_k_for(m_tiles, n_tiles, k_blocks, budget=128):
+    """Enough K slices to put ~``budget`` CTAs on the 148 SMs when the output has few tiles (weight gradients)."""
     tiles = max(1, m_tiles * n_tiles)
-    return max(1, min(k_blocks, 128 // tiles))
+    return max(1, min(k_blocks, budget // tiles))
+
+
+_aux_streams = {}
+
+
+def _aux_stream(dev):
+    """Second stream of a device for the independent half of a backward step (forked and joined inside one autograd node)."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    st = _aux_streams.get(key)
+    if st is None:
+        st = _aux_streams[key] = torch.cuda.Stream(device=dev)
+    return st
 
 
 _salt_counter = [0]
@@ -540,8 +552,20 @@ class _TowerLayer(torch.autograd.Function):
         check(
             L.rh_bn_act_bwd(h.data_ptr(), cols, rows, cols, ptr(mean), ptr(var), float(cfg["eps"]), ptr(gamma), ptr(beta), cfg["act"], ptr(act_param), float(cfg["dice_eps"]), float(cfg["p_drop"]), cfg["seed"],
                             ptr(counter), g.data_ptr(), g_ld, int(training), d_h.data_ptr(), cols, d_gamma.data_ptr(), d_beta.data_ptr(), d_alpha.data_ptr() if ctx.has_param else None, stream_ptr()), "rh_bn_act_bwd")
+        from . import config
+        fork = None
         if ctx.use_tc:  # dW[cols, K] = d_h^T x: both operands read as stored (MN-major), K = rows split over CTAs
-            d_W = gemm3x(d_h, True, x2, True, cols, K, rows, split_k=_split_k_for((cols + 127) // 128, (K + 127) // 128, (rows + 31) // 32), out_cols=K)
+            concurrent = config.concurrent_tower_bwd and ctx.needs_input_grad[0]
+            split = _split_k_for((cols + 127) // 128, (K + 127) // 128, (rows + 31) // 32, budget=64 if concurrent else 128)
+            d_W = torch.zeros((cols, K), dtype=torch.float32, device=dev) if split > 1 else torch.empty((cols, K), dtype=torch.float32, device=dev)
+            if concurrent:
+                # dW and dX only share their input d_h: dW runs on a second stream (half the SMs each), joined before returning
+                cur, fork = torch.cuda.current_stream(), _aux_stream(dev)
+                fork.wait_stream(cur)
+                with torch.cuda.stream(fork):
+                    gemm3x(d_h, True, x2, True, cols, K, rows, split_k=split, out=d_W)
+            else:
+                gemm3x(d_h, True, x2, True, cols, K, rows, split_k=split, out=d_W)
         else:
             d_W = torch.mm(d_h.t(), x2)
         if not training and ctx.has_bias:  # eval: BN is affine, the Linear bias sees sum_rows d_h = d_beta * gamma * rstd
@@ -557,6 +581,8 @@ class _TowerLayer(torch.autograd.Function):
                 gemm3x(d_h, False, ctx.Wp, True, rows, K, cols, out=buf)
             else:
                 torch.mm(d_h, W, out=d_x)
+        if fork is not None:
+            torch.cuda.current_stream().wait_stream(fork)
         return (d_x, d_W, d_b if ctx.has_bias else None, d_gamma if gamma is not None else None, d_beta if beta is not None else None, d_alpha.view_as(act_param) if ctx.has_param else None, None)
 
 
