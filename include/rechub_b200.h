@@ -298,6 +298,20 @@ int rh_bn_act_bwd(const float* h, int64_t h_ld, int64_t rows, int cols,
                   float* d_h, int64_t d_h_ld,
                   float* d_gamma, float* d_beta, float* d_act_param, void* stream);
 
+/* Output head of a ranking tower in one pass: the MLP's output layer nn.Linear(k, 1) (reference basic/layers.py:279-280) fused
+ * with the model's tail  sigmoid(y_deep + extra0 + extra1)  — DeepFM's  y_linear + y_fm + y_deep  (models/ranking/deepfm.py:41-43).
+ *   x (rows, k) row stride x_ld;  w (k);  bias (1) or NULL;  extra0/extra1 (rows) or NULL;  out (rows)
+ *   out[r] = f(<x[r], w> + bias + extra0[r] + extra1[r]),  f = sigmoid if apply_sigmoid else identity.   k <= 1024. */
+int rh_head_fwd(const float* x, int64_t x_ld, int64_t rows, int k, const float* w, const float* bias,
+                const float* extra0, const float* extra1, int apply_sigmoid, float* out, void* stream);
+
+/* Backward of rh_head_fwd.  d_logit[r] = d_out[r] * out[r] * (1 - out[r]) (or d_out[r] without the sigmoid);
+ *   d_x[r, :] = d_logit[r] * w (or NULL);  d_w (k) += sum_r d_logit[r] * x[r, :];  d_b (1) += sum_r d_logit[r]  (both must
+ *   arrive zeroed, either may be NULL);  d_extra (rows) = d_logit (the gradient of every extra term), or NULL. */
+int rh_head_bwd(const float* x, int64_t x_ld, int64_t rows, int k, const float* w, const float* out,
+                const float* d_out, int apply_sigmoid, float* d_x, int64_t d_x_ld, float* d_w, float* d_b,
+                float* d_extra, void* stream);
+
 /* One launch of SGD / Adam / Adagrad (kinds as rh_rowwise_update) over n_tensors small dense tensors — the tower's
  * weights (the dense half of optimizer.step(), trainers/ctr_trainer.py:99).  params/grads/state1/state2: host arrays of
  * device pointers; numel: host array.  lr_dev / bias_corr_dev: the device scalars of rh_opt_advance. */

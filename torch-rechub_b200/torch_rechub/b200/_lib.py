@@ -57,6 +57,8 @@ PROTOTYPES = {
     "rh_colstats": [c_p, c_i64, c_i64, c_i, c_p, c_p, c_p, c_p, c_p, c_f, c_p],
     "rh_bn_act_fwd": [c_p, c_i64, c_i64, c_i, c_p, c_p, c_f, c_p, c_p, c_i, c_p, c_f, c_f, ctypes.c_uint32, c_p, c_p, c_i64, c_p],
     "rh_bn_act_bwd": [c_p, c_i64, c_i64, c_i, c_p, c_p, c_f, c_p, c_p, c_i, c_p, c_f, c_f, ctypes.c_uint32, c_p, c_p, c_i64, c_i, c_p, c_i64, c_p, c_p, c_p, c_p],
+    "rh_head_fwd": [c_p, c_i64, c_i64, c_i, c_p, c_p, c_p, c_p, c_i, c_p, c_p],
+    "rh_head_bwd": [c_p, c_i64, c_i64, c_i, c_p, c_p, c_p, c_i, c_p, c_i64, c_p, c_p, c_p, c_p],
     "rh_dense_update": [c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_f, c_f, c_f, c_f, c_p],
     "rh_gemm_tf32x3": [c_p, c_i64, c_i, c_p, c_i64, c_i, c_p, c_i64, c_i, c_i, c_i, c_p, c_i, c_p],
     "rh_din_attn_input_fwd": [c_p, c_i, c_p, c_i, c_i, c_p, c_p, c_i, c_i64, c_i, c_i, c_p, c_p, c_p, c_p, c_p],

@@ -50,5 +50,11 @@ lagged_loss = _flag("RECHUB_B200_LAGGED_LOSS", True)
 # d_h, and each fills about half of the 148 SMs at batch 4096).
 concurrent_tower_bwd = _flag("RECHUB_B200_CONCURRENT_BWD", True)
 
+# Hybrid optimiser: the row-wise table update and the dense tower update on two streams (they share only the step counter).
+concurrent_optimizers = _flag("RECHUB_B200_CONCURRENT_OPT", True)
+
+# Output head (Linear(K,1) + side terms + sigmoid) as one launch each way (rh_head_fwd/bwd) instead of ~10 library launches.
+fused_head = _flag("RECHUB_B200_FUSED_HEAD", True)
+
 # Set by the graph runner while inputs live in static buffers that the next batch overwrites.
 static_inputs = False

@@ -606,6 +606,49 @@ def tower_layer(x, linear, bn, act_code, act_param, dice_eps, p_drop, training):
 # =====================================================================================================
 # DIN target attention pieces
 # =====================================================================================================
+class _Head(torch.autograd.Function):
+    """p = f(x @ w^T + b + extras...), f = sigmoid or identity: the tower's ``Linear(K, 1)`` output layer fused with the model's
+    tail (reference basic/layers.py:279-280 + e.g. models/ranking/deepfm.py:41-43).  One launch forward, one backward."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, apply_sigmoid, *extras):
+        L = _lib.lib()
+        x2 = _rowmajor(x)
+        rows, K = x2.shape
+        ex = [e.contiguous() for e in extras]
+        out = torch.empty(rows, dtype=torch.float32, device=x2.device)
+        check(L.rh_head_fwd(x2.data_ptr(), x2.stride(0) if rows > 1 else K, rows, K, W.data_ptr(), ptr(b), ptr(ex[0]) if len(ex) > 0 else None, ptr(ex[1]) if len(ex) > 1 else None, int(apply_sigmoid),
+                            out.data_ptr(), stream_ptr()), "rh_head_fwd")
+        ctx.sig, ctx.n_extra, ctx.has_bias = bool(apply_sigmoid), len(ex), b is not None
+        ctx.save_for_backward(x2, W, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        L = _lib.lib()
+        x2, W, out = ctx.saved_tensors
+        rows, K = x2.shape
+        dev = x2.device
+        d_out = d_out.contiguous()
+        gbuf = torch.zeros(K + 1, dtype=torch.float32, device=dev)  # [d_w | d_b]
+        need_x = ctx.needs_input_grad[0]
+        d_x = torch.empty((rows, K), dtype=torch.float32, device=dev) if need_x else None
+        d_e = torch.empty(rows, dtype=torch.float32, device=dev) if ctx.n_extra else None
+        check(L.rh_head_bwd(x2.data_ptr(), x2.stride(0) if rows > 1 else K, rows, K, W.data_ptr(), out.data_ptr(), d_out.data_ptr(), int(ctx.sig), ptr(d_x), K, gbuf.data_ptr(),
+                            gbuf.data_ptr() + 4 * K, ptr(d_e), stream_ptr()), "rh_head_bwd")
+        return (d_x, gbuf[:K].view_as(W), gbuf[K:K + 1] if ctx.has_bias else None, None) + (d_e,) * ctx.n_extra
+
+
+def output_head(x, linear, extras=(), sigmoid=True):
+    """``f(linear(x).squeeze(1) + sum(extras))`` for a ``Linear(K, 1)`` on CUDA, or None when the shape is outside the kernel."""
+    from . import config
+    W = linear.weight
+    if (not config.fused_head or not x.is_cuda or x.dim() != 2 or x.dtype != torch.float32 or W.shape[0] != 1 or W.shape[1] > 1024 or W.dtype != torch.float32 or len(extras) > 2
+            or not W.is_contiguous() or any(e.dim() != 1 or e.shape[0] != x.shape[0] or e.dtype != torch.float32 for e in extras)):
+        return None
+    return _Head.apply(x, W, linear.bias, sigmoid, *extras)
+
+
 class _DinAttnInput(torch.autograd.Function):
     """(att_in (B*L, 4D), hist (B, L, D), target (B, D)) from the two tables; backward ends in the scatter-add."""
 

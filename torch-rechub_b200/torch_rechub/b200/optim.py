@@ -14,7 +14,7 @@ import ctypes
 
 import torch
 
-from . import _lib, table as _table
+from . import _lib, config, table as _table
 from ._lib import RhField, check, stream_ptr
 
 _KINDS = {torch.optim.SGD: 0, torch.optim.Adam: 1, torch.optim.Adagrad: 2}
@@ -70,9 +70,17 @@ class RowwiseOptimizer(object):
 
     # -- step ----------------------------------------------------------------------------------------
     def step(self):
+        self.advance()
+        self.apply()
+
+    def advance(self):
+        """Step counter += 1 and the Adam bias corrections, on the device (shared with the dense optimiser)."""
+        check(_lib.lib().rh_opt_advance(self._step_dev.data_ptr(), self._bc_dev.data_ptr(), self.betas[0], self.betas[1], stream_ptr()), "rh_opt_advance")
+
+    def apply(self):
+        """Update (and re-zero the gradient of) every row touched since the last step."""
         L = _lib.lib()
         st = stream_ptr()
-        check(L.rh_opt_advance(self._step_dev.data_ptr(), self._bc_dev.data_ptr(), self.betas[0], self.betas[1], st), "rh_opt_advance")
         # one (table, id-list) entry per lookup recorded by the backward kernels
         entries = []
         for p in self.params:
@@ -145,16 +153,22 @@ class DenseOptimizer(object):
         self.rw = rowwise
         self.state = {}
 
-    def step(self):
-        L = _lib.lib()
+    def prepare(self):
+        """Allocate the moment buffers of every parameter that has a gradient (on the caller's stream)."""
         rw = self.rw
         ps = [p for p in self.params if p.grad is not None]
-        if not ps:
-            return
         for p in ps:
             if id(p) not in self.state:
                 self.state[id(p)] = (torch.zeros_like(p, memory_format=torch.contiguous_format) if rw.kind != 0 else None,
                                      torch.zeros_like(p, memory_format=torch.contiguous_format) if rw.kind == 1 else None)
+        return ps
+
+    def step(self):
+        L = _lib.lib()
+        rw = self.rw
+        ps = self.prepare()
+        if not ps:
+            return
         grads = [p.grad if p.grad.is_contiguous() else p.grad.contiguous() for p in ps]
         n = len(ps)
         numel = (ctypes.c_int64 * n)(*[p.numel() for p in ps])
@@ -213,8 +227,22 @@ class HybridOptimizer(object):
     def step(self):
         lr = self.dense.param_groups[0]["lr"]
         self.rowwise.set_lr(float(lr) if not torch.is_tensor(lr) else float(lr.item()))
-        self.rowwise.step()  # advances the shared step counter / bias corrections first
-        self.dense_engine.step()
+        self.rowwise.advance()  # the shared step counter / bias corrections first
+        dev = self.dense_engine.params[0].device if self.dense_engine.params else None
+        if config.concurrent_optimizers and dev is not None and dev.type == "cuda":
+            # the touched-row update (random 64-B accesses, latency-bound) and the tower update (a few 100 k contiguous floats)
+            # share nothing but the step counter: run them side by side
+            from . import ops
+            cur, aux = torch.cuda.current_stream(), ops._aux_stream(dev)
+            self.dense_engine.prepare()
+            aux.wait_stream(cur)
+            with torch.cuda.stream(aux):
+                self.dense_engine.step()
+            self.rowwise.apply()
+            cur.wait_stream(aux)
+        else:
+            self.rowwise.apply()
+            self.dense_engine.step()
 
     def zero_grad(self, set_to_none=True):
         self.rowwise.zero_grad(set_to_none)

@@ -295,8 +295,27 @@ class MLP(nn.Module):
     def forward(self, x):
         if not x.is_cuda:
             return self.mlp(x)
-        from ..b200 import ops
+        return self._forward_cuda(x, len(self.mlp))
+
+    def forward_head(self, x, extras=(), sigmoid=True):
+        """``f(self(x).squeeze(1) + sum(extras))`` with the ``Linear(., 1)`` output layer, the per-sample ``extras`` (``(B,)``
+        tensors) and the sigmoid in ONE launch (``rh_head_fwd``); None when this tower has no such head or ``x`` is not on CUDA."""
         mods = list(self.mlp)
+        if not x.is_cuda or not mods or not isinstance(mods[-1], nn.Linear) or mods[-1].out_features != 1:
+            return None
+        from ..b200 import ops
+        h = self._forward_cuda(x, len(mods) - 1)
+        y = ops.output_head(h, mods[-1], extras, sigmoid)
+        if y is None:  # outside the kernel's shapes: finish with the library route
+            y = mods[-1](h).squeeze(1)
+            for e in extras:
+                y = y + e
+            y = torch.sigmoid(y) if sigmoid else y
+        return y
+
+    def _forward_cuda(self, x, n_mods):
+        from ..b200 import ops
+        mods = list(self.mlp)[:n_mods]
         i = 0
         while i < len(mods):
             m = mods[i]

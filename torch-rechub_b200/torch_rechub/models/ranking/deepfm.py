@@ -83,6 +83,14 @@ class DeepFM(torch.nn.Module):
         idx = torch.tensor([c for s0 in starts for c in range(s0, s0 + dim)], device=input_deep.device)
         return input_deep.index_select(1, idx).unflatten(1, (n, dim))
 
+    def _tail(self, input_deep, y_fm, y_linear):
+        """sigmoid(y_linear + y_fm + mlp(input_deep)) with the (B,) per-sample terms of the fused front end (deepfm.py:41-43)."""
+        p = self.mlp.forward_head(input_deep, (y_linear, y_fm), sigmoid=True)
+        if p is not None:
+            return p
+        y = y_linear.unsqueeze(1) + y_fm.unsqueeze(1) + self.mlp(input_deep)
+        return torch.sigmoid(y.squeeze(1))
+
     def forward(self, x):
         front = self.embedding._dist
         if front is not None:
@@ -93,8 +101,7 @@ class DeepFM(torch.nn.Module):
                        len({f.name for f in self.fm_features}) == len(self.fm_features) <= 64)
             if fusable:  # ONE exchange; the receiving kernel unpacks the rows and reduces FM + LR in the same pass
                 input_deep, y_fm, y_linear = front.run(x, self.deep_features, fm_features=self.fm_features, lr=(self.linear.fc.weight, self.linear.fc.bias))
-                y = y_linear.unsqueeze(1) + y_fm.unsqueeze(1) + self.mlp(input_deep)
-                return torch.sigmoid(y.squeeze(1))
+                return self._tail(input_deep, y_fm, y_linear)
             input_deep = self.embedding(x, self.deep_features, squeeze_dim=True)
             input_fm = self._fm_from_deep(input_deep) if self.fm_features else None
             if input_fm is None:
@@ -105,8 +112,7 @@ class DeepFM(torch.nn.Module):
         if plan is not None:
             from ...b200 import ops
             input_deep, y_fm, y_linear = ops.fused_tile(plan, self.linear.fc.weight, self.linear.fc.bias)
-            y = y_linear.unsqueeze(1) + y_fm.unsqueeze(1) + self.mlp(input_deep)
-            return torch.sigmoid(y.squeeze(1))
+            return self._tail(input_deep, y_fm, y_linear)
         input_deep = self.embedding(x, self.deep_features, squeeze_dim=True)  # (B, deep_dims)
         input_fm = self.embedding(x, self.fm_features, squeeze_dim=False)  # (B, n_fm, D)
         y_linear = self.linear(input_fm.flatten(start_dim=1))
