@@ -333,3 +333,37 @@ def test_double_lookup_accumulates_and_sparse_zero():
             first = g.clone()
         else:
             assert torch.allclose(g, first, rtol=1e-5, atol=1e-6)  # duplicates accumulate through atomics: order varies
+
+
+@pytest.mark.parametrize("rows,k,n_extra,sig,bias", [(1, 1, 0, True, True), (5, 17, 1, False, True), (4096, 128, 2, True, True), (777, 300, 2, True, False), (64, 1024, 1, True, True)])
+def test_output_head_matches_torch(rows, k, n_extra, sig, bias):
+    """rh_head_fwd/bwd (Linear(K,1) + side terms + sigmoid) against the library ops it replaces (layers.py:279-280, deepfm.py:41-43)."""
+    from torch_rechub.b200 import ops
+    g = torch.Generator().manual_seed(rows + k)
+    lin = torch.nn.Linear(k, 1, bias=bias).to(DEV)
+    x = torch.randn(rows, k, generator=g).to(DEV).requires_grad_(True)
+    extras = [torch.randn(rows, generator=g).to(DEV).requires_grad_(True) for _ in range(n_extra)]
+    got = ops.output_head(x, lin, extras, sigmoid=sig)
+    assert got is not None and got.shape == (rows,)
+    x_r = x.detach().clone().requires_grad_(True)
+    lin_r = copy.deepcopy(lin)
+    extras_r = [e.detach().clone().requires_grad_(True) for e in extras]
+    ref = lin_r(x_r).squeeze(1)
+    for e in extras_r:
+        ref = ref + e
+    ref = torch.sigmoid(ref) if sig else ref
+    assert_close(got, ref, rtol=1e-5, atol=1e-6, what="head forward")
+    w_out = torch.randn(rows, generator=g).to(DEV)
+    (got * w_out).sum().backward()
+    (ref * w_out).sum().backward()
+
+    def scale_close(a, b, what):
+        scale = float(b.abs().max()) + 1e-12
+        assert float((a - b).abs().max()) <= 2e-5 * scale + 1e-7, what
+
+    scale_close(x.grad, x_r.grad, "d_x")
+    scale_close(lin.weight.grad, lin_r.weight.grad, "d_w")
+    if bias:
+        scale_close(lin.bias.grad, lin_r.bias.grad, "d_b")
+    for e, e_r in zip(extras, extras_r):
+        scale_close(e.grad, e_r.grad, "d_extra")
