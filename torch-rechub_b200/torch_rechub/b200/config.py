@@ -51,7 +51,7 @@ lagged_loss = _flag("RECHUB_B200_LAGGED_LOSS", True)
 concurrent_tower_bwd = _flag("RECHUB_B200_CONCURRENT_BWD", True)
 
 # Hybrid optimiser: the row-wise table update and the dense tower update on two streams (they share only the step counter).
-concurrent_optimizers = _flag("RECHUB_B200_CONCURRENT_OPT", True)
+concurrent_optimizers = _flag("RECHUB_B200_CONCURRENT_OPT", False)  # measured: no gain at batch 4096 (0.2258 vs 0.2253 ms)
 
 # Output head (Linear(K,1) + side terms + sigmoid) as one launch each way (rh_head_fwd/bwd) instead of ~10 library launches.
 fused_head = _flag("RECHUB_B200_FUSED_HEAD", True)
