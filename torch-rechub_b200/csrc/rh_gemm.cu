@@ -97,16 +97,12 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 //             atom = 32 MN elements (128 B) x 4 k rows (512 B), 32-B chunks XOR-ed with (row & 3).  Our tile = four TMA
 //             boxes {32 MN, 32 K} of 4096 B: MN groups LBO = 4096 B apart, 4-k groups SBO = 512 B apart; one MMA k-step
 //             (8 k rows) = +1024 B.
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, bool mn_major, int variant = 0) {
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, bool mn_major) {
   uint64_t lbo = 1u, sbo = 1024u >> 4, type = 2;
   if (mn_major) {
     type = 1;
     lbo = 4096u >> 4;
     sbo = 512u >> 4;
-    if (variant == 1) {
-      lbo = 512u >> 4;
-      sbo = 4096u >> 4;
-    }
   }
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (type << 61);
 }
@@ -119,7 +115,6 @@ struct GemmP {
   int a_mn, b_mn;   // operand majors: 0 = K-major, 1 = MN-major
   int kblocks_per_split;
   int reduce;       // 1: red.global.add into C (split-K), 0: plain stores
-  int variant;      // debug: descriptor variant for MN-major operands
 };
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -194,8 +189,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (lane == 0) {
         const uint32_t base = smem_u32(smem + (size_t)s * kStageBytes);
-        const uint64_t a_hi = make_desc(base, p.a_mn != 0, p.variant), b_hi = make_desc(base + kTileBytes, p.b_mn != 0, p.variant);
-        const uint64_t a_lo = make_desc(base + 2 * kTileBytes, p.a_mn != 0, p.variant), b_lo = make_desc(base + 3 * kTileBytes, p.b_mn != 0, p.variant);
+        const uint64_t a_hi = make_desc(base, p.a_mn != 0), b_hi = make_desc(base + kTileBytes, p.b_mn != 0);
+        const uint64_t a_lo = make_desc(base + 2 * kTileBytes, p.a_mn != 0), b_lo = make_desc(base + 3 * kTileBytes, p.b_mn != 0);
 #pragma unroll
         for (int kk = 0; kk < kBK / 8; ++kk) {
           const uint64_t da = (uint64_t)(kk * a_step), db = (uint64_t)(kk * b_step);
@@ -370,7 +365,6 @@ extern "C" int rh_gemm_tf32x3(const float* A, int64_t lda, int a_mn_major, const
   p.b_mn = b_mn_major != 0;
   p.kblocks_per_split = per;
   p.reduce = split_k > 1 ? 1 : 0;
-  p.variant = getenv("RH_GEMM_VARIANT") ? atoi(getenv("RH_GEMM_VARIANT")) : 0;
 
   static bool configured = false;
   if (!configured) {
