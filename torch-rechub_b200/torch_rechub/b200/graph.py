@@ -39,6 +39,10 @@ class LaggedReader(object):
     def pending(self):
         return len(self.queue)
 
+    def reset(self):
+        """Forget results of an interrupted loop."""
+        self.queue.clear()
+
     def push(self, loss):
         from . import _lib
         if len(self.queue) == self.depth:
@@ -81,6 +85,8 @@ class GraphedStep(object):
             print("[rechub-b200] cuda_graph needs config.rowwise_optimizer (dense optimisers run eagerly)")
 
     def _signature(self, x_dict, y):
+        if isinstance(x_dict, PackedColumns):  # three packed tensors describe all the columns: keep the per-step host cost flat
+            return tuple((None if t is None else (tuple(t.shape), t.dtype)) for t in (x_dict.ids, x_dict.nums, x_dict.seqs)) + (tuple(y.shape), y.dtype)
         return tuple((k, tuple(v.shape), v.dtype) for k, v in x_dict.items()) + (tuple(y.shape), y.dtype)
 
     def _capture(self, x_dict, y):

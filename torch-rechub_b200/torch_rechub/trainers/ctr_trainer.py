@@ -95,6 +95,7 @@ class CTRTrainer(object):
         self.reg_loss_fn = RegularizationLoss(**regularization_params)
         self.model_logger = model_logger
         self._graph_step = None
+        self._lagged = None
 
     # ---------------------------------------------------------------------------------------------
     def _make_optimizer(self, optimizer_fn, optimizer_params):
@@ -138,7 +139,10 @@ class CTRTrainer(object):
         if on_cuda:
             from ..b200 import _lib, config, graph
             if config.lagged_loss:
-                lagged = graph.LaggedReader(self.device)
+                if self._lagged is None:
+                    self._lagged = graph.LaggedReader(self.device)  # pinned slots + events, kept across epochs
+                lagged = self._lagged
+                lagged.reset()
         tk0 = tqdm.tqdm(data_loader, desc="train", smoothing=0, mininterval=1.0)
 
         def account(loss_value):
