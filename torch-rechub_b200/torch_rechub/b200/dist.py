@@ -88,8 +88,10 @@ class _ShardedP2P(torch.autograd.Function):
 
       forward   rh_ids_scatter (ids -> owners)  | barrier | rh_fields_fwd_p2p (owner gathers, rows land in the samples' GPUs)
                 | barrier | rh_fields_fwd on the received rows (unpack + dense columns + FM + LR)
-      backward  rh_fields_bwd with peer table_grad pointers (row gradients RED into the owners' buffers over NVLink)
-                | barrier | rh_fields_bwd on the owner (scatter-add into its tables) | barrier
+      backward  direct gradients (default): rh_fields_bwd REDs every row gradient over NVLink into the OWNER's gradient buffer
+                at the row id | barrier (issued by DistEngine.train_step after it launched the dense all-reduce)
+                staged gradients: rh_fields_bwd REDs into the owner's staging buffer | barrier | rh_fields_bwd on the owner
+                (scatter-add into its tables) | re-zero the staging buffer
     """
 
     @staticmethod
@@ -244,7 +246,9 @@ class _ShardedP2P(torch.autograd.Function):
 class ShardedFront(object):
     """Field-sharded replacement for ``EmbeddingLayer.forward`` (installed by :func:`attach`).
 
-    CUDA route per call (all launches static-shaped, graph-capturable):
+    CUDA route (default, ``config.p2p_exchange``): :class:`_ShardedP2P` — ids, rows and row gradients move through NVLink peer
+    memory inside the engine's own kernels (see its docstring).
+    NCCL route (``RECHUB_B200_P2P=0``; the checker of the peer-memory route), all launches static-shaped and graph-capturable:
       1 kernel    pack my samples' ids per owner                       (index_select / stack)
       NCCL        ids all-to-all
       1 launch    owner-side ``rh_fields_fwd`` over the global batch   -> rows (W*b, fmax*dim)

@@ -486,8 +486,10 @@ def _dropout_seed(module):
 class _TowerLayer(torch.autograd.Function):
     """y = dropout(act(bn(x @ W^T + b))): one tower layer (basic/layers.py:282-285) as GEMM + statistics + ONE fused pass.
 
-    The GEMMs are library calls (cuBLAS through torch.mm, fp32); everything between them is rh_colstats /
-    rh_bn_act_fwd / rh_bn_act_bwd.  No activation, mask or normalised copy is stored: backward recomputes from h.
+    The GEMMs run on the tensor cores through rh_gemm_tf32x3 (fp32-accurate 3xTF32; batches under 128 rows use torch.mm);
+    everything between them is rh_colstats / rh_bn_act_fwd / rh_bn_act_bwd.  No activation, mask or normalised copy is
+    stored: backward recomputes from h.  In backward the weight-gradient GEMM runs on a second stream next to the
+    input-gradient GEMM (config.concurrent_tower_bwd).
     """
 
     @staticmethod
