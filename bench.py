@@ -164,16 +164,30 @@ def build_model(device):
     return model.to(device), dense, sparse
 
 
-def make_pool(n_pool, seed):
-    """n_pool synthetic batches in pinned host memory, packed (ids (B,26) int64, dense (B,13) fp32, labels (B,) fp32)."""
+ZIPF_ALPHA = 1.05  # the secondary, skewed id distribution
+
+
+def make_pool(n_pool, seed, ids_dist="uniform"):
+    """n_pool synthetic batches in pinned host memory, packed (ids (B,26) int64, dense (B,13) fp32, labels (B,) fp32).
+    ``ids_dist``: "uniform" (the primary workload: worst case for L2) or "zipf" (rank r drawn with p ~ r^-1.05, ranks
+    scattered over the vocabulary by a fixed multiplicative hash so that hot rows are not neighbours)."""
     import torch
     from torch_rechub.b200.data import PackedColumns
     g = torch.Generator().manual_seed(seed)
     pool = []
     id_names = ["C%d" % i for i in range(N_SPARSE)]
     num_names = ["I%d" % i for i in range(N_DENSE)]
+    cdf = None
+    if ids_dist == "zipf":
+        w = torch.arange(1, VOCAB + 1, dtype=torch.float64).pow_(-ZIPF_ALPHA)
+        cdf = torch.cumsum(w / w.sum(), 0)
     for _ in range(n_pool):
-        ids = torch.randint(0, VOCAB, (BATCH, N_SPARSE), generator=g).pin_memory()
+        if cdf is None:
+            ids = torch.randint(0, VOCAB, (BATCH, N_SPARSE), generator=g)
+        else:
+            rank = torch.searchsorted(cdf, torch.rand(BATCH, N_SPARSE, generator=g, dtype=torch.float64)).clamp_(max=VOCAB - 1)
+            ids = (rank * 2654435761) % VOCAB  # odd multiplier: a bijection on ranks for any vocabulary not divisible by it
+        ids = ids.pin_memory()
         nums = torch.rand(BATCH, N_DENSE, generator=g).pin_memory()
         y = torch.randint(0, 2, (BATCH,), generator=g).float().pin_memory()
         pool.append((PackedColumns(id_names, ids, num_names, nums), y))
@@ -267,7 +281,7 @@ def run_b200_arm(args):
 
     model, dense, sparse = build_model(device)
     trainer = CTRTrainer(model, device=str(device), n_epoch=1)  # defaults: Adam lr 1e-3 weight_decay 1e-5 (ctr_trainer.py:60)
-    pool = make_pool(N_POOL, seed=2022 + rank)
+    pool = make_pool(N_POOL, seed=2022 + rank, ids_dist=args.ids)
     pool_dev = [(x.to(device, non_blocking=False), y.to(device)) for x, y in pool]
     torch.cuda.synchronize()
 
@@ -395,7 +409,8 @@ def run_b200_arm(args):
         "vs_baseline": None,
         "dtype": "fp32",
         "data": "synthetic",
-        "config": workload_config("single GPU" if world == 1 else "tables sharded by field over %d ranks + dp tower" % world),
+        "config": dict(workload_config("single GPU" if world == 1 else "tables sharded by field over %d ranks + dp tower" % world),
+                       **({} if args.ids == "uniform" else {"ids": "zipf(alpha=%.2f) int64, %d distinct batches cycled (secondary workload)" % (ZIPF_ALPHA, N_POOL)})),
         "clocks": clocks,
         "e2e": {"value": total_samples / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8, "ms_per_step": e2e_s / args.steps * 1e3,
                 "api": "CTRTrainer.train_one_epoch(loader of pinned PackedColumns batches)"},
@@ -428,6 +443,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ids", default="uniform", choices=["uniform", "zipf"], help="id distribution of the synthetic batches (uniform = the headline workload)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
