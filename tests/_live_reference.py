@@ -48,6 +48,9 @@ def load_reference():
         importlib.import_module("torch_rechub.basic.layers")
         importlib.import_module("torch_rechub.basic.features")
         importlib.import_module("torch_rechub.utils.data")
+        importlib.import_module("torch_rechub.utils.match")
+        importlib.import_module("torch_rechub.models.matching")
+        importlib.import_module("torch_rechub.basic.loss_func")
         assert ref.__file__.startswith(REFERENCE_ROOT), ref.__file__
     finally:
         sys.path.remove(REFERENCE_ROOT)

@@ -1,7 +1,8 @@
 """Losses on the CTR path (mirror of reference ``torch_rechub/basic/loss_func.py:6-68``).
 
-Only ``RegularizationLoss`` is on the hot path (``trainers/ctr_trainer.py:94`` calls it every step);
-the matching/generative losses of the reference file are out of scope.
+``RegularizationLoss`` is on the CTR hot path (``trainers/ctr_trainer.py:94`` calls it every step); ``BPRLoss`` is the
+pair-wise criterion of ``MatchTrainer`` (reference ``loss_func.py:95-107``).  The generative-model losses of
+the reference file are out of scope.
 """
 import torch
 import torch.nn as nn
@@ -44,3 +45,16 @@ class RegularizationLoss(nn.Module):
             if l2 > 0:
                 total = total + l2 * torch.sum(p**2)
         return total
+
+
+class BPRLoss(nn.Module):
+    """Bayesian personalised ranking: ``mean(-log sigmoid(pos - neg))`` (reference ``loss_func.py:95-107``).
+
+    ``neg_score`` may hold one negative per sample ``(B,)`` or several ``(B, K)``; ``in_batch_neg`` is accepted for call
+    compatibility with ``MatchTrainer`` and changes nothing.
+    """
+
+    def forward(self, pos_score, neg_score, in_batch_neg=False):
+        pos = pos_score.reshape(-1)
+        margin = pos - neg_score if neg_score.dim() == 1 else pos.unsqueeze(1) - neg_score
+        return -torch.log(torch.sigmoid(margin)).mean()

@@ -2,7 +2,8 @@
 
 Host-side code; only the pieces ``examples/ranking/run_criteo.py`` and ``run_amazon_electronics.py`` use
 (``DataGenerator``, ``TorchDataset``, ``df_to_dict``, ``generate_seq_feature``, ``pad_sequences``,
-``get_auto_embedding_dim``).  Matching / generative dataset helpers are out of scope.
+``get_auto_embedding_dim``) plus ``MatchDataGenerator`` for the two-tower path.  Generative dataset helpers are
+out of scope.
 """
 import random
 
@@ -42,6 +43,20 @@ class PredictDataset(Dataset):
 
     def __len__(self):
         return len(self.x[next(iter(self.x.keys()))])
+
+
+class MatchDataGenerator(object):
+    """Train / test-user / all-item DataLoaders of the matching examples (reference ``:41-58``): a labelled ``TorchDataset`` when
+    ``y`` is given, a label-free one for pair-wise training; the test and item loaders keep their order (ground-truth alignment)."""
+
+    def __init__(self, x, y=[]):
+        super().__init__()
+        self.dataset = TorchDataset(x, y) if len(y) != 0 else PredictDataset(x)
+
+    def generate_dataloader(self, x_test_user, x_all_item, batch_size, num_workers=8):
+        train = DataLoader(self.dataset, batch_size=batch_size, shuffle=True, num_workers=num_workers)
+        ordered = lambda cols: DataLoader(PredictDataset(cols), batch_size=batch_size, shuffle=False, num_workers=num_workers)
+        return train, ordered(x_test_user), ordered(x_all_item)
 
 
 class DataGenerator(object):
