@@ -403,3 +403,95 @@ def din_forward_backward(sd, x, y, feature_names, history_names, target_names, s
         add(n, x[n], d)
     out["grads"] = grads
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# two-tower retrieval
+# ---------------------------------------------------------------------------------------------------------
+def l2_normalize(h, eps=1e-12):
+    """F.normalize(h, p=2, dim=1) (models/matching/dssm.py:61,71): h / max(||h||_2, eps)."""
+    n = np.maximum(np.sqrt((h * h).sum(axis=1, keepdims=True)), eps)
+    return h / n, n
+
+
+def l2_normalize_backward(u, n, d_u):
+    """d/dh of h / ||h||: (d_u - u <u, d_u>) / ||h|| (rows whose norm was clamped are never produced by the towers)."""
+    return (d_u - u * (u * d_u).sum(axis=1, keepdims=True)) / n
+
+
+def tower_tile(sd, x, features, dtype=np.float64):
+    """EmbeddingLayer.forward(squeeze_dim=True) over sparse AND pooled sequence features in list order (basic/layers.py:80-117).
+    ``features``: ``("sparse", name, table)`` or ``("seq", name, table, pooling)`` with ``table`` the owning table's name."""
+    parts = []
+    for f in features:
+        w = _f(sd["embedding.embed_dict.%s.weight" % f[2]], dtype)
+        parts.append(embedding_lookup(w, x[f[1]]).astype(dtype) if f[0] == "sparse" else seq_pool(w, x[f[1]], f[3], None, dtype))
+    return np.concatenate(parts, axis=1)
+
+
+def tower_tile_backward(sd, x, features, d_tile, grads, dtype=np.float64):
+    """Dense table gradients of tower_tile, accumulated into ``grads`` (several features may share one table)."""
+    col = 0
+    for f in features:
+        key = "embedding.embed_dict.%s.weight" % f[2]
+        shape = sd[key].shape
+        d = d_tile[:, col:col + shape[1]]
+        col += shape[1]
+        ids = np.asarray(x[f[1]]).astype(np.int64)
+        if f[0] == "sparse":
+            g = embedding_grad(shape, ids, d, None, dtype)
+        else:
+            m = input_mask(ids, None).astype(dtype)  # (B, L)
+            scale = m / (m.sum(axis=1, keepdims=True) + 1e-16) if f[3] == "mean" else m
+            g = embedding_grad(shape, ids.reshape(-1), (scale[:, :, None] * d[:, None, :]).reshape(-1, shape[1]), None, dtype)
+        grads[key] = grads.get(key, 0) + g
+    return grads
+
+
+def hard_negative_indices(scores, k):
+    """utils/match.py:131-135: per row the k best-scoring columns other than the diagonal, best first."""
+    masked = scores.copy()
+    np.fill_diagonal(masked, -np.inf)
+    return np.argsort(-masked, axis=1, kind="stable")[:, :k]
+
+
+def dssm_forward_backward(sd, x, user_features, item_features, n_user_hidden, n_item_hidden, neg_ratio, activation="relu", train=True, backward=True, dtype=np.float64):
+    """DSSM towers (models/matching/dssm.py:40-72) + MatchTrainer's in-batch branch with HARD negatives and cross entropy
+    (trainers/match_trainer.py:118-140, utils/match.py:104-161).  Returns the tower embeddings, the point-wise probability
+    ``sigmoid(<u, v>)``, the (B, B) scores, the sampled columns, the ``[positive | negatives]`` logits, the loss and — with
+    ``backward`` — every parameter gradient of that loss."""
+    tu = tower_tile(sd, x, user_features, dtype)
+    ti = tower_tile(sd, x, item_features, dtype)
+    hu, cu = mlp_forward(sd, "user_mlp.mlp.", tu, n_user_hidden, activation, train, output_layer=False, dtype=dtype)
+    hi, ci = mlp_forward(sd, "item_mlp.mlp.", ti, n_item_hidden, activation, train, output_layer=False, dtype=dtype)
+    u, nu = l2_normalize(hu)
+    v, nv = l2_normalize(hi)
+    scores = u @ v.T
+    B = scores.shape[0]
+    k = neg_ratio if (neg_ratio is not None and 0 < neg_ratio <= B - 1) else B - 1
+    neg = hard_negative_indices(scores, k)
+    rows = np.arange(B)
+    logits = np.concatenate([scores[rows, rows][:, None], scores[rows[:, None], neg]], axis=1)
+    mx = logits.max(axis=1, keepdims=True)
+    lse = mx[:, 0] + np.log(np.exp(logits - mx).sum(axis=1))
+    loss = float(np.mean(lse - logits[:, 0]))  # CrossEntropyLoss(mean) with the positive in column 0
+    out = {"user_emb": u, "item_emb": v, "prob": 1 / (1 + np.exp(-(u * v).sum(axis=1))), "scores": scores, "neg_idx": neg, "logits": logits, "loss": loss}
+    if not backward:
+        return out
+    d_logits = np.exp(logits - lse[:, None])
+    d_logits[:, 0] -= 1.0
+    d_logits /= B
+    d_scores = np.zeros_like(scores)
+    d_scores[rows, rows] += d_logits[:, 0]
+    np.add.at(d_scores, (rows[:, None].repeat(k, axis=1), neg), d_logits[:, 1:])
+    d_hu = l2_normalize_backward(u, nu, d_scores @ v)
+    d_hi = l2_normalize_backward(v, nv, d_scores.T @ u)
+    d_tu, gu = mlp_backward("user_mlp.mlp.", cu, d_hu, n_user_hidden, activation, train, output_layer=False)
+    d_ti, gi = mlp_backward("item_mlp.mlp.", ci, d_hi, n_item_hidden, activation, train, output_layer=False)
+    grads = {}
+    grads.update(gu)
+    grads.update(gi)
+    tower_tile_backward(sd, x, user_features, d_tu, grads, dtype)
+    tower_tile_backward(sd, x, item_features, d_ti, grads, dtype)
+    out["grads"] = grads
+    return out

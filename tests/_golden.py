@@ -75,3 +75,40 @@ def build_model(name, rec, features_mod, models_mod, initializer=None):
 def torch_inputs(rec, device="cpu"):
     import torch
     return {k: torch.from_numpy(np.array(v)).to(device) for k, v in rec["x"].items()}, torch.from_numpy(np.array(rec["y"])).to(device)
+
+
+# ---- two-tower golden (dssm.npz) ------------------------------------------------------------------------------------
+DSSM_USER = [("sparse", "user_id", "user_id"), ("seq", "hist_item_id", "item_id", "mean")]
+DSSM_ITEM = [("sparse", "item_id", "item_id")]
+
+
+def dssm_oracle_run(orc, rec, backward=True):
+    m = rec["meta"]
+    return orc.dssm_forward_backward(rec["sd"], rec["x"], DSSM_USER, DSSM_ITEM, m["n_hidden"], m["n_hidden"], m["neg_ratio"], train=True, backward=backward)
+
+
+def build_dssm(rec, F, M):
+    """This package's (or the reference's) DSSM with the golden state_dict loaded."""
+    import torch
+    m = rec["meta"]
+    user = [F.SparseFeature("user_id", m["n_users"], embed_dim=8), F.SequenceFeature("hist_item_id", m["n_items"], embed_dim=8, pooling="mean", shared_with="item_id")]
+    item = [F.SparseFeature("item_id", m["n_items"], embed_dim=8)]
+    model = M.DSSM(user, item, user_params={"dims": [16, 8], "activation": "relu"}, item_params={"dims": [16, 8], "activation": "relu"})
+    model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in rec["sd"].items()})
+    return model
+
+
+def check_dssm_against_golden(rec, out, grads, emb_tol, grad_rtol):
+    """``out``: dict with user_emb / item_emb / prob / logits / loss (numpy); ``grads``: name -> numpy.  The sampled columns are
+    compared through the logits they select: duplicate items in a batch tie exactly, and any of the tied columns is a valid pick."""
+    for k in ("user_emb", "item_emb", "prob"):
+        assert np.abs(out[k] - rec[k]).max() <= emb_tol, (k, np.abs(out[k] - rec[k]).max())
+    assert np.abs(out["logits"] - rec["logits"]).max() <= 2 * emb_tol
+    assert abs(float(out["loss"]) - float(rec["loss"])) <= 4 * emb_tol
+    assert set(grads) == set(rec["grad"]), set(grads) ^ set(rec["grad"])
+    for k, ref in rec["grad"].items():
+        got = np.asarray(grads[k]).reshape(ref.shape)
+        scale = max(np.abs(ref).max(), 1e-3)
+        if k.endswith(".bias") and k[:-4] + "weight" in rec["grad"]:  # a Linear bias in front of BatchNorm has a true gradient of 0
+            scale = max(scale, np.abs(rec["grad"][k[:-4] + "weight"]).max())
+        assert np.abs(got - ref).max() <= grad_rtol * scale, (k, np.abs(got - ref).max(), scale)

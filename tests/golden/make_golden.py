@@ -2,7 +2,7 @@
 
     python tests/golden/make_golden.py
 
-Writes tests/golden/{deepfm_tutorial,deepfm_runcriteo,dcn,dcnv2,din,din_softmax}.npz: the reference model's
+Writes tests/golden/{deepfm_tutorial,deepfm_runcriteo,dcn,dcnv2,din,din_softmax}.npz (and dssm.npz, see dump_dssm): the reference model's
 state_dict, the input batch, the labels, its pre-sigmoid logits / probabilities in train mode (dropout 0, BatchNorm
 batch statistics) and in eval mode, and every parameter gradient of BCELoss(mean) in train mode — including the
 dense (vocab, dim) table gradients the reference materialises.  Tables are initialised N(0, 0.05) instead of the
@@ -95,5 +95,48 @@ def main():
              {"n_hidden": 2, "n_att_hidden": 2, "use_softmax": int(softmax)})
 
 
+def dump_dssm():
+    """dssm.npz: the reference DSSM (mean-pooled history sharing the item table) + MatchTrainer's in-batch branch with HARD
+    negatives (deterministic) and cross entropy: tower embeddings, point-wise probabilities, scores, sampled columns, logits,
+    loss and every parameter gradient, train mode (BatchNorm batch statistics)."""
+    F = L.ref_module("basic.features")
+    I = L.ref_module("basic.initializers")
+    M = L.ref_module("models.matching")
+    U = L.ref_module("utils.match")
+    init = I.RandomNormal(0, 0.3)
+    B, Lh, n_users, n_items, K = 40, 6, 17, 29, 5
+    g = torch.Generator().manual_seed(77)
+    lens = torch.randint(1, Lh + 1, (B,), generator=g)
+    x = {"user_id": torch.randint(0, n_users, (B,), generator=g), "item_id": torch.randint(0, n_items, (B,), generator=g),
+         "hist_item_id": torch.randint(1, n_items, (B, Lh), generator=g) * (torch.arange(Lh).unsqueeze(0) < lens.unsqueeze(1))}
+    torch.manual_seed(7)
+    user = [F.SparseFeature("user_id", n_users, embed_dim=8, initializer=init), F.SequenceFeature("hist_item_id", n_items, embed_dim=8, pooling="mean", shared_with="item_id")]
+    item = [F.SparseFeature("item_id", n_items, embed_dim=8, initializer=init)]
+    model = M.DSSM(user, item, user_params={"dims": [16, 8], "activation": "relu"}, item_params={"dims": [16, 8], "activation": "relu"})
+    model.train()
+    rec = {}
+    for k, v in x.items():
+        rec["x." + k] = v.numpy()
+    for k, v in model.state_dict().items():
+        rec["sd." + k] = v.numpy()
+    ue, ie = model.user_tower(x), model.item_tower(x)
+    scores = ue @ ie.t()
+    neg = U.inbatch_negative_sampling(scores, neg_ratio=K, hard_negative=True)
+    logits = U.gather_inbatch_logits(scores, neg)
+    loss = torch.nn.CrossEntropyLoss()(logits, torch.zeros(B, dtype=torch.long))
+    model.zero_grad()
+    loss.backward()
+    rec.update({"user_emb": ue.detach().numpy(), "item_emb": ie.detach().numpy(), "prob": torch.sigmoid((ue * ie).sum(1)).detach().numpy(), "scores": scores.detach().numpy(),
+                "neg_idx": neg.numpy(), "logits": logits.detach().numpy(), "loss": np.array(loss.item())})
+    for k, prm in model.named_parameters():
+        rec["grad." + k] = prm.grad.numpy()
+    for k, v in {"neg_ratio": K, "n_users": n_users, "n_items": n_items, "n_hidden": 2}.items():
+        rec["meta." + k] = np.array(v)
+    np.savez_compressed(os.path.join(HERE, "dssm.npz"), **rec)
+    gaps = np.sort(scores.detach().numpy() - 10 * np.eye(B), axis=1)
+    print("dssm loss", loss.item(), "min gap between ranked scores", float(np.diff(gaps, axis=1)[:, -K - 1:].min()))
+
+
 if __name__ == "__main__":
     main()
+    dump_dssm()

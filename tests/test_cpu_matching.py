@@ -173,3 +173,45 @@ def test_reference_matching_tests_pass_against_this_package(tmp_path):
     res = subprocess.run(cmd, env=dict(os.environ, PYTHONPATH=PKG), cwd=str(tdir), capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
     assert "passed" in res.stdout
+
+
+def test_package_cpu_route_matches_dssm_golden():
+    """Needs no live reference (runs on the GPU box too): this package's DSSM + in-batch hard negatives vs tests/golden/dssm.npz."""
+    import _golden
+    import torch_rechub.basic.features as F
+    import torch_rechub.models.matching as M
+    from torch_rechub.utils.match import gather_inbatch_logits, inbatch_negative_sampling
+    rec = _golden.load("dssm")
+    model = _golden.build_dssm(rec, F, M).train()
+    x = {k: torch.from_numpy(v) for k, v in rec["x"].items()}
+    ue, ie = model.user_tower(x), model.item_tower(x)
+    scores = ue @ ie.t()
+    neg = inbatch_negative_sampling(scores, neg_ratio=rec["meta"]["neg_ratio"], hard_negative=True)
+    logits = gather_inbatch_logits(scores, neg)
+    loss = torch.nn.CrossEntropyLoss()(logits, torch.zeros(logits.size(0), dtype=torch.long))
+    model.zero_grad()
+    loss.backward()
+    out = {"user_emb": ue.detach().numpy(), "item_emb": ie.detach().numpy(), "prob": torch.sigmoid((ue * ie).sum(1)).detach().numpy(), "logits": logits.detach().numpy(), "loss": float(loss)}
+    _golden.check_dssm_against_golden(rec, out, {k: p.grad.numpy() for k, p in model.named_parameters()}, emb_tol=1e-7, grad_rtol=1e-6)
+    assert np.array_equal(neg.numpy(), rec["neg_idx"])
+
+
+def test_batched_sampler_properties_on_cpu_tensors():
+    """The CUDA route's batched draw, exercised here on CPU tensors: shape, range, no positive, no repeats, seed behaviour,
+    uniform coverage, and agreement of the batched hard-negative pick with the row-wise one."""
+    from torch_rechub.utils.match import _sample_batched, _sample_rowwise
+    n, k = 101, 13
+    scores = torch.randn(n, n, generator=torch.Generator().manual_seed(1))
+    diag = torch.arange(n).unsqueeze(1)
+    a = _sample_batched(scores, k, False, torch.Generator().manual_seed(3))
+    assert a.shape == (n, k) and a.dtype == torch.long
+    assert int(a.min()) >= 0 and int(a.max()) < n and not bool((a == diag).any())
+    assert all(len(set(row)) == k for row in a.tolist())
+    assert torch.equal(a, _sample_batched(scores, k, False, torch.Generator().manual_seed(3)))
+    assert not torch.equal(a, _sample_batched(scores, k, False, torch.Generator().manual_seed(4)))
+    full = _sample_batched(scores, n - 1, False, None)
+    others = torch.arange(n).expand(n, n)[diag != torch.arange(n)].view(n, n - 1)
+    assert torch.equal(full.sort(dim=1).values, others)
+    counts = torch.bincount(_sample_batched(torch.zeros(64, 64), 8, False, torch.Generator().manual_seed(0)).flatten(), minlength=64)
+    assert int(counts.min()) > 0 and int(counts.max()) < 30  # 512 uniform draws over 64 columns: mean 8
+    assert torch.equal(_sample_batched(scores, k, True, None), _sample_rowwise(scores, k, True, None))

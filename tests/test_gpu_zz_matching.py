@@ -1,0 +1,122 @@
+"""GPU parity of the two-tower path: DSSM towers through the fused gather (+ mean-pooled history sharing
+the item table) and the tower kernels, MatchTrainer's in-batch branch with the batched CUDA sampler — against the golden
+vectors recorded from the live reference and against the numpy oracle on fresh inputs.  (Sorted last on purpose: it was
+written after the last GPU session of its round.)"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import _golden
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+import rechub_oracle as orc  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _inbatch(model, x, k):
+    from torch_rechub.utils.match import gather_inbatch_logits, inbatch_negative_sampling
+    ue, ie = model.user_tower(x), model.item_tower(x)
+    scores = ue @ ie.t()
+    neg = inbatch_negative_sampling(scores, neg_ratio=k, hard_negative=True)
+    logits = gather_inbatch_logits(scores, neg)
+    loss = torch.nn.CrossEntropyLoss()(logits, torch.zeros(logits.size(0), dtype=torch.long, device=logits.device))
+    return ue, ie, scores, neg, logits, loss
+
+
+def _as_out(ue, ie, logits, loss):
+    return {"user_emb": ue.detach().cpu().numpy(), "item_emb": ie.detach().cpu().numpy(), "prob": torch.sigmoid((ue * ie).sum(1)).detach().cpu().numpy(),
+            "logits": logits.detach().cpu().numpy(), "loss": float(loss)}
+
+
+def test_dssm_cuda_matches_reference_golden():
+    import torch_rechub.basic.features as F
+    import torch_rechub.models.matching as M
+    rec = _golden.load("dssm")
+    model = _golden.build_dssm(rec, F, M).to(DEV).train()
+    x = {k: torch.from_numpy(v).to(DEV) for k, v in rec["x"].items()}
+    ue, ie, scores, neg, logits, loss = _inbatch(model, x, rec["meta"]["neg_ratio"])
+    model.zero_grad()
+    loss.backward()
+    grads = {k: (p.grad.detach().cpu().numpy() if p.grad is not None else np.zeros(tuple(p.shape), np.float32)) for k, p in model.named_parameters()}
+    _golden.check_dssm_against_golden(rec, _as_out(ue, ie, logits, loss), grads, emb_tol=2e-5, grad_rtol=2e-4)
+    assert not bool((neg == torch.arange(neg.size(0), device=DEV).unsqueeze(1)).any())
+
+
+def test_dssm_cuda_against_numpy_oracle_on_a_larger_batch():
+    import torch_rechub.basic.features as F
+    import torch_rechub.models.matching as M
+    from torch_rechub.basic.initializers import RandomNormal
+    torch.manual_seed(31)
+    B, L, n_users, n_items, K = 512, 10, 3000, 5000, 7
+    init = RandomNormal(0, 0.3)
+    user = [F.SparseFeature("user_id", n_users, embed_dim=16, initializer=init), F.SequenceFeature("hist_item_id", n_items, embed_dim=16, pooling="mean", shared_with="item_id")]
+    item = [F.SparseFeature("item_id", n_items, embed_dim=16, initializer=init)]
+    model = M.DSSM(user, item, user_params={"dims": [64, 32]}, item_params={"dims": [64, 32]}).to(DEV).train()
+    g = torch.Generator().manual_seed(4)
+    lens = torch.randint(1, L + 1, (B,), generator=g)
+    x = {"user_id": torch.randint(0, n_users, (B,), generator=g), "item_id": torch.randperm(n_items, generator=g)[:B],  # distinct items: no exact score ties
+         "hist_item_id": torch.randint(1, n_items, (B, L), generator=g) * (torch.arange(L).unsqueeze(0) < lens.unsqueeze(1))}
+    sd = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+    ref = orc.dssm_forward_backward(sd, {k: v.numpy() for k, v in x.items()}, _golden.DSSM_USER, _golden.DSSM_ITEM, 2, 2, K, train=True)
+    ue, ie, scores, neg, logits, loss = _inbatch(model, {k: v.to(DEV) for k, v in x.items()}, K)
+    model.zero_grad()
+    loss.backward()
+    assert np.abs(ue.detach().cpu().numpy() - ref["user_emb"]).max() < 5e-5 and np.abs(ie.detach().cpu().numpy() - ref["item_emb"]).max() < 5e-5
+    assert np.abs(np.sort(logits.detach().cpu().numpy()[:, 1:], axis=1) - np.sort(ref["logits"][:, 1:], axis=1)).max() < 1e-4
+    assert abs(float(loss) - ref["loss"]) < 1e-4
+    for k, p in model.named_parameters():
+        want = np.asarray(ref["grads"][k]).reshape(tuple(p.shape))
+        scale = max(np.abs(want).max(), 1e-4)
+        if k.endswith(".bias") and k[:-4] + "weight" in ref["grads"]:
+            scale = max(scale, np.abs(ref["grads"][k[:-4] + "weight"]).max())
+        got = p.grad.detach().cpu().numpy() if p.grad is not None else np.zeros_like(want)
+        assert np.abs(got - want).max() <= 1e-3 * scale, (k, np.abs(got - want).max(), scale)
+
+
+def test_cuda_inbatch_sampler_properties():
+    from torch_rechub.utils.match import inbatch_negative_sampling
+    n, k = 257, 19
+    scores = torch.randn(n, n, device=DEV)
+    diag = torch.arange(n, device=DEV).unsqueeze(1)
+    gen = torch.Generator(device=DEV)
+    gen.manual_seed(3)
+    a = inbatch_negative_sampling(scores, neg_ratio=k, generator=gen)
+    assert a.shape == (n, k) and a.dtype == torch.long and a.device.type == "cuda"
+    assert int(a.min()) >= 0 and int(a.max()) < n and not bool((a == diag).any())
+    assert all(len(set(row)) == k for row in a.cpu().tolist())  # without replacement
+    gen.manual_seed(3)
+    assert torch.equal(a, inbatch_negative_sampling(scores, neg_ratio=k, generator=gen))
+    gen.manual_seed(4)
+    assert not torch.equal(a, inbatch_negative_sampling(scores, neg_ratio=k, generator=gen))
+    full = inbatch_negative_sampling(scores)  # default: every other column
+    assert full.shape == (n, n - 1) and torch.equal(full.sort(dim=1).values, torch.arange(n, device=DEV).expand(n, n)[diag != torch.arange(n, device=DEV)].view(n, n - 1))
+    counts = torch.bincount(inbatch_negative_sampling(torch.zeros(64, 64, device=DEV), neg_ratio=16).flatten(), minlength=64)
+    assert int(counts.min()) > 0  # 63 rows each take 16 of a column's 63 chances: P(some column never drawn) ~ 64 * (47/63)^63 ~ 6e-7
+    hard = inbatch_negative_sampling(scores, neg_ratio=k, hard_negative=True)
+    assert torch.equal(hard.cpu(), inbatch_negative_sampling(scores.cpu(), neg_ratio=k, hard_negative=True))
+
+
+def test_match_trainer_inbatch_epoch_on_cuda():
+    import torch_rechub.basic.features as F
+    import torch_rechub.models.matching as M
+    from torch_rechub.trainers import MatchTrainer
+    torch.manual_seed(5)
+    user = [F.SparseFeature("user_id", 50, embed_dim=8), F.SequenceFeature("hist_item_id", 80, embed_dim=8, pooling="mean", shared_with="item_id")]
+    item = [F.SparseFeature("item_id", 80, embed_dim=8)]
+    model = M.DSSM(user, item, user_params={"dims": [16]}, item_params={"dims": [16]})
+    g = torch.Generator().manual_seed(6)
+    data = [({"user_id": torch.randint(0, 50, (32,), generator=g), "item_id": torch.randint(0, 80, (32,), generator=g), "hist_item_id": torch.randint(0, 80, (32, 5), generator=g)}, torch.zeros(32))
+            for _ in range(6)]
+    before = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    t = MatchTrainer(model, mode=0, in_batch_neg=True, in_batch_neg_ratio=5, sampler_seed=1, n_epoch=1, device=DEV)
+    loss = t.train_one_epoch(data, log_interval=2)
+    assert np.isfinite(loss) and 0.0 < loss < 10.0
+    after = model.state_dict()
+    assert any(not torch.equal(before[k].to(DEV), after[k]) for k in before if k.endswith("weight"))
+    emb = model.user_tower({k: v.to(DEV) for k, v in data[0][0].items()})
+    assert torch.allclose(emb.norm(dim=1), torch.ones(32, device=DEV), atol=1e-5)

@@ -33,6 +33,16 @@ def test_oracle_matches_reference_golden_train(name):
         assert np.abs(got - ref).max() <= 2e-5 * scale, (k, np.abs(got - ref).max(), scale)
 
 
+def test_dssm_oracle_matches_reference_golden():
+    """Two towers + in-batch hard negatives + cross entropy: embeddings, logits, loss, every gradient."""
+    rec = _golden.load("dssm")
+    out = _golden.dssm_oracle_run(orc, rec)
+    _golden.check_dssm_against_golden(rec, out, out["grads"], emb_tol=2e-6, grad_rtol=2e-5)
+    rows = np.arange(out["scores"].shape[0])[:, None]
+    assert np.abs(out["scores"][rows, out["neg_idx"]] - rec["scores"][rows, rec["neg_idx"]]).max() < 2e-6
+    assert not np.any(out["neg_idx"] == rows)
+
+
 @pytest.mark.parametrize("name", _golden.NAMES)
 def test_oracle_matches_reference_golden_eval(name):
     rec = _golden.load(name)

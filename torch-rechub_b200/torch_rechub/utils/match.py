@@ -120,20 +120,36 @@ def inbatch_negative_sampling(scores, neg_ratio=None, hard_negative=False, gener
     if n <= 1:
         raise ValueError("In-batch negative sampling requires batch_size > 1")
     k = neg_ratio if (neg_ratio is not None and 0 < neg_ratio <= n - 1) else n - 1
-    dev = scores.device
+    if scores.device.type == "cuda":
+        return _sample_batched(scores, k, hard_negative, generator)
+    return _sample_rowwise(scores, k, hard_negative, generator)
+
+
+def _sample_batched(scores, k, hard_negative, generator):
+    """All rows at once (the CUDA route): top-k of the diagonal-masked scores, or the k smallest of one (B, B) matrix of uniform
+    keys whose diagonal is pushed to the end — a uniform draw without replacement from the other B - 1 columns."""
+    n = scores.size(0)
     if hard_negative:
         masked = scores.detach().clone()
         masked.fill_diagonal_(float("-inf"))
-        if dev.type == "cuda":
-            return torch.topk(masked, k=k, dim=1).indices
-        return torch.stack([torch.topk(masked[i], k=k).indices for i in range(n)])  # row by row: the reference's tie order
-    if dev.type == "cuda":
-        keys = torch.rand((n, n), device=dev, generator=generator)
-        keys.fill_diagonal_(2.0)  # sorts last: never among the first K <= B - 1
-        return torch.argsort(keys, dim=1)[:, :k]
-    out = torch.empty((n, k), dtype=torch.long)
+        return torch.topk(masked, k=k, dim=1).indices
+    keys = torch.rand((n, n), device=scores.device, generator=generator)
+    keys.fill_diagonal_(2.0)  # sorts last: never among the first k <= B - 1
+    return torch.argsort(keys, dim=1)[:, :k]
+
+
+def _sample_rowwise(scores, k, hard_negative, generator):
+    """Row by row (the CPU route): replays the reference's RNG stream — one ``randperm(B - 1)`` per row — and its top-k tie order."""
+    n = scores.size(0)
+    out = torch.empty((n, k), dtype=torch.long, device=scores.device)
+    if hard_negative:
+        masked = scores.detach().clone()
+        masked.fill_diagonal_(float("-inf"))
+        for i in range(n):
+            out[i] = torch.topk(masked[i], k=k).indices
+        return out
     for i in range(n):
-        pick = torch.randperm(n - 1, generator=generator)[:k]  # positions in the row with its own column removed
+        pick = torch.randperm(n - 1, device=scores.device, generator=generator)[:k]  # positions in the row with its own column removed
         out[i] = pick + (pick >= i).long()
     return out
 
