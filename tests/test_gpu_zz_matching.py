@@ -55,14 +55,16 @@ def test_dssm_cuda_against_numpy_oracle_on_a_larger_batch():
     B, L, n_users, n_items, K = 512, 10, 3000, 5000, 7
     init = RandomNormal(0, 0.3)
     user = [F.SparseFeature("user_id", n_users, embed_dim=16, initializer=init), F.SequenceFeature("hist_item_id", n_items, embed_dim=16, pooling="mean", shared_with="item_id")]
-    item = [F.SparseFeature("item_id", n_items, embed_dim=16, initializer=init)]
-    model = M.DSSM(user, item, user_params={"dims": [64, 32]}, item_params={"dims": [64, 32]}).to(DEV).train()
+    item = [F.SparseFeature("item_id", n_items, embed_dim=16, initializer=init), F.SparseFeature("cate_id", 40, embed_dim=16, initializer=init)]
+    model = M.DSSM(user, item, user_params={"dims": [64, 32]}, item_params={"dims": [64, 32]}).to(DEV).train()  # both towers: 32 -> 64 -> 32 (tensor-core GEMMs)
     g = torch.Generator().manual_seed(4)
     lens = torch.randint(1, L + 1, (B,), generator=g)
     x = {"user_id": torch.randint(0, n_users, (B,), generator=g), "item_id": torch.randperm(n_items, generator=g)[:B],  # distinct items: no exact score ties
+         "cate_id": torch.randint(0, 40, (B,), generator=g),
          "hist_item_id": torch.randint(1, n_items, (B, L), generator=g) * (torch.arange(L).unsqueeze(0) < lens.unsqueeze(1))}
     sd = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
-    ref = orc.dssm_forward_backward(sd, {k: v.numpy() for k, v in x.items()}, _golden.DSSM_USER, _golden.DSSM_ITEM, 2, 2, K, train=True)
+    item_spec = _golden.DSSM_ITEM + [("sparse", "cate_id", "cate_id")]
+    ref = orc.dssm_forward_backward(sd, {k: v.numpy() for k, v in x.items()}, _golden.DSSM_USER, item_spec, 2, 2, K, train=True)
     ue, ie, scores, neg, logits, loss = _inbatch(model, {k: v.to(DEV) for k, v in x.items()}, K)
     model.zero_grad()
     loss.backward()

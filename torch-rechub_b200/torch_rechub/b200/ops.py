@@ -431,6 +431,8 @@ def _tc_ok(rows, *mats):
     from . import config
     if not config.tensor_core_gemm or rows < 128:
         return False
+    if any(m.dim() == 2 and min(m.shape) < 32 for m in mats):  # thinner than one 32-float TMA box: not worth a 128 x 128 tile
+        return False
     return all(m.dtype == torch.float32 and m.dim() == 2 and m.stride(1) == 1 and m.stride(0) % 4 == 0 and m.data_ptr() % 16 == 0 for m in mats)
 
 
@@ -502,7 +504,7 @@ class _TowerLayer(torch.autograd.Function):
         st = stream_ptr()
         h = torch.empty((rows, cols), dtype=torch.float32, device=dev)
         Wp = None
-        use_tc = cols % 4 == 0 and _tc_ok(rows, x2)
+        use_tc = cols % 4 == 0 and cols >= 32 and _tc_ok(rows, x2)
         if use_tc:
             Wp = _padded_weight(W)  # (cols, K) view with a 16-byte row stride
             gemm3x(x2, False, Wp, False, rows, cols, K, bias=b, out=h)
