@@ -455,11 +455,12 @@ def hard_negative_indices(scores, k):
     return np.argsort(-masked, axis=1, kind="stable")[:, :k]
 
 
-def dssm_forward_backward(sd, x, user_features, item_features, n_user_hidden, n_item_hidden, neg_ratio, activation="relu", train=True, backward=True, dtype=np.float64):
+def dssm_forward_backward(sd, x, user_features, item_features, n_user_hidden, n_item_hidden, neg_ratio, activation="relu", train=True, backward=True, dtype=np.float64, neg_idx=None):
     """DSSM towers (models/matching/dssm.py:40-72) + MatchTrainer's in-batch branch with HARD negatives and cross entropy
     (trainers/match_trainer.py:118-140, utils/match.py:104-161).  Returns the tower embeddings, the point-wise probability
     ``sigmoid(<u, v>)``, the (B, B) scores, the sampled columns, the ``[positive | negatives]`` logits, the loss and — with
-    ``backward`` — every parameter gradient of that loss."""
+    ``backward`` — every parameter gradient of that loss.  ``neg_idx`` overrides the sampler (any (B, K) column choice: random
+    negatives, or another implementation's hard negatives when two scores tie within rounding)."""
     tu = tower_tile(sd, x, user_features, dtype)
     ti = tower_tile(sd, x, item_features, dtype)
     hu, cu = mlp_forward(sd, "user_mlp.mlp.", tu, n_user_hidden, activation, train, output_layer=False, dtype=dtype)
@@ -469,7 +470,8 @@ def dssm_forward_backward(sd, x, user_features, item_features, n_user_hidden, n_
     scores = u @ v.T
     B = scores.shape[0]
     k = neg_ratio if (neg_ratio is not None and 0 < neg_ratio <= B - 1) else B - 1
-    neg = hard_negative_indices(scores, k)
+    neg = hard_negative_indices(scores, k) if neg_idx is None else np.asarray(neg_idx).astype(np.int64)
+    k = neg.shape[1]
     rows = np.arange(B)
     logits = np.concatenate([scores[rows, rows][:, None], scores[rows[:, None], neg]], axis=1)
     mx = logits.max(axis=1, keepdims=True)
