@@ -334,6 +334,21 @@ int rh_gemm_tf32x3(const float* A, int64_t lda, int a_mn_major,
                    float* C, int64_t ldc, int M, int N, int K,
                    const float* bias, int split_k, void* stream);
 
+/* The same GEMM (split_k = 1) with BatchNorm1d's training-mode column statistics of C = A B^T + bias computed in the epilogue —
+ * rh_gemm_tf32x3 followed by rh_colstats in one launch (MLP.forward, basic/layers.py:282-283: Linear then BatchNorm1d).
+ * Every CTA reduces its 128 rows to a per-column (mean, M2) pair (two-pass inside each warp, Chan's merge above it); the
+ * last CTA of each 128-column block merges the row tiles in a fixed order and writes
+ *   stats (2N + 1): mean | biased variance | step-counter bits          — exactly what rh_colstats produces,
+ * updates running_mean / running_var (unbiased) with `momentum` and increments num_batches_tracked (all may be NULL).
+ *   scratch: rh_gemm_stats_scratch_floats(M, N) floats, zeroed ONCE by the caller (the kernel leaves its tickets zero). */
+int64_t rh_gemm_stats_scratch_floats(int M, int N);
+int rh_gemm_tf32x3_stats(const float* A, int64_t lda, int a_mn_major,
+                         const float* B, int64_t ldb, int b_mn_major,
+                         float* C, int64_t ldc, int M, int N, int K, const float* bias,
+                         float* stats, float* scratch,
+                         float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                         float momentum, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * DIN target attention (models/ranking/din.py:77-93, ActivationUnit.forward).
  * ------------------------------------------------------------------------------------------- */

@@ -64,3 +64,75 @@ def test_is_more_accurate_than_tf32_and_matches_fp32_level():
     e3 = (C.double() - ref).abs().max().item()
     e32 = (fp32.double() - ref).abs().max().item()
     assert e3 < 4 * e32 + 1e-5, (e3, e32)  # same order as cuBLAS fp32; TF32 alone would be ~1e-2 here
+
+
+def _colstats_enabled():
+    from torch_rechub.b200 import config
+    return bool(config.gemm_colstats)
+
+
+@pytest.mark.skipif(not _colstats_enabled(), reason="rh_gemm_tf32x3_stats awaits its first GPU session: run with RECHUB_B200_GEMM_COLSTATS=1")
+@pytest.mark.parametrize("M,N,K,bias", [(4096, 256, 429, True), (4096, 128, 256, True), (300, 72, 52, True), (129, 36, 32, False), (1000, 260, 64, True), (128, 128, 32, True)])
+def test_gemm_with_column_statistics_epilogue(M, N, K, bias):
+    """GEMM + BatchNorm training statistics in one launch vs fp64: C, mean, biased variance, running statistics, step counter;
+    two launches in a row (the tickets must come back to zero) and a column with a huge common offset (the per-tile two-pass
+    + Chan merge must not cancel)."""
+    from torch_rechub.b200 import _lib
+    from torch_rechub.b200.ops import _pad4
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn(M, K, generator=g) * 1.5 + 0.1).to(DEV)
+    Kp = _pad4(K)
+    Wbuf = torch.zeros(N, Kp, device=DEV)
+    Wbuf[:, :K] = (torch.randn(N, K, generator=g) * 0.7 - 0.2).to(DEV)
+    Abuf = torch.zeros(M, Kp, device=DEV)
+    Abuf[:, :K] = A
+    bvec = None
+    if bias:
+        bvec = torch.randn(N, generator=g).to(DEV)
+        bvec[0] = 3000.0  # mean >> std in one column
+    scratch = torch.zeros(int(L.rh_gemm_stats_scratch_floats(M, N)), device=DEV)
+    rm0, rv0 = torch.rand(N, device=DEV), torch.rand(N, device=DEV) + 0.5
+    ref = A.double() @ Wbuf[:, :K].double().t() + (bvec.double() if bias else 0.0)
+    mean_ref, var_ref = ref.mean(0), ref.var(0, unbiased=False)
+    for launch in range(2):
+        C = torch.empty(M, N, device=DEV)
+        stats = torch.empty(2 * N + 1, device=DEV)
+        rm, rv, nbt = rm0.clone(), rv0.clone(), torch.tensor(41 + launch, device=DEV)
+        _lib.check(L.rh_gemm_tf32x3_stats(Abuf.data_ptr(), Kp, 0, Wbuf.data_ptr(), Kp, 0, C.data_ptr(), N, M, N, K, _lib.ptr(bvec), stats.data_ptr(), scratch.data_ptr(), rm.data_ptr(), rv.data_ptr(),
+                                          nbt.data_ptr(), 0.1, _lib.stream_ptr()), "rh_gemm_tf32x3_stats")
+        torch.cuda.synchronize()
+        scale = (A.double().abs() @ Wbuf[:, :K].double().abs().t()).max().item() + (3000.0 if bias else 0.0)
+        assert (C.double() - ref).abs().max().item() / scale < 2e-6
+        mean, var = stats[:N].double(), stats[N:2 * N].double()
+        assert ((mean - mean_ref).abs() <= 2e-6 * mean_ref.abs() + 1e-5).all(), (mean - mean_ref).abs().max()
+        assert ((var - var_ref).abs() <= 2e-5 * var_ref + 1e-6).all(), ((var - var_ref).abs() / var_ref).max()
+        assert int(nbt) == 42 + launch and int(stats[2 * N:].view(torch.int32)) == 42 + launch
+        unbiased = var_ref * (M / (M - 1.0))
+        assert torch.allclose(rm.double(), 0.9 * rm0.double() + 0.1 * mean_ref, rtol=1e-5, atol=1e-5)
+        assert torch.allclose(rv.double(), 0.9 * rv0.double() + 0.1 * unbiased, rtol=1e-4, atol=1e-6)
+        assert int(scratch[-((N + 127) // 128):].view(torch.int32).abs().max()) == 0  # tickets back to zero
+
+
+@pytest.mark.skipif(not _colstats_enabled(), reason="rh_gemm_tf32x3_stats awaits its first GPU session: run with RECHUB_B200_GEMM_COLSTATS=1")
+def test_tower_with_fused_statistics_matches_cpu_route():
+    import copy
+    from torch_rechub.basic.layers import MLP
+    torch.manual_seed(9)
+    cpu = MLP(64, dims=[128, 64], dropout=0.0, activation="relu")
+    gpu = copy.deepcopy(cpu).to(DEV)
+    x = torch.randn(513, 64) * 2 + 0.3
+    yc, yg = cpu(x), gpu(x.to(DEV))
+    assert (yg.cpu() - yc).abs().max().item() < 2e-5 * yc.abs().max().item() + 2e-6
+    w = torch.randn(513, 1)
+    (yc * w).sum().backward()
+    (yg * w.to(DEV)).sum().backward()
+    for (n, p), q in zip(gpu.named_parameters(), cpu.parameters()):
+        scale = max(q.grad.abs().max().item(), 1e-3)
+        if n.endswith("0.bias") or n.endswith("4.bias"):
+            continue
+        assert (p.grad.cpu() - q.grad).abs().max().item() <= 2e-4 * scale, n
+    for mc, mg in zip(cpu.mlp, gpu.mlp):
+        if isinstance(mc, torch.nn.BatchNorm1d):
+            assert torch.allclose(mg.running_mean.cpu(), mc.running_mean, rtol=1e-5, atol=1e-6) and torch.allclose(mg.running_var.cpu(), mc.running_var, rtol=1e-5, atol=1e-6)
+            assert int(mg.num_batches_tracked) == int(mc.num_batches_tracked)

@@ -18,6 +18,7 @@
 // Replaces the Linear GEMMs of MLP.forward/backward (reference basic/layers.py:281-292; cuBLAS sgemm via ATen there).
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "rh_common.cuh"
 
@@ -115,8 +116,47 @@ struct GemmP {
   int a_mn, b_mn;   // operand majors: 0 = K-major, 1 = MN-major
   int kblocks_per_split;
   int reduce;       // 1: red.global.add into C (split-K), 0: plain stores
+  // STATS instantiation only (BatchNorm column statistics of C in the epilogue):
+  float* stats;            // (2N + 1): mean | biased variance | step counter bits
+  float* partial;          // [n_tile][m_tile][2][128]: per-tile column mean and M2
+  unsigned* tickets;       // [n_tiles], zero on entry, left zero
+  float* running_mean;
+  float* running_var;
+  long long* num_batches_tracked;
+  float momentum;
 };
 
+// Transpose-reduce across a warp: every lane holds 32 values v[j]; afterwards lane j holds sum over lanes of v[j] in v[0].
+// 31 shuffles (16 + 8 + 4 + 2 + 1) instead of 32 x 5 for column-wise warp sums.
+template <int S>
+__device__ __forceinline__ void butterfly_step(float (&v)[32], int lane) {
+  const bool up = (lane & S) != 0;
+#pragma unroll
+  for (int i = 0; i < S; ++i) {
+    const float keep = up ? v[i + S] : v[i];
+    const float send = up ? v[i] : v[i + S];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, S);
+  }
+}
+__device__ __forceinline__ void warp_transpose_sum(float (&v)[32], int lane) {
+  butterfly_step<16>(v, lane);
+  butterfly_step<8>(v, lane);
+  butterfly_step<4>(v, lane);
+  butterfly_step<2>(v, lane);
+  butterfly_step<1>(v, lane);
+}
+
+// Chan's pairwise update of (count, mean, M2) with another group's (nb, mean_b, M2_b).
+__device__ __forceinline__ void welford_merge(float& n, float& mean, float& m2, float nb, float mean_b, float m2_b) {
+  if (nb <= 0.f) return;
+  const float tot = n + nb;
+  const float delta = mean_b - mean;
+  mean += delta * (nb / tot);
+  m2 += m2_b + delta * delta * (n * nb / tot);
+  n = tot;
+}
+
+template <bool STATS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmP p) {
   extern __shared__ uint8_t smem_raw[];
@@ -250,6 +290,35 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(x[j]));
+        if constexpr (STATS) {
+          // column statistics of this warp's 32 rows (bias included: BatchNorm sees h = xW^T + b), two-pass inside the warp:
+          // column means by a transpose-reduce, then the squared deviations from the warp's own mean
+          const int nbs = n0 + c * 32;
+          const bool row_ok = m < p.M;
+          int cnt = p.M - (m0 + q * 32);
+          cnt = cnt < 0 ? 0 : (cnt > 32 ? 32 : cnt);
+          float t[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float v = __uint_as_float(r[j]);
+            if (add_bias && nbs + j < p.N) v += __ldg(p.bias + nbs + j);
+            t[j] = row_ok ? v : 0.f;
+          }
+          float dsq[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dsq[j] = t[j];
+          warp_transpose_sum(dsq, lane);
+          const float wmean = cnt > 0 ? dsq[0] / (float)cnt : 0.f;  // lane j: mean of column nbs + j over the warp's rows
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float d = t[j] - __shfl_sync(0xffffffffu, wmean, j);
+            dsq[j] = row_ok ? d * d : 0.f;
+          }
+          warp_transpose_sum(dsq, lane);
+          float* sm_stats = reinterpret_cast<float*>(smem);  // [4 warps][2][128]; the stage ring is idle by now
+          sm_stats[(q * 2 + 0) * 128 + c * 32 + lane] = wmean;
+          sm_stats[(q * 2 + 1) * 128 + c * 32 + lane] = dsq[0];
+        }
         if (m < p.M) {
           const int nb = n0 + c * 32;
           float* crow = p.C + (int64_t)m * p.ldc + nb;
@@ -274,6 +343,67 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                   else crow[j + e] = vv[e];
                 }
               }
+            }
+          }
+        }
+      }
+      if constexpr (STATS) {
+        // ---- the four epilogue warps merge their row groups, publish the tile's (mean, M2) per column, and the last m-tile of
+        // ---- this column block merges all tiles in a fixed order (deterministic) and finalises BatchNorm's statistics
+        float* sm_stats = reinterpret_cast<float*>(smem);
+        int* sm_flag = reinterpret_cast<int*>(smem + 4096);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int tcol = threadIdx.x - 128;  // 0..127: one column of the tile per epilogue thread
+        const int m_tiles = gridDim.x;
+        {
+          float n = 0.f, mean = 0.f, m2 = 0.f;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            int cnt = p.M - (m0 + w * 32);
+            cnt = cnt < 0 ? 0 : (cnt > 32 ? 32 : cnt);
+            welford_merge(n, mean, m2, (float)cnt, sm_stats[(w * 2 + 0) * 128 + tcol], sm_stats[(w * 2 + 1) * 128 + tcol]);
+          }
+          float* out = p.partial + ((size_t)blockIdx.y * m_tiles + blockIdx.x) * 256;
+          __stcg(out + tcol, mean);
+          __stcg(out + 128 + tcol, m2);
+        }
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tcol == 0) {
+          const unsigned ticket = atomicAdd(p.tickets + blockIdx.y, 1u);
+          *sm_flag = (ticket == (unsigned)(m_tiles - 1)) ? 1 : 0;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (*sm_flag) {
+          __threadfence();
+          const int col = n0 + tcol;
+          if (col < p.N) {
+            float n = 0.f, mean = 0.f, m2 = 0.f;
+            for (int mt = 0; mt < m_tiles; ++mt) {
+              int cnt = p.M - mt * kBM;
+              cnt = cnt > kBM ? kBM : cnt;
+              const float* in = p.partial + ((size_t)blockIdx.y * m_tiles + mt) * 256;
+              welford_merge(n, mean, m2, (float)cnt, __ldcg(in + tcol), __ldcg(in + 128 + tcol));
+            }
+            float var = m2 / n;
+            if (var < 0.f) var = 0.f;
+            p.stats[col] = mean;
+            p.stats[p.N + col] = var;
+            if (p.running_mean != nullptr) p.running_mean[col] = (1.f - p.momentum) * p.running_mean[col] + p.momentum * mean;
+            if (p.running_var != nullptr) {
+              const float unbiased = p.M > 1 ? var * (n / (n - 1.f)) : var;
+              p.running_var[col] = (1.f - p.momentum) * p.running_var[col] + p.momentum * unbiased;
+            }
+          }
+          if (tcol == 0) {
+            p.tickets[blockIdx.y] = 0u;  // ready for the next launch (graph replays included)
+            if (blockIdx.y == 0) {      // once per launch: the step counter = dropout stream id of this forward (as rh_colstats)
+              long long count = 0;
+              if (p.num_batches_tracked != nullptr) {
+                count = *p.num_batches_tracked + 1;
+                *p.num_batches_tracked = count;
+              }
+              p.stats[2 * p.N] = __int_as_float((int)(count & 0x7fffffff));
             }
           }
         }
@@ -334,8 +464,17 @@ static int make_map(CUtensorMap* map, const float* base, int64_t ld, int rows, i
 
 using namespace rh;
 
-extern "C" int rh_gemm_tf32x3(const float* A, int64_t lda, int a_mn_major, const float* B, int64_t ldb, int b_mn_major, float* C, int64_t ldc,
-                              int M, int N, int K, const float* bias, int split_k, void* stream) {
+struct StatsArgs {
+  float* stats;
+  float* scratch;
+  float* running_mean;
+  float* running_var;
+  int64_t* num_batches_tracked;
+  float momentum;
+};
+
+static int gemm_impl(const float* A, int64_t lda, int a_mn_major, const float* B, int64_t ldb, int b_mn_major, float* C, int64_t ldc, int M, int N,
+                     int K, const float* bias, int split_k, void* stream, const StatsArgs* st) {
   RH_REQUIRE(A && B && C, RH_ERR_INVALID_ARG, "rh_gemm_tf32x3: NULL pointer");
   RH_REQUIRE(M > 0 && N > 0 && K > 0 && ldc >= N, RH_ERR_INVALID_ARG, "rh_gemm_tf32x3: bad sizes");
   RH_REQUIRE(lda % 4 == 0 && ldb % 4 == 0, RH_ERR_UNSUPPORTED, "rh_gemm_tf32x3: TMA needs 16-byte row strides (lda=%lld ldb=%lld)", (long long)lda,
@@ -355,6 +494,7 @@ extern "C" int rh_gemm_tf32x3(const float* A, int64_t lda, int a_mn_major, const
   if (rc != RH_OK) return rc;
 
   GemmP p;
+  memset(&p, 0, sizeof(p));
   p.C = C;
   p.ldc = ldc;
   p.bias = bias;
@@ -365,15 +505,47 @@ extern "C" int rh_gemm_tf32x3(const float* A, int64_t lda, int a_mn_major, const
   p.b_mn = b_mn_major != 0;
   p.kblocks_per_split = per;
   p.reduce = split_k > 1 ? 1 : 0;
-
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem);
-    RH_REQUIRE(e == cudaSuccess, RH_ERR_CUDA, "rh_gemm_tf32x3: cannot reserve %zu bytes of shared memory: %s", kGemmSmem, cudaGetErrorString(e));
-    configured = true;
-  }
   dim3 grid((M + kBM - 1) / kBM, (N + kBN - 1) / kBN, split_k);
-  gemm_tf32x3_kernel<<<grid, kGemmThreads, kGemmSmem, (cudaStream_t)stream>>>(map_a, map_b, p);
+
+  static bool configured[2] = {false, false};
+  const int which = st != nullptr ? 1 : 0;
+  if (!configured[which]) {
+    cudaError_t e = which ? cudaFuncSetAttribute(gemm_tf32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem)
+                          : cudaFuncSetAttribute(gemm_tf32x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem);
+    RH_REQUIRE(e == cudaSuccess, RH_ERR_CUDA, "rh_gemm_tf32x3: cannot reserve %zu bytes of shared memory: %s", kGemmSmem, cudaGetErrorString(e));
+    configured[which] = true;
+  }
+  if (st != nullptr) {
+    RH_REQUIRE(split_k == 1, RH_ERR_INVALID_ARG, "rh_gemm_tf32x3_stats: column statistics need the whole K range in one CTA (split_k = 1)");
+    RH_REQUIRE(st->stats != nullptr && st->scratch != nullptr, RH_ERR_INVALID_ARG, "rh_gemm_tf32x3_stats: stats / scratch is NULL");
+    p.stats = st->stats;
+    p.partial = st->scratch;
+    p.tickets = reinterpret_cast<unsigned*>(st->scratch + (size_t)grid.x * grid.y * 256);
+    p.running_mean = st->running_mean;
+    p.running_var = st->running_var;
+    p.num_batches_tracked = reinterpret_cast<long long*>(st->num_batches_tracked);
+    p.momentum = st->momentum;
+    gemm_tf32x3_kernel<true><<<grid, kGemmThreads, kGemmSmem, (cudaStream_t)stream>>>(map_a, map_b, p);
+  } else {
+    gemm_tf32x3_kernel<false><<<grid, kGemmThreads, kGemmSmem, (cudaStream_t)stream>>>(map_a, map_b, p);
+  }
   RH_LAUNCH_CHECK();
   return RH_OK;
+}
+
+extern "C" int rh_gemm_tf32x3(const float* A, int64_t lda, int a_mn_major, const float* B, int64_t ldb, int b_mn_major, float* C, int64_t ldc,
+                              int M, int N, int K, const float* bias, int split_k, void* stream) {
+  return gemm_impl(A, lda, a_mn_major, B, ldb, b_mn_major, C, ldc, M, N, K, bias, split_k, stream, nullptr);
+}
+
+extern "C" int64_t rh_gemm_stats_scratch_floats(int M, int N) {
+  const int64_t mt = (M + kBM - 1) / kBM, nt = (N + kBN - 1) / kBN;
+  return mt * nt * 256 + nt;
+}
+
+extern "C" int rh_gemm_tf32x3_stats(const float* A, int64_t lda, int a_mn_major, const float* B, int64_t ldb, int b_mn_major, float* C, int64_t ldc,
+                                    int M, int N, int K, const float* bias, float* stats, float* scratch, float* running_mean,
+                                    float* running_var, int64_t* num_batches_tracked, float momentum, void* stream) {
+  StatsArgs st = {stats, scratch, running_mean, running_var, num_batches_tracked, momentum};
+  return gemm_impl(A, lda, a_mn_major, B, ldb, b_mn_major, C, ldc, M, N, K, bias, 1, stream, &st);
 }

@@ -61,12 +61,14 @@ PROTOTYPES = {
     "rh_head_bwd": [c_p, c_i64, c_i64, c_i, c_p, c_p, c_p, c_i, c_p, c_i64, c_p, c_p, c_p, c_p],
     "rh_dense_update": [c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_f, c_f, c_f, c_f, c_p],
     "rh_gemm_tf32x3": [c_p, c_i64, c_i, c_p, c_i64, c_i, c_p, c_i64, c_i, c_i, c_i, c_p, c_i, c_p],
+    "rh_gemm_stats_scratch_floats": [c_i, c_i],
+    "rh_gemm_tf32x3_stats": [c_p, c_i64, c_i, c_p, c_i64, c_i, c_p, c_i64, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_f, c_p],
     "rh_din_attn_input_fwd": [c_p, c_i, c_p, c_i, c_i, c_p, c_p, c_i, c_i64, c_i, c_i, c_p, c_p, c_p, c_p, c_p],
     "rh_din_weighted_sum_fwd": [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p],
     "rh_din_weighted_sum_bwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p],
     "rh_din_attn_input_bwd": [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_p, c_i, c_i64, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
 }
-_RESTYPES = {"rh_last_error": ctypes.c_char_p, "rh_launch_count": ctypes.c_ulonglong}
+_RESTYPES = {"rh_last_error": ctypes.c_char_p, "rh_launch_count": ctypes.c_ulonglong, "rh_gemm_stats_scratch_floats": ctypes.c_int64}
 
 _lock = threading.Lock()
 _lib = None

@@ -56,5 +56,9 @@ concurrent_optimizers = _flag("RECHUB_B200_CONCURRENT_OPT", False)  # measured: 
 # Output head (Linear(K,1) + side terms + sigmoid) as one launch each way (rh_head_fwd/bwd) instead of ~10 library launches.
 fused_head = _flag("RECHUB_B200_FUSED_HEAD", True)
 
+# Tower forward: BatchNorm's training-mode column statistics computed in the GEMM epilogue (rh_gemm_tf32x3_stats) instead of a
+# separate rh_colstats pass over the activation.  Off until its GPU validation (tests/test_gpu_gemm.py, gated on this flag).
+gemm_colstats = _flag("RECHUB_B200_GEMM_COLSTATS", False)
+
 # Set by the graph runner while inputs live in static buffers that the next batch overwrites.
 static_inputs = False

@@ -461,6 +461,20 @@ def _split_k_for(m_tiles, n_tiles, k_blocks, budget=128):
     return max(1, min(k_blocks, budget // tiles))
 
 
+_gemm_scratch = {}
+
+
+def _gemm_stats_scratch(dev, rows, cols):
+    """Per (device, shape) scratch of rh_gemm_tf32x3_stats: per-tile partial statistics + tickets; zeroed once, the kernel keeps
+    its tickets zero.  Launches that share it are ordered on one stream (the tower's forward)."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), rows, cols)
+    buf = _gemm_scratch.get(key)
+    if buf is None:
+        n = int(_lib.lib().rh_gemm_stats_scratch_floats(rows, cols))
+        buf = _gemm_scratch[key] = torch.zeros(n, dtype=torch.float32, device=dev)
+    return buf
+
+
 _aux_streams = {}
 
 
@@ -505,16 +519,26 @@ class _TowerLayer(torch.autograd.Function):
         h = torch.empty((rows, cols), dtype=torch.float32, device=dev)
         Wp = None
         use_tc = cols % 4 == 0 and cols >= 32 and _tc_ok(rows, x2)
+        training = cfg["training"]
+        stats = None
         if use_tc:
             Wp = _padded_weight(W)  # (cols, K) view with a 16-byte row stride
-            gemm3x(x2, False, Wp, False, rows, cols, K, bias=b, out=h)
+            from . import config
+            if training and config.gemm_colstats:  # GEMM + BatchNorm column statistics in ONE launch
+                stats = torch.empty(2 * cols + 1, dtype=torch.float32, device=dev)
+                check(L.rh_gemm_tf32x3_stats(x2.data_ptr(), x2.stride(0), 0, Wp.data_ptr(), Wp.stride(0), 0, h.data_ptr(), h.stride(0), rows, cols, K, ptr(b), stats.data_ptr(),
+                                             _gemm_stats_scratch(dev, rows, cols).data_ptr(), ptr(cfg["running_mean"]), ptr(cfg["running_var"]), ptr(cfg["num_batches_tracked"]), float(cfg["momentum"]), st),
+                      "rh_gemm_tf32x3_stats")
+            else:
+                gemm3x(x2, False, Wp, False, rows, cols, K, bias=b, out=h)
         elif b is not None:
             torch.addmm(b, x2, W.t(), out=h)
         else:
             torch.mm(x2, W.t(), out=h)
-        training = cfg["training"]
         counter = None
-        if training:
+        if training and stats is not None:
+            mean, var, counter = stats[:cols], stats[cols:2 * cols], stats[2 * cols:]
+        elif training:
             stats = torch.empty(2 * cols + 1, dtype=torch.float32, device=dev)
             check(L.rh_colstats(h.data_ptr(), cols, rows, cols, stats.data_ptr(), _colstats_scratch(dev, cols).data_ptr(), ptr(cfg["running_mean"]), ptr(cfg["running_var"]), ptr(cfg["num_batches_tracked"]),
                                 float(cfg["momentum"]), st), "rh_colstats")
