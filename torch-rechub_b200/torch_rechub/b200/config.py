@@ -60,5 +60,9 @@ fused_head = _flag("RECHUB_B200_FUSED_HEAD", True)
 # separate rh_colstats pass over the activation.  Off until its GPU validation (tests/test_gpu_gemm.py, gated on this flag).
 gemm_colstats = _flag("RECHUB_B200_GEMM_COLSTATS", False)
 
+# The same head for the other ranking models (DCN / DCNv2: LR over [cross | deep]; WideDeep: wide term + deep head; DIN: the final
+# tower).  Off until its GPU validation: run the GPU suite with RECHUB_B200_FUSED_HEAD_ALL=1.
+fused_head_all = _flag("RECHUB_B200_FUSED_HEAD_ALL", False)
+
 # Set by the graph runner while inputs live in static buffers that the next batch overwrites.
 static_inputs = False

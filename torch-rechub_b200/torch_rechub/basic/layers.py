@@ -252,6 +252,20 @@ class LR(nn.Module):
         y = self.fc(x)
         return torch.sigmoid(y) if self.sigmoid else y
 
+    def probability(self, x, extras=()):
+        """``sigmoid(fc(x).squeeze(1) + sum(extras))`` — the tail of DCN / DCNv2 / WideDeep — as one launch on CUDA when
+        ``config.fused_head_all`` is set (``rh_head_fwd``); the library ops otherwise."""
+        if x.is_cuda:
+            from ..b200 import config, ops
+            if config.fused_head_all:
+                p = ops.output_head(x, self.fc, extras, sigmoid=True)
+                if p is not None:
+                    return p
+        y = self.fc(x).squeeze(1)
+        for e in extras:
+            y = y + e
+        return torch.sigmoid(y)
+
 
 _FUSED_ACTS = {nn.ReLU: "relu", Dice: "dice", nn.PReLU: "prelu", nn.Sigmoid: "sigmoid", nn.LeakyReLU: "leakyrelu"}
 

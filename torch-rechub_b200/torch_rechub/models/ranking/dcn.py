@@ -26,5 +26,4 @@ class DCN(torch.nn.Module):
         embed_x = self.embedding(x, self.features, squeeze_dim=True)  # CUDA: one fused gather launch
         cn_out = self.cn(embed_x)  # CUDA: all cross layers in one launch
         mlp_out = self.mlp(embed_x)
-        y = self.linear(torch.cat([cn_out, mlp_out], dim=1))
-        return torch.sigmoid(y.squeeze(1))
+        return self.linear.probability(torch.cat([cn_out, mlp_out], dim=1))  # sigmoid(LR([cross | deep])), dcn.py:36-38

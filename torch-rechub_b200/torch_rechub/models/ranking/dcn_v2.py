@@ -47,4 +47,4 @@ class DCNv2(torch.nn.Module):
             final_out = self.stacked_dnn(cross_out)
         else:  # parallel
             final_out = torch.cat([cross_out, self.parallel_dnn(embed_x)], dim=1)
-        return torch.sigmoid(self.linear(final_out).squeeze(1))
+        return self.linear.probability(final_out)  # sigmoid(LR(final_out)), dcn_v2.py:57-59

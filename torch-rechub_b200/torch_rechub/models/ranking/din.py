@@ -76,6 +76,12 @@ class DIN(nn.Module):
                 attention_pooling.append(attention_seq.unsqueeze(1))
             attention_pooling = torch.cat(attention_pooling, dim=1)  # (B, n_hist, D)
             mlp_in = torch.cat([attention_pooling.flatten(start_dim=1), embed_x_target.flatten(start_dim=1), embed_x_features.flatten(start_dim=1)], dim=1)
+        if mlp_in.is_cuda:
+            from ...b200 import config
+            if config.fused_head_all:
+                p = self.mlp.forward_head(mlp_in, (), sigmoid=True)
+                if p is not None:
+                    return p
         y = self.mlp(mlp_in)
         return torch.sigmoid(y.squeeze(1))
 

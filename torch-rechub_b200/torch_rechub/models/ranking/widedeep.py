@@ -27,5 +27,11 @@ class WideDeep(torch.nn.Module):
     def forward(self, x):
         input_wide = self.embedding(x, self.wide_features, squeeze_dim=True)
         input_deep = self.embedding(x, self.deep_features, squeeze_dim=True)
+        if input_deep.is_cuda:
+            from ...b200 import config
+            if config.fused_head_all:  # the wide term rides along as a per-sample extra of the deep tower's fused head
+                p = self.mlp.forward_head(input_deep, (self.linear(input_wide).squeeze(1),), sigmoid=True)
+                if p is not None:
+                    return p
         y = self.linear(input_wide) + self.mlp(input_deep)
         return torch.sigmoid(y.squeeze(1))
