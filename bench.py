@@ -345,15 +345,20 @@ def run_b200_arm(args):
                 yield pool[(self.start + i) % N_POOL]
 
     trainer.train_one_epoch(HostLoader(max(args.warmup, 3), 0))
-    barrier()
-    t0 = time.perf_counter()
-    trainer.train_one_epoch(HostLoader(args.steps, 7))
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+    # K steps are ~50 ms of wall clock: one host hiccup moves the number by 20 %.  Three epochs of K steps each, the MEDIAN
+    # epoch (max over ranks per epoch) is reported.
+    E2E_EPOCHS = 3
+    epoch_s = []
+    for e in range(E2E_EPOCHS):
+        barrier()
+        t0 = time.perf_counter()
+        trainer.train_one_epoch(HostLoader(args.steps, 7 + e * args.steps))
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        epoch_s.append(float(t.item()))
+    e2e_s = sorted(epoch_s)[E2E_EPOCHS // 2]
     h2d = pool[0][0].h2d_bytes() + pool[0][1].numel() * 4
 
     # ---- roofline of the fused forward kernel -------------------------------------------------------------------
@@ -413,7 +418,7 @@ def run_b200_arm(args):
                        **({} if args.ids == "uniform" else {"ids": "zipf(alpha=%.2f) int64, %d distinct batches cycled (secondary workload)" % (ZIPF_ALPHA, N_POOL)})),
         "clocks": clocks,
         "e2e": {"value": total_samples / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8, "ms_per_step": e2e_s / args.steps * 1e3,
-                "api": "CTRTrainer.train_one_epoch(loader of pinned PackedColumns batches)"},
+                "api": "CTRTrainer.train_one_epoch(loader of pinned PackedColumns batches)", "epochs_timed": E2E_EPOCHS, "epoch_ms": [round(v * 1e3, 3) for v in epoch_s], "reported": "median epoch"},
         "gpu_launches": per_step_launches * args.steps,
         "gpu_launches_per_step": per_step_launches,
         "roofline": roof,
