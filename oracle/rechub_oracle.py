@@ -326,6 +326,91 @@ def crossnetmix_forward(sd, prefix, x, n_layers, n_experts, dtype=np.float64):
     return xl[:, :, 0]
 
 
+def crossnetmix_forward_backward(sd, prefix, x, n_layers, n_experts, d_out=None, dtype=np.float64):
+    """CrossNetMix.forward (basic/layers.py:470-506) in 2-D form with its hand-derived backward.
+
+    Per layer i and expert e:  g_e = x_l Wg_e^T;  t1 = tanh(x_l V_e);  t2 = tanh(t1 C_e^T);  o_e = x_0 * (t2 U_e^T + b_i);
+    s = softmax_e(g);  x_{l+1} = sum_e s_e o_e + x_l.   The gating Linears are shared by all layers (``:466``), so their
+    gradients accumulate across layers.  Returns ``(x_L, d_x, grads)`` (the last two None without ``d_out``)."""
+    x0 = _f(x, dtype)
+    gates = [_f(sd[prefix + "gating.%d.weight" % e], dtype) for e in range(n_experts)]  # (1, W) each
+    layers, xl = [], x0
+    for i in range(n_layers):
+        U, V, C = (_f(sd[prefix + "%s.%d" % (k, i)], dtype) for k in ("u_list", "v_list", "c_list"))
+        b = _f(sd[prefix + "bias.%d" % i], dtype)[:, 0]
+        g = np.stack([xl @ gates[e][0] for e in range(n_experts)], axis=1)  # (B, E)
+        t1 = [np.tanh(xl @ V[e]) for e in range(n_experts)]
+        t2 = [np.tanh(t1[e] @ C[e].T) for e in range(n_experts)]
+        uvb = [t2[e] @ U[e].T + b for e in range(n_experts)]
+        o = [x0 * uvb[e] for e in range(n_experts)]
+        sm = np.exp(g - g.max(axis=1, keepdims=True))
+        sm /= sm.sum(axis=1, keepdims=True)
+        nxt = sum(o[e] * sm[:, e:e + 1] for e in range(n_experts)) + xl
+        layers.append((xl, U, V, C, t1, t2, uvb, o, sm))
+        xl = nxt
+    if d_out is None:
+        return xl, None, None
+    grads = {prefix + "gating.%d.weight" % e: np.zeros_like(gates[e]) for e in range(n_experts)}
+    d_x0 = np.zeros_like(x0)
+    d_next = _f(d_out, dtype)
+    for i in reversed(range(n_layers)):
+        xin, U, V, C, t1, t2, uvb, o, sm = layers[i]
+        d_xl = d_next.copy()  # the residual
+        d_s = np.stack([(d_next * o[e]).sum(axis=1) for e in range(n_experts)], axis=1)
+        d_g = sm * (d_s - (sm * d_s).sum(axis=1, keepdims=True))
+        dU, dV, dC = np.zeros_like(U), np.zeros_like(V), np.zeros_like(C)
+        d_b = np.zeros(x0.shape[1], dtype=dtype)
+        for e in range(n_experts):
+            grads[prefix + "gating.%d.weight" % e] += (d_g[:, e] @ xin)[None, :]
+            d_xl += d_g[:, e:e + 1] * gates[e]
+            d_o = d_next * sm[:, e:e + 1]
+            d_x0 += d_o * uvb[e]
+            d_uv = d_o * x0
+            d_b += d_uv.sum(axis=0)
+            dU[e] = d_uv.T @ t2[e]
+            d_c = (d_uv @ U[e]) * (1 - t2[e]**2)
+            dC[e] = d_c.T @ t1[e]
+            d_a = (d_c @ C[e]) * (1 - t1[e]**2)
+            dV[e] = xin.T @ d_a
+            d_xl += d_a @ V[e].T
+        grads[prefix + "u_list.%d" % i], grads[prefix + "v_list.%d" % i], grads[prefix + "c_list.%d" % i] = dU, dV, dC
+        grads[prefix + "bias.%d" % i] = d_b[:, None]
+        d_next = d_xl
+    return xl, d_next + d_x0, grads
+
+
+def dcnv2_forward_backward(sd, x, y, dense_names, sparse_names, n_cross, n_hidden, n_experts=4, activation="relu", train=True, backward=True, dtype=np.float64):
+    """DCNv2.forward, default ``parallel`` structure with CrossNetMix (models/ranking/dcn_v2.py:47-59) + BCELoss backward."""
+    y = _f(y, dtype)
+    tile, embs = embedding_tile(sd, x, sparse_names, dense_names, dtype=dtype)
+    W = tile.shape[1]
+    cross_out, _, _ = crossnetmix_forward_backward(sd, "crossnet.", tile, n_cross, n_experts, None, dtype)
+    dnn_out, caches = mlp_forward(sd, "parallel_dnn.mlp.", tile, n_hidden, activation, train, False, dtype)
+    final = np.concatenate([cross_out, dnn_out], axis=1)
+    lw, lb = _f(sd["linear.fc.weight"], dtype), _f(sd["linear.fc.bias"], dtype)
+    logit = (final @ lw.T + lb)[:, 0]
+    loss, d_logit, prob = bce_and_dlogit(logit, y)
+    out = {"logit": logit, "prob": prob, "loss": loss, "tile": tile}
+    if not backward:
+        return out
+    g = d_logit[:, None]
+    grads = {"linear.fc.weight": g.T @ final, "linear.fc.bias": g.sum(axis=0)}
+    d_final = g @ lw
+    _, d_tile_c, cg = crossnetmix_forward_backward(sd, "crossnet.", tile, n_cross, n_experts, d_final[:, :W], dtype)
+    d_tile_m, mg = mlp_backward("parallel_dnn.mlp.", caches, d_final[:, W:], n_hidden, activation, train, False)
+    grads.update(cg)
+    grads.update(mg)
+    d_tile = d_tile_c + d_tile_m
+    col = 0
+    for n, e in zip(sparse_names, embs):
+        key = "embedding.embed_dict.%s.weight" % n
+        w = e.shape[1]
+        grads[key] = grads.get(key, 0) + embedding_grad(sd[key].shape, x[n], d_tile[:, col:col + w], dtype=dtype)
+        col += w
+    out["grads"] = grads
+    return out
+
+
 def dcnv2_forward(sd, x, dense_names, sparse_names, n_cross, n_hidden, n_experts=4, activation="relu", train=True, dtype=np.float64):
     """DCNv2.forward, default ``parallel`` structure with CrossNetMix (models/ranking/dcn_v2.py:47-59)."""
     tile, _ = embedding_tile(sd, x, sparse_names, dense_names, dtype=dtype)

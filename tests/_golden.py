@@ -41,7 +41,7 @@ def oracle_run(orc, name, rec, train=True, backward=True):
     if name == "dcn":
         return orc.dcn_forward_backward(rec["sd"], rec["x"], rec["y"], dense, sparse, m["n_cross"], m["n_hidden"], train=train, backward=backward)
     if name == "dcnv2":
-        return orc.dcnv2_forward(rec["sd"], rec["x"], dense, sparse, m["n_cross"], m["n_hidden"], train=train)
+        return orc.dcnv2_forward_backward(rec["sd"], rec["x"], rec["y"], dense, sparse, m["n_cross"], m["n_hidden"], train=train, backward=backward)
     return orc.din_forward_backward(rec["sd"], rec["x"], rec["y"], DIN_FEATURES, DIN_HISTORY, DIN_FEATURES, DIN_SHARED, m["n_att_hidden"], m["n_hidden"], use_softmax=bool(m["use_softmax"]), train=train,
                                     backward=backward)
 
