@@ -64,5 +64,9 @@ gemm_colstats = _flag("RECHUB_B200_GEMM_COLSTATS", False)
 # tower).  Off until its GPU validation: run the GPU suite with RECHUB_B200_FUSED_HEAD_ALL=1.
 fused_head_all = _flag("RECHUB_B200_FUSED_HEAD_ALL", False)
 
+# CrossNetMix (DCN-v2) with the experts batched into three GEMMs per layer instead of a Python loop over experts
+# (basic/layers.py::CrossNetMix._forward_batched; same algebra, ~20x fewer launches).
+batched_crossmix = _flag("RECHUB_B200_BATCHED_CROSSMIX", True)
+
 # Set by the graph runner while inputs live in static buffers that the next batch overwrites.
 static_inputs = False

@@ -423,7 +423,35 @@ class CrossNetMix(nn.Module):
         self.gating = nn.ModuleList([nn.Linear(input_dim, 1, bias=False) for _ in range(self.num_experts)])
         self.bias = torch.nn.ParameterList([nn.Parameter(nn.init.zeros_(torch.empty(input_dim, 1))) for _ in range(self.num_layers)])
 
+    def _forward_batched(self, x):
+        """The same map with the experts batched into three GEMMs per layer (the CUDA route; ~60 launches per layer otherwise):
+
+            [a | g] = x_l [V_1 .. V_E | Wg^T]            one (B, W) x (W, E r + E) product: every expert's projection AND the gates
+            t2_e    = tanh(C_e tanh(a_e)),  s = softmax(g)
+            x_{l+1} = x_0 * ([s_1 t2_1 .. s_E t2_E] [U_1 .. U_E]^T + b) + x_l
+
+        — the gate-weighted sum over experts moves inside the last product's K dimension (sum_e s_e = 1 keeps the bias whole).
+        Algebraically identical to the loop below; fp32 rounding differs by reassociation only."""
+        n, width = x.shape
+        E = self.num_experts
+        gates = torch.cat([g.weight for g in self.gating], dim=0)  # (E, W)
+        x_0, x_l = x, x
+        for i in range(self.num_layers):
+            U, V, C = self.u_list[i], self.v_list[i], self.c_list[i]  # (E, W, r), (E, W, r), (E, r, r)
+            r = V.shape[2]
+            first = torch.cat([V.permute(1, 0, 2).reshape(width, E * r), gates.t()], dim=1)  # (W, E r + E)
+            ag = x_l @ first
+            t1 = torch.tanh(ag[:, :E * r]).view(n, E, r)
+            t2 = torch.tanh(torch.einsum("ber,esr->bes", t1, C))  # C_e @ t1_e per expert
+            z = (t2 * torch.softmax(ag[:, E * r:], dim=1).unsqueeze(2)).reshape(n, E * r)
+            x_l = x_0 * (z @ U.permute(0, 2, 1).reshape(E * r, width) + self.bias[i].view(1, width)) + x_l
+        return x_l.squeeze()  # the reference's squeeze() quirk at B == 1 (layers.py:505), kept on this route too
+
     def forward(self, x):
+        if x.is_cuda and x.dim() == 2:
+            from ..b200 import config
+            if config.batched_crossmix:
+                return self._forward_batched(x)
         x_0 = x.unsqueeze(2)  # (B, width, 1)
         x_l = x_0
         for i in range(self.num_layers):
