@@ -30,6 +30,10 @@ p2p_exchange = _flag("RECHUB_B200_P2P", True)
 # staging buffer on the owner + an owner-side scatter-add pass.
 p2p_field_major_ids = _flag("RECHUB_B200_P2P_FIELD_MAJOR", True)
 p2p_direct_grads = _flag("RECHUB_B200_P2P_DIRECT_GRADS", True)
+# Issue the post-backward barrier (all row-gradient REDs landed) AFTER launching the dense all-reduce, so that it overlaps it.
+# The barrier and the all-reduce are then concurrent branches of the captured graph and BOTH wait on peers: correct only while
+# every rank's executor orders the two branches the same way.  Measured on 2 GPUs only -> off by default.
+p2p_defer_barrier = _flag("RECHUB_B200_P2P_DEFER_BARRIER", False)
 
 # Check the device-side out-of-range-id flag after every forward (one D2H sync per step).  When off the
 # flag is checked at the trainer's existing sync points (``loss.item()``) and by ``check_errors()``.

@@ -492,8 +492,9 @@ class DistEngine(object):
             p.grad = None  # autograd then hands over fresh gradient tensors (no accumulate kernels)
         opt = trainer.optimizer
         split = hasattr(opt, "rowwise") and hasattr(opt, "dense_engine")
+        from . import config
         for f in self.fronts:
-            f.lazy_clean, f.defer_barrier, f.deferred = not split, True, None
+            f.lazy_clean, f.defer_barrier, f.deferred = not split, bool(config.p2p_defer_barrier), None
         loss = trainer._loss(x_dict, y)
         loss.backward(self._inv_world)  # d(loss / world): the all-reduce SUM then yields the gradient of the global-batch mean
         for f in self.fronts:
