@@ -7,22 +7,20 @@ class EarlyStopper(object):
 
     Args:
         patience (int): tolerated number of consecutive non-improving evaluations.
+
+    Attributes read by the trainers: ``best_auc``, ``best_weights``, ``trial_counter``.
     """
 
     def __init__(self, patience):
-        self.patience = patience
-        self.trial_counter = 0
-        self.best_auc = 0
-        self.best_weights = None
+        self.patience, self.trial_counter = patience, 0
+        self.best_auc, self.best_weights = 0, None
 
     def stop_training(self, val_auc, weights):
-        """Return True when training should stop (reference ``callback.py:17-33``)."""
-        improved = val_auc > self.best_auc
-        if improved:
-            self.best_auc, self.trial_counter = val_auc, 0
-            self.best_weights = copy.deepcopy(weights)
+        """True when ``val_auc`` failed to beat the best one ``patience`` times in a row; a new best snapshots ``weights``."""
+        if val_auc > self.best_auc:
+            self.best_auc, self.trial_counter, self.best_weights = val_auc, 0, copy.deepcopy(weights)
             return False
-        if self.trial_counter + 1 < self.patience:
+        exhausted = self.trial_counter + 1 >= self.patience
+        if not exhausted:
             self.trial_counter += 1
-            return False
-        return True
+        return exhausted

@@ -3,6 +3,8 @@ import torch
 
 from ...basic.layers import LR, MLP, CrossNetMix, CrossNetV2, EmbeddingLayer
 
+_STRUCTURES = ("crossnet_only", "stacked", "parallel")
+
 
 class DCNv2(torch.nn.Module):
     """Deep & Cross Network v2 with (by default) the mixture of low-rank experts cross net.
@@ -14,37 +16,30 @@ class DCNv2(torch.nn.Module):
         model_structure (str): ``"crossnet_only"``, ``"stacked"`` or ``"parallel"``.
         use_low_rank_mixture (bool): ``CrossNetMix`` when True, else full-rank ``CrossNetV2``.
         low_rank (int), num_experts (int): ``CrossNetMix`` sizes.
+
+    Sub-module names (= state_dict keys) follow the reference: ``embedding``, ``crossnet``, ``stacked_dnn`` or ``parallel_dnn``,
+    ``linear`` — created in that order, so a seed reproduces the reference's initial weights.
     """
 
     def __init__(self, features, n_cross_layers, mlp_params, model_structure="parallel", use_low_rank_mixture=True, low_rank=32, num_experts=4, **kwargs):
-        super(DCNv2, self).__init__()
-        self.features = features
-        self.dims = sum([fea.embed_dim for fea in features])
+        super().__init__()
+        width = sum(fea.embed_dim for fea in features)
+        self.features, self.dims, self.model_structure = features, width, model_structure
         self.embedding = EmbeddingLayer(features)
-        if use_low_rank_mixture:
-            self.crossnet = CrossNetMix(self.dims, n_cross_layers, low_rank=low_rank, num_experts=num_experts)
-        else:
-            self.crossnet = CrossNetV2(self.dims, n_cross_layers)
-        self.model_structure = model_structure
-        assert self.model_structure in ["crossnet_only", "stacked", "parallel"], \
-            "model_structure={} not supported!".format(self.model_structure)
-        if self.model_structure == "stacked":
-            self.stacked_dnn = MLP(self.dims, output_layer=False, **mlp_params)
-            final_dim = mlp_params["dims"][-1]
-        if self.model_structure == "parallel":
-            self.parallel_dnn = MLP(self.dims, output_layer=False, **mlp_params)
-            final_dim = mlp_params["dims"][-1] + self.dims
-        if self.model_structure == "crossnet_only":
-            final_dim = self.dims
-        self.linear = LR(final_dim)
+        self.crossnet = CrossNetMix(width, n_cross_layers, low_rank=low_rank, num_experts=num_experts) if use_low_rank_mixture else CrossNetV2(width, n_cross_layers)
+        if model_structure not in _STRUCTURES:  # an AssertionError, as the reference's assert (dcn_v2.py:35-36)
+            raise AssertionError("model_structure={} not supported!".format(model_structure))
+        head_width = width
+        if model_structure != "crossnet_only":
+            setattr(self, model_structure + "_dnn", MLP(width, output_layer=False, **mlp_params))
+            head_width = mlp_params["dims"][-1] + (width if model_structure == "parallel" else 0)
+        self.linear = LR(head_width)
 
     def forward(self, x):
-        embed_x = self.embedding(x, self.features, squeeze_dim=True)
-        cross_out = self.crossnet(embed_x)
-        if self.model_structure == "crossnet_only":
-            final_out = cross_out
-        elif self.model_structure == "stacked":
-            final_out = self.stacked_dnn(cross_out)
-        else:  # parallel
-            final_out = torch.cat([cross_out, self.parallel_dnn(embed_x)], dim=1)
-        return self.linear.probability(final_out)  # sigmoid(LR(final_out)), dcn_v2.py:57-59
+        tile = self.embedding(x, self.features, squeeze_dim=True)
+        crossed = self.crossnet(tile)
+        if self.model_structure == "stacked":
+            crossed = self.stacked_dnn(crossed)
+        elif self.model_structure == "parallel":
+            crossed = torch.cat([crossed, self.parallel_dnn(tile)], dim=1)
+        return self.linear.probability(crossed)  # sigmoid(LR(.)), dcn_v2.py:57-59
