@@ -15,23 +15,21 @@ class WideDeep(torch.nn.Module):
     """
 
     def __init__(self, wide_features, deep_features, mlp_params):
-        super(WideDeep, self).__init__()
-        self.wide_features = wide_features
-        self.deep_features = deep_features
-        self.wide_dims = sum([fea.embed_dim for fea in wide_features])
-        self.deep_dims = sum([fea.embed_dim for fea in deep_features])
+        super().__init__()
+        width = lambda feas: sum(fea.embed_dim for fea in feas)
+        self.wide_features, self.deep_features = wide_features, deep_features
+        self.wide_dims, self.deep_dims = width(wide_features), width(deep_features)
+        # creation order linear -> embedding -> mlp: the reference's RNG consumption (widedeep.py:27-29)
         self.linear = LR(self.wide_dims)
         self.embedding = EmbeddingLayer(wide_features + deep_features)
         self.mlp = MLP(self.deep_dims, **mlp_params)
 
     def forward(self, x):
-        input_wide = self.embedding(x, self.wide_features, squeeze_dim=True)
-        input_deep = self.embedding(x, self.deep_features, squeeze_dim=True)
-        if input_deep.is_cuda:
+        wide, deep = (self.embedding(x, feas, squeeze_dim=True) for feas in (self.wide_features, self.deep_features))
+        if deep.is_cuda:
             from ...b200 import config
             if config.fused_head_all:  # the wide term rides along as a per-sample extra of the deep tower's fused head
-                p = self.mlp.forward_head(input_deep, (self.linear(input_wide).squeeze(1),), sigmoid=True)
+                p = self.mlp.forward_head(deep, (self.linear(wide).squeeze(1),), sigmoid=True)
                 if p is not None:
                     return p
-        y = self.linear(input_wide) + self.mlp(input_deep)
-        return torch.sigmoid(y.squeeze(1))
+        return torch.sigmoid((self.linear(wide) + self.mlp(deep)).squeeze(1))
