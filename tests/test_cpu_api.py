@@ -180,3 +180,26 @@ def test_batched_crossnetmix_route_equals_the_reference_loop():
         for n, p in m.named_parameters():
             assert (p.grad - ref[n]).abs().max().item() <= 2e-5 * ref[n].abs().max().item() + 1e-7, n
         assert (x1.grad - x2.grad).abs().max().item() <= 2e-5 * x1.grad.abs().max().item() + 1e-7
+
+
+def test_packed_loader_int32_ids_feed_the_same_model_outputs():
+    from torch_rechub.b200.data import PackedLoader
+    from torch_rechub.basic.features import DenseFeature, SparseFeature
+    from torch_rechub.models.ranking import DeepFM
+    g = np.random.RandomState(0)
+    n = 50
+    x = {"I0": g.rand(n), "C0": g.randint(0, 30, n), "C1": g.randint(0, 30, n)}
+    y = g.randint(0, 2, n)
+    torch.manual_seed(0)
+    feats = [SparseFeature("C0", 30, 8), SparseFeature("C1", 30, 8)]
+    model = DeepFM([DenseFeature("I0")] + feats, feats, {"dims": [8]}).eval()
+    outs = []
+    for dt in (torch.int64, torch.int32):
+        (xb, yb), = list(PackedLoader(x, y, batch_size=n, id_dtype=dt))
+        assert xb["C0"].dtype == dt and xb.h2d_bytes() == n * (2 * (8 if dt == torch.int64 else 4) + 4)
+        outs.append(model(xb))
+    assert torch.equal(outs[0], outs[1])
+    with pytest.raises(ValueError):
+        PackedLoader({"C0": np.array([2**31])}, np.array([0]), batch_size=1, id_names=["C0"], num_names=[], id_dtype=torch.int32)
+    with pytest.raises(ValueError):
+        PackedLoader(x, y, batch_size=n, id_dtype=torch.int16)
