@@ -133,6 +133,58 @@ def test_dssm_and_match_trainer_match_reference(kw):
         assert torch.equal(a, b), k
 
 
+def _variant(F, M, kind, n_users=14, n_items=30):
+    torch.manual_seed(33)
+    user = [F.SparseFeature("user_id", n_users, embed_dim=8), F.SequenceFeature("hist_item_id", n_items, embed_dim=8, pooling="mean", shared_with="item_id")]
+    item = [F.SparseFeature("item_id", n_items, embed_dim=8)]
+    if kind == "youtube":
+        neg = [F.SequenceFeature("neg_items", n_items, embed_dim=8, pooling="concat", shared_with="item_id")]
+        return M.YoutubeDNN(user, item, neg, user_params={"dims": [16, 8]}, temperature=0.5)
+    neg = [F.SparseFeature("neg_items", n_items, embed_dim=8, shared_with="item_id")]
+    return M.FaceBookDSSM(user, item, neg, user_params={"dims": [16, 8]}, item_params={"dims": [8]})
+
+
+def _variant_batches(kind, n_batches=4, b=10, n_users=14, n_items=30, L=5, n_neg=3):
+    g = torch.Generator().manual_seed(18)
+    out = []
+    for _ in range(n_batches):
+        x = {"user_id": torch.randint(0, n_users, (b,), generator=g), "item_id": torch.randint(0, n_items, (b,), generator=g), "hist_item_id": torch.randint(0, n_items, (b, L), generator=g),
+             "neg_items": torch.randint(0, n_items, (b, n_neg) if kind == "youtube" else (b,), generator=g)}
+        out.append((x, torch.zeros(b, dtype=torch.long)))
+    return out
+
+
+@needs_ref
+@pytest.mark.parametrize("kind,mode", [("youtube", 2), ("facebook", 1)])
+def test_listwise_and_pairwise_variants_match_reference(kind, mode):
+    """YoutubeDNN (list-wise softmax) and FaceBookDSSM (pair-wise BPR): same weights, outputs, tower modes and MatchTrainer
+    epoch as the live reference — the trainer's modes 2 and 1 without in-batch negatives."""
+    import torch_rechub.basic.features as F
+    import torch_rechub.models.matching as M
+    from torch_rechub.trainers import MatchTrainer
+    rF, rM, rT = live.ref_module("basic.features"), live.ref_module("models.matching"), live.ref_module("trainers").MatchTrainer
+    mine, theirs = _variant(F, M, kind), _variant(rF, rM, kind)
+    assert list(mine.state_dict().keys()) == list(theirs.state_dict().keys())
+    for (k, a), b in zip(mine.state_dict().items(), theirs.state_dict().values()):
+        assert torch.equal(a, b), k
+    data = _variant_batches(kind)
+    mine.eval(), theirs.eval()
+    ya, yb = mine(data[0][0]), theirs(data[0][0])
+    if kind == "youtube":
+        assert ya.shape == (10, 4) and torch.equal(ya, yb)
+    else:
+        assert torch.equal(ya[0], yb[0]) and torch.equal(ya[1], yb[1])
+    for tower in ("user", "item"):
+        mine.mode = theirs.mode = tower
+        assert torch.equal(mine(data[0][0]), theirs(data[0][0]))
+    mine.mode = theirs.mode = None
+    la = MatchTrainer(mine, mode=mode, n_epoch=1, device="cpu").train_one_epoch(data, log_interval=2)
+    lb = rT(theirs, mode=mode, n_epoch=1, device="cpu").train_one_epoch(data, log_interval=2)
+    assert la == lb
+    for (k, a), b in zip(mine.state_dict().items(), theirs.state_dict().values()):
+        assert torch.equal(a, b), k
+
+
 def test_match_trainer_rejects_models_without_towers_and_bad_modes():
     from torch_rechub.trainers import MatchTrainer
     with pytest.raises(ValueError):
@@ -141,7 +193,7 @@ def test_match_trainer_rejects_models_without_towers_and_bad_modes():
         MatchTrainer(torch.nn.Linear(2, 1), mode=3)
     import torch_rechub.models.matching as M
     with pytest.raises(NotImplementedError):
-        M.YoutubeDNN()
+        M.MIND()
 
 
 def test_fit_saves_and_inference_embedding_roundtrip(tmp_path):
@@ -169,7 +221,7 @@ def test_reference_matching_tests_pass_against_this_package(tmp_path):
     tdir.mkdir(parents=True)
     for name in ("test_inbatch_sampling.py", "test_e2e_matching.py"):
         shutil.copy(os.path.join(live.REFERENCE_ROOT, "tests", name), tdir / name)
-    cmd = [sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", str(tdir), "-k", "inbatch or (DSSM and not FaceBook)"]
+    cmd = [sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", str(tdir), "-k", "inbatch or DSSM or YoutubeDNN"]
     res = subprocess.run(cmd, env=dict(os.environ, PYTHONPATH=PKG), cwd=str(tdir), capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
     assert "passed" in res.stdout
