@@ -89,7 +89,7 @@ class _ShardedP2P(torch.autograd.Function):
       forward   rh_ids_scatter (ids -> owners)  | barrier | rh_fields_fwd_p2p (owner gathers, rows land in the samples' GPUs)
                 | barrier | rh_fields_fwd on the received rows (unpack + dense columns + FM + LR)
       backward  direct gradients (default): rh_fields_bwd REDs every row gradient over NVLink into the OWNER's gradient buffer
-                at the row id | barrier (issued by DistEngine.train_step after it launched the dense all-reduce)
+                at the row id | barrier (config.p2p_defer_barrier: issued by DistEngine.train_step after the all-reduce launch)
                 staged gradients: rh_fields_bwd REDs into the owner's staging buffer | barrier | rh_fields_bwd on the owner
                 (scatter-add into its tables) | re-zero the staging buffer
     """
