@@ -70,7 +70,7 @@ fused_head_all = _flag("RECHUB_B200_FUSED_HEAD_ALL", False)
 
 # CrossNetMix (DCN-v2) with the experts batched into three GEMMs per layer instead of a Python loop over experts
 # (basic/layers.py::CrossNetMix._forward_batched; same algebra, ~20x fewer launches).
-batched_crossmix = _flag("RECHUB_B200_BATCHED_CROSSMIX", True)
+batched_crossmix = _flag("RECHUB_B200_BATCHED_CROSSMIX", False)  # CPU-verified against the loop; first GPU run pending -> opt-in
 
 # Set by the graph runner while inputs live in static buffers that the next batch overwrites.
 static_inputs = False
