@@ -12,3 +12,4 @@ run timeout 200 python bench.py --no-cpu-baseline
 run env RECHUB_B200_GEMM_COLSTATS=1 timeout 200 python bench.py --no-cpu-baseline
 run timeout 200 python bench.py --no-cpu-baseline --ids zipf
 run timeout 120 python tools/kernel_times.py
+run timeout 200 python tools/sweep_gemm.py
