@@ -210,6 +210,13 @@ int rh_fields_rowwise_update(const rh_field* fields, int n_fields, int dim, int 
                              int64_t state_row_stride,
                              float beta1, float beta2, float eps, float weight_decay, void* stream);
 
+/* L2 prefetch (prefetch.global.L2, nothing loaded or stored) of the rows the ids select in up to three arrays per field:
+ * rh_field.table (vocab, dim), rh_field.table_grad (vocab, dim; may be NULL) and state[f] (vocab, state_row_stride floats; the
+ * interleaved optimiser records; `state` may be NULL).  Meant for the NEXT batch, one step ahead on a copy stream: the
+ * reference has no counterpart (its lookups are synchronous index_select calls, basic/layers.py:83). */
+int rh_fields_prefetch(const rh_field* fields, int n_fields, int dim, int batch,
+                       float* const* state, int64_t state_row_stride, void* stream);
+
 /* table_grad[ids] = 0 for all tables of one batch in a single launch (sparse zero_grad). */
 int rh_fields_zero(const rh_field* fields, int n_fields, int dim, int batch, void* stream);
 

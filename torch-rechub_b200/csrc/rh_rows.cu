@@ -388,6 +388,26 @@ __global__ void __launch_bounds__(128) fields_zero_kernel(const __grid_constant_
   if ((uint64_t)id < (uint64_t)p.vocab[f]) *reinterpret_cast<float4*>(p.grad[f] + id * p.dim + 4 * q) = f4_zero();
 }
 
+// L2 prefetch of the rows a FUTURE batch will touch (tables, gradient rows, optimiser records): one thread per (sample, array).
+// Issued one step ahead on the copy stream, it turns the latency-bound random accesses of the next step's gather, scatter and
+// row-wise update into L2 hits.  Nothing is read into registers and nothing is written: a wrong or stale id costs bandwidth only.
+__global__ void __launch_bounds__(128) fields_prefetch_kernel(const __grid_constant__ MultiP p, int64_t state_row_bytes) {
+  const int f = blockIdx.y;
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= p.batch) return;
+  const int64_t id = load_id(p.ids[f], r * p.id_stride[f], p.is_i32[f] != 0);
+  if ((uint64_t)id >= (uint64_t)p.vocab[f]) return;
+  const int64_t row_bytes = (int64_t)p.dim * 4;
+  const char* bases[3] = {reinterpret_cast<const char*>(p.table[f]), reinterpret_cast<const char*>(p.grad[f]), reinterpret_cast<const char*>(p.st1[f])};
+  const int64_t strides[3] = {row_bytes, row_bytes, state_row_bytes};
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    if (bases[a] == nullptr) continue;
+    const char* row = bases[a] + id * strides[a];
+    for (int64_t off = 0; off < strides[a]; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + off));
+  }
+}
+
 __global__ void opt_advance_kernel(int32_t* step_dev, float* bc_dev, float beta1, float beta2) {
   const int step = *step_dev + 1;
   *step_dev = step;
@@ -578,6 +598,34 @@ extern "C" int rh_fields_rowwise_update(const rh_field* fields, int n_fields, in
   const int threads = 128;
   dim3 grid((unsigned)(((int64_t)batch * G + threads - 1) / threads), n_fields);
   fields_rowwise_update_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(p, a, step_dev, lr_dev, bias_corr_dev, G, state_row_stride);
+  RH_LAUNCH_CHECK();
+  return RH_OK;
+}
+
+extern "C" int rh_fields_prefetch(const rh_field* fields, int n_fields, int dim, int batch, float* const* state, int64_t state_row_stride,
+                                  void* stream) {
+  RH_REQUIRE(n_fields > 0 && n_fields <= RH_MAX_FIELDS && fields != nullptr, RH_ERR_INVALID_ARG, "rh_fields_prefetch: n_fields %d not in [1,%d]",
+             n_fields, RH_MAX_FIELDS);
+  RH_REQUIRE(dim > 0 && state_row_stride >= 0, RH_ERR_INVALID_ARG, "rh_fields_prefetch: bad dim / state_row_stride");
+  if (batch <= 0) return RH_OK;
+  static thread_local rh::MultiP p;
+  memset(&p, 0, sizeof(p));
+  for (int i = 0; i < n_fields; ++i) {
+    const rh_field& s = fields[i];
+    RH_REQUIRE(s.table != nullptr && s.ids != nullptr && s.vocab > 0, RH_ERR_INVALID_ARG, "rh_fields_prefetch: field %d: table/ids NULL", i);
+    RH_REQUIRE(s.id_stride >= 0 && s.id_stride < (int64_t)1 << 31, RH_ERR_INVALID_ARG, "rh_fields_prefetch: field %d: id_stride out of range", i);
+    p.table[i] = const_cast<float*>(s.table);
+    p.grad[i] = s.table_grad;
+    p.st1[i] = state != nullptr ? state[i] : nullptr;
+    p.ids[i] = s.ids;
+    p.id_stride[i] = (int32_t)s.id_stride;
+    p.vocab[i] = s.vocab;
+    p.is_i32[i] = (uint8_t)(s.ids_are_i32 != 0);
+  }
+  p.batch = batch;
+  p.dim = dim;
+  dim3 grid((unsigned)((batch + 127) / 128), n_fields);
+  fields_prefetch_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(p, state_row_stride * 4);
   RH_LAUNCH_CHECK();
   return RH_OK;
 }

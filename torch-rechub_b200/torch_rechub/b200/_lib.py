@@ -47,6 +47,7 @@ PROTOTYPES = {
     "rh_rowwise_update": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_i, c_i64, c_i, c_p, c_p, c_p, c_i64, c_f, c_f, c_f, c_f, c_p],
     "rh_opt_advance": [c_p, c_p, c_f, c_f, c_p],
     "rh_fields_rowwise_update": [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_i64, c_f, c_f, c_f, c_f, c_p],
+    "rh_fields_prefetch": [c_p, c_i, c_i, c_i, c_p, c_i64, c_p],
     "rh_fields_zero": [c_p, c_i, c_i, c_i, c_p],
     "rh_fm_fwd": [c_p, c_i, c_i, c_i, c_i, c_p, c_p],
     "rh_fm_bwd": [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p],

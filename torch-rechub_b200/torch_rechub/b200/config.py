@@ -72,5 +72,9 @@ fused_head_all = _flag("RECHUB_B200_FUSED_HEAD_ALL", False)
 # (basic/layers.py::CrossNetMix._forward_batched; same algebra, ~20x fewer launches).
 batched_crossmix = _flag("RECHUB_B200_BATCHED_CROSSMIX", False)  # CPU-verified against the loop; first GPU run pending -> opt-in
 
+# Pipelined loop: prefetch into L2 the table / gradient / optimiser rows the NEXT batch will touch (rh_fields_prefetch on the copy
+# stream, one step ahead).  Written after the round's last GPU session -> off until measured.
+next_batch_prefetch = _flag("RECHUB_B200_NEXT_BATCH_PREFETCH", False)
+
 # Set by the graph runner while inputs live in static buffers that the next batch overwrites.
 static_inputs = False

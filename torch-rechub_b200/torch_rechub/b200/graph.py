@@ -77,6 +77,7 @@ class GraphedStep(object):
         self.staging_x = self.staging_y = None  # landing buffers of the copy stream (host batches only)
         self.copy_stream = None
         self.ev_h2d = self.ev_consumed = None
+        self._pf_cols = None  # (id column name, table weight) pairs of the next-batch L2 prefetch
         self.calls = 0
         self.stream = None  # warm-up AND capture run on this side stream (autograd binds AccumulateGrad nodes to the stream
         # they were first used on; a default-stream node inside a capture invalidates it)
@@ -130,9 +131,58 @@ class GraphedStep(object):
         with torch.cuda.stream(cs):
             self._copy_batch(x_dict, y, self.staging_x, self.staging_y)
             self.ev_h2d.record(cs)
+            if config.next_batch_prefetch:
+                self._prefetch_rows(self.staging_x)  # on the copy stream, behind the H2D copy, while the previous step computes
         cur.wait_event(self.ev_h2d)
         self._copy_batch(self.staging_x, self.staging_y, self.static_x, self.static_y)
         self.ev_consumed.record(cur)
+
+    def _prefetch_rows(self, staged):
+        """``rh_fields_prefetch`` for every 1-D sparse id column of the staged batch: table rows, their gradient rows and their
+        interleaved Adam records into L2, one step before the kernels that touch them."""
+        import ctypes
+        from . import _lib, table as _table
+        from ..basic.features import SparseFeature
+        from ..basic.layers import EmbeddingLayer
+        if self._pf_cols is None:
+            cols, seen = [], set()
+            for mod in self.trainer.model.modules():
+                if isinstance(mod, EmbeddingLayer):
+                    for fea in mod.features:
+                        if isinstance(fea, SparseFeature) and fea.name in staged and fea.name not in seen:
+                            w = mod.table_of(fea).weight
+                            if w.is_cuda and w.dim() == 2 and w.numel() > 0 and w.shape[1] % 4 == 0:
+                                seen.add(fea.name)
+                                cols.append((fea.name, w))
+            self._pf_cols = cols
+        by_dim = {}
+        for name, w in self._pf_cols:
+            ids = staged[name]
+            if ids.dim() == 1 and ids.dtype in (torch.int64, torch.int32):
+                by_dim.setdefault(w.shape[1], []).append((ids, w))
+        rw = getattr(self.trainer.optimizer, "rowwise", None)
+        L, st = _lib.lib(), _lib.stream_ptr()
+        for dim, items in by_dim.items():
+            for i in range(0, len(items), _lib.RH_MAX_FIELDS):
+                chunk = items[i:i + _lib.RH_MAX_FIELDS]
+                arr = (_lib.RhField * len(chunk))()
+                states = (ctypes.c_void_p * len(chunk))()
+                stride = 0
+                for j, (ids, w) in enumerate(chunk):
+                    slot = _table.find_slot(w)
+                    a = arr[j]
+                    a.table = w.data_ptr()
+                    a.table_grad = slot.buffer.data_ptr() if slot is not None and slot.buffer is not None else None
+                    a.ids = ids.data_ptr()
+                    a.id_stride = ids.stride(0) if ids.shape[0] > 1 else 1
+                    a.ids_are_i32 = int(ids.dtype == torch.int32)
+                    a.vocab = w.shape[0]
+                    a.padding_idx, a.tile_col, a.fm_slot = -1, -1, -1
+                    rec = rw.state.get(id(w)) if rw is not None else None
+                    if rec is not None and rec.get("stride") == 2 * dim:  # interleaved (m | v) records
+                        states[j] = rec["m"].data_ptr()
+                        stride = 2 * dim
+                _lib.check(L.rh_fields_prefetch(arr, len(chunk), dim, chunk[0][0].shape[0], states if stride else None, stride, st), "rh_fields_prefetch")
 
     def _side_stream(self):
         if self.stream is None:
