@@ -32,11 +32,20 @@ def _make(kind):
     sparse = [SparseFeature("C%d" % i, 31 + i, 8, initializer=init) for i in range(5)]
     if kind == "deepfm":
         return DeepFM(dense + sparse, sparse, {"dims": [16, 8], "dropout": 0.0, "activation": "relu"})
+    if kind == "din":  # sequence features: the layer stays replicated (data parallel), SURVEY §8e
+        from torch_rechub.basic.features import SequenceFeature
+        from torch_rechub.models.ranking import DIN
+        feats = [SparseFeature("target_item", 30, 8, initializer=init), SparseFeature("user", 11, 8, initializer=init)]
+        hist = [SequenceFeature("hist_item", 30, 8, pooling="concat", shared_with="target_item")]
+        return DIN(features=feats, history_features=hist, target_features=feats[:1], mlp_params={"dims": [16, 8]}, attention_mlp_params={"dims": [16, 8]})
     return DCN(dense + sparse, n_cross_layers=2, mlp_params={"dims": [16, 8]})
 
 
-def _batch(rank, b=24):
+def _batch(rank, b=24, kind=None):
     g = torch.Generator().manual_seed(100 + rank)
+    if kind == "din":
+        x = {"target_item": torch.randint(1, 30, (b,), generator=g), "user": torch.randint(0, 11, (b,), generator=g), "hist_item": torch.randint(0, 30, (b, 5), generator=g)}
+        return x, torch.randint(0, 2, (b,), generator=g).float()
     x = {"I%d" % i: torch.rand(b, generator=g) for i in range(2)}
     x.update({"C%d" % i: torch.randint(0, 31, (b,), generator=g) for i in range(5)})
     return x, torch.randint(0, 2, (b,), generator=g).float()
@@ -52,9 +61,12 @@ def _worker(rank, world, port, kind, out):
     full_sd = copy.deepcopy(model.state_dict())
     trainer = CTRTrainer(model, optimizer_fn=torch.optim.SGD, optimizer_params={"lr": 0.1}, device="cpu")
     assert trainer._dist is not None and trainer._dist.world == world
-    n_owned = sum(1 for f in trainer._dist.fronts for n, o in f.owner.items() if o == rank)
-    assert n_owned in (2, 3) and len(trainer._dist.foreign) == 5 - n_owned
-    x, y = _batch(rank)
+    if kind == "din":
+        assert not trainer._dist.fronts and len(trainer._dist.replicated_ids) == 2 and not trainer._dist.foreign
+    else:
+        n_owned = sum(1 for f in trainer._dist.fronts for n, o in f.owner.items() if o == rank)
+        assert n_owned in (2, 3) and len(trainer._dist.foreign) == 5 - n_owned
+    x, y = _batch(rank, kind=kind)
     model.train()
     loss = trainer._train_step(x, y)
     sd = trainer._dist.full_state_dict()
@@ -63,7 +75,7 @@ def _worker(rank, world, port, kind, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kind", ["deepfm", "dcn"])
+@pytest.mark.parametrize("kind", ["deepfm", "dcn", "din"])
 def test_two_rank_sharded_step_matches_dataparallel_semantics(kind):
     world = 2
     out = mp.get_context("spawn").Manager().dict()
@@ -81,7 +93,7 @@ def test_two_rank_sharded_step_matches_dataparallel_semantics(kind):
         for m, (rm, rv) in zip(bn_mods, saved_stats):  # each replica starts from the same running statistics
             m.running_mean.copy_(rm)
             m.running_var.copy_(rv)
-        x, y = _batch(r)
+        x, y = _batch(r, kind=kind)
         loss = torch.nn.BCELoss()(ref(x), y) / world
         loss.backward()
         total += float(loss)

@@ -414,8 +414,14 @@ class DistEngine(object):
         from .table import FieldTable
         self.fronts = []
         self.owned, self.foreign = [], []
+        self.replicated_ids = set()  # table weights that stay whole on every rank (dense all-reduce of their gradients)
         for mod in model.modules():
             if isinstance(mod, EmbeddingLayer):
+                if any(isinstance(f, SequenceFeature) for f in mod.features):
+                    # a layer with sequence features (DIN: SURVEY §8e — its tables are a few MB) is not sharded: plain data
+                    # parallelism, the tables' dense gradients ride the all-reduce bucket with the tower's
+                    self.replicated_ids.update(id(t.weight) for t in mod.embed_dict.values())
+                    continue
                 front = ShardedFront(mod, self.group, self.device)
                 mod._dist = front
                 self.fronts.append(front)

@@ -194,8 +194,10 @@ class HybridOptimizer(object):
         self.scheduler_target = dense
 
     @classmethod
-    def build(cls, model, optimizer_fn, optimizer_params):
-        """None when the configuration has no row-wise counterpart (then the trainer stays on the dense optimiser)."""
+    def build(cls, model, optimizer_fn, optimizer_params, exclude=()):
+        """None when the configuration has no row-wise counterpart (then the trainer stays on the dense optimiser).
+        ``exclude``: ids of table weights that must stay on the dense side (tables replicated across ranks: their gradients are
+        all-reduced as dense tensors, so every rank has to apply the same dense update)."""
         from .table import FieldTable
         kind = _KINDS.get(optimizer_fn)
         if kind is None:
@@ -205,7 +207,7 @@ class HybridOptimizer(object):
             return None  # momentum / amsgrad / lr_decay ...: keep exact dense semantics
         tables = []
         for mod in model.modules():
-            if isinstance(mod, FieldTable) and mod.weight.is_cuda and mod.weight.requires_grad and mod.weight.dtype == torch.float32:
+            if isinstance(mod, FieldTable) and mod.weight.is_cuda and mod.weight.requires_grad and mod.weight.dtype == torch.float32 and id(mod.weight) not in exclude:
                 tables.append(mod.weight)
         if not tables:
             return None

@@ -102,7 +102,8 @@ class CTRTrainer(object):
         if self.device.type == "cuda":
             from ..b200 import config, optim
             if config.rowwise_optimizer:
-                hybrid = optim.HybridOptimizer.build(self.model, optimizer_fn, optimizer_params)
+                exclude = self._dist.replicated_ids if self._dist is not None else ()
+                hybrid = optim.HybridOptimizer.build(self.model, optimizer_fn, optimizer_params, exclude=exclude)
                 if hybrid is not None:
                     return hybrid
         return optimizer_fn([p for p in self.model.parameters() if p.numel() > 0], **optimizer_params)
