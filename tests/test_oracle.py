@@ -124,3 +124,40 @@ def test_ref_port_matches_live_reference():
         a.sum().backward()
         b.sum().backward()
         assert torch.equal(ref.embedding.embed_dict["C0"].weight.grad, port.tables[0].weight.grad)
+
+
+@pytest.mark.parametrize("seed,B,F,D,V,n_dense", [(1, 1, 2, 4, 7, 0), (2, 33, 9, 16, 50, 5), (3, 64, 3, 8, 11, 1), (4, 17, 26, 16, 23, 13)])
+def test_oracle_matches_package_cpu_route_on_fresh_inputs(seed, B, F, D, V, n_dense):
+    """Beyond the golden files: random shapes, seeded inputs — the oracle against this package's CPU route (itself bit-identical
+    to the live reference, tests/test_cpu_api.py) for DeepFM and DCN: logits and every parameter gradient."""
+    from torch_rechub.basic.features import DenseFeature, SparseFeature
+    from torch_rechub.basic.initializers import RandomNormal
+    from torch_rechub.models.ranking import DCN, DeepFM
+    torch.manual_seed(seed)
+    init = RandomNormal(0, 0.1)
+    dense = [DenseFeature("I%d" % i) for i in range(n_dense)]
+    sparse = [SparseFeature("C%d" % i, V, D, initializer=init) for i in range(F)]
+    g = torch.Generator().manual_seed(seed)
+    x = {"I%d" % i: torch.rand(B, generator=g) for i in range(n_dense)}
+    x.update({"C%d" % i: torch.randint(0, V, (B,), generator=g) for i in range(F)})
+    y = torch.randint(0, 2, (B,), generator=g).float()
+    xn, yn = {k: v.numpy() for k, v in x.items()}, y.numpy()
+    dn, sn = [f.name for f in dense], [f.name for f in sparse]
+    train = B > 1  # BatchNorm cannot take batch statistics of one row
+    cases = [(DeepFM(dense + sparse, sparse, {"dims": [12, 6], "dropout": 0.0, "activation": "relu"}), lambda sd: orc.deepfm_forward_backward(sd, xn, yn, dn, sn, sn, 2, train=train)),
+             (DCN(dense + sparse, n_cross_layers=2, mlp_params={"dims": [12, 6]}), lambda sd: orc.dcn_forward_backward(sd, xn, yn, dn, sn, 2, 2, train=train))]
+    for model, run in cases:
+        model.train(train)
+        p = model(x)
+        loss = torch.nn.BCELoss()(p, y)
+        model.zero_grad()
+        loss.backward()
+        out = run({k: v.detach().numpy() for k, v in model.state_dict().items()})
+        assert np.abs(out["prob"] - p.detach().numpy()).max() < 1e-6
+        assert abs(out["loss"] - float(loss)) < 1e-6
+        for k, prm in model.named_parameters():
+            ref = prm.grad.numpy()
+            scale = max(np.abs(ref).max(), 1e-3)
+            if k.endswith(".bias") and k[:-4] + "weight" in out["grads"]:
+                scale = max(scale, np.abs(dict(model.named_parameters())[k[:-4] + "weight"].grad.numpy()).max())
+            assert np.abs(np.asarray(out["grads"][k]).reshape(ref.shape) - ref).max() <= 5e-5 * scale, (type(model).__name__, k)
