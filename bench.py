@@ -145,7 +145,9 @@ def workload_config(parallelism, step="zero_grad + fwd + BCE + bwd (scatter-add 
 # -----------------------------------------------------------------------------------------------------------------
 # B200 arm
 # -----------------------------------------------------------------------------------------------------------------
-def build_model(device):
+def build_model(device, init_std=1e-4, mlp_params=None):
+    """The benchmarked DeepFM.  ``init_std`` / ``mlp_params`` let the parity tests build the SAME model with numerically
+    non-trivial tables (N(0, 0.05)) and dropout 0 (tests/test_gpu_fullshape.py)."""
     import torch
     from torch_rechub.basic.features import DenseFeature, SparseFeature
     from torch_rechub.models.ranking import DeepFM
@@ -158,9 +160,9 @@ def build_model(device):
         with torch.device(device):
             t = FieldTable(VOCAB, DIM)
         with torch.no_grad():
-            t.weight.normal_(0.0, 1e-4)
+            t.weight.normal_(0.0, init_std)
         f.embed = t
-    model = DeepFM(deep_features=dense + sparse, fm_features=sparse, mlp_params=dict(MLP_PARAMS))
+    model = DeepFM(deep_features=dense + sparse, fm_features=sparse, mlp_params=dict(MLP_PARAMS if mlp_params is None else mlp_params))
     return model.to(device), dense, sparse
 
 

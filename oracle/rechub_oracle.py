@@ -37,16 +37,84 @@ def embedding_lookup(weight, ids):
     return weight[idx]
 
 
+class CompactGrad(object):
+    """A dense (V, D) table gradient stored as its non-zero rows: ``ids`` (sorted, unique) and ``rows``.  Same numbers as the
+    dense form (``dense()``); used for full-size tables (26 x 1M x 16) where 52 dense float64 gradients would not fit the
+    "oracle finishes in seconds" budget.  Supports ``+`` with 0 and with another CompactGrad (two lookups of one table)."""
+
+    def __init__(self, shape, ids, rows):
+        self.shape, self.ids, self.rows = tuple(shape), ids, rows
+
+    def __add__(self, other):
+        if isinstance(other, (int, float)) and other == 0:
+            return self
+        ids = np.concatenate([self.ids, other.ids])
+        rows = np.concatenate([self.rows, other.rows])
+        u, inv = np.unique(ids, return_inverse=True)
+        out = np.zeros((len(u), self.shape[1]), dtype=rows.dtype)
+        np.add.at(out, inv, rows)
+        return CompactGrad(self.shape, u, out)
+
+    __radd__ = __add__
+
+    def dense(self):
+        g = np.zeros(self.shape, dtype=self.rows.dtype)
+        g[self.ids] = self.rows
+        return g
+
+
+COMPACT_TABLE_GRADS = False  # tests at full table size switch this on (see ``compact_table_grads``)
+
+
+class compact_table_grads(object):
+    """``with compact_table_grads():`` -> table gradients come back as :class:`CompactGrad` instead of dense arrays."""
+
+    def __enter__(self):
+        global COMPACT_TABLE_GRADS
+        self.prev, COMPACT_TABLE_GRADS = COMPACT_TABLE_GRADS, True
+
+    def __exit__(self, *a):
+        global COMPACT_TABLE_GRADS
+        COMPACT_TABLE_GRADS = self.prev
+
+
 def embedding_grad(weight_shape, ids, d_out, padding_idx=None, dtype=np.float64):
     """aten::embedding_dense_backward: dense (V, D) gradient, duplicates accumulate, padding row stays 0."""
-    g = np.zeros(weight_shape, dtype=dtype)
     idx = np.asarray(ids).astype(np.int64).reshape(-1)
-    d = d_out.reshape(-1, weight_shape[1])
+    d = np.asarray(d_out, dtype=dtype).reshape(-1, weight_shape[1])
     if padding_idx is not None:
         keep = idx != padding_idx
         idx, d = idx[keep], d[keep]
+    if COMPACT_TABLE_GRADS:
+        u, inv = np.unique(idx, return_inverse=True)
+        rows = np.zeros((len(u), weight_shape[1]), dtype=dtype)
+        np.add.at(rows, inv, d)
+        return CompactGrad(weight_shape, u, rows)
+    g = np.zeros(weight_shape, dtype=dtype)
     np.add.at(g, idx, d)
     return g
+
+
+def table_rows(sd, key, ids, dtype=np.float64):
+    """Rows ``ids`` of the table ``sd[key]`` in ``dtype``: the lookup first, the widening second (a 1M-row table is never
+    converted whole)."""
+    return _f(embedding_lookup(np.asarray(sd[key]), ids), dtype)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# optimiser step (trainers/ctr_trainer.py:60-61,99: ``optimizer_fn(params, lr=1e-3, weight_decay=1e-5)`` -> torch.optim.Adam)
+# ---------------------------------------------------------------------------------------------------------
+def adam_update(w, g, m, v, step, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0):
+    """One torch.optim.Adam step (L2 ``weight_decay`` added to the gradient, bias corrections by ``step`` >= 1) on arrays of any
+    shape; returns (w, m, v).  float64 throughout.  Applied to the rows a batch touched it restates the row-wise (lazy) mode:
+    untouched rows keep w, m, v while ``step`` is the global step count."""
+    g = g + weight_decay * w
+    m = beta1 * m + (1 - beta1) * g
+    v = beta2 * v + (1 - beta2) * g * g
+    bc1 = 1 - beta1**step
+    bc2 = 1 - beta2**step
+    w = w - (lr / bc1) * m / (np.sqrt(v) / np.sqrt(bc2) + eps)
+    return w, m, v
 
 
 def fm_forward(e, reduce_sum=True):
@@ -200,7 +268,7 @@ def bce_and_dlogit(logit, y):
 def embedding_tile(sd, x, sparse_names, dense_names, table_of=None, dtype=np.float64):
     """EmbeddingLayer.forward(squeeze_dim=True) (basic/layers.py:77-127): sparse block first (list order), dense appended."""
     table_of = table_of or {}
-    embs = [embedding_lookup(_f(sd["embedding.embed_dict.%s.weight" % table_of.get(n, n)], dtype), x[n]) for n in sparse_names]
+    embs = [table_rows(sd, "embedding.embed_dict.%s.weight" % table_of.get(n, n), x[n], dtype) for n in sparse_names]
     parts = [np.concatenate(embs, axis=1)] if embs else []
     dense = [_f(x[n], np.float32).astype(dtype).reshape(len(x[n]), -1) for n in dense_names]
     if dense:
@@ -216,7 +284,7 @@ def deepfm_forward_backward(sd, x, y, dense_names, deep_sparse_names, fm_names, 
     deep tile = [deep sparse embeddings..., dense values]; FM/LR over ``fm_names`` embeddings."""
     y = _f(y, dtype)
     tile, deep_embs = embedding_tile(sd, x, deep_sparse_names, dense_names, dtype=dtype)
-    e_fm = np.stack([embedding_lookup(_f(sd["embedding.embed_dict.%s.weight" % n], dtype), x[n]) for n in fm_names], axis=1)  # (B, F, D)
+    e_fm = np.stack([table_rows(sd, "embedding.embed_dict.%s.weight" % n, x[n], dtype) for n in fm_names], axis=1)  # (B, F, D)
     B, F, D = e_fm.shape
     lw, lb = _f(sd["linear.fc.weight"], dtype), _f(sd["linear.fc.bias"], dtype)
     y_lin = e_fm.reshape(B, F * D) @ lw.T + lb
@@ -425,10 +493,10 @@ def din_forward_backward(sd, x, y, feature_names, history_names, target_names, s
     """DIN.forward + ActivationUnit.forward (models/ranking/din.py:38-55, 77-93), Dice everywhere, no padding mask.
     ``shared_with[h]`` names the table a history feature looks up."""
     y = _f(y, dtype)
-    tbl = lambda n: _f(sd["embedding.embed_dict.%s.weight" % shared_with.get(n, n)], dtype)
-    e_feat = [embedding_lookup(tbl(n), x[n]) for n in feature_names]
-    e_hist = [embedding_lookup(tbl(n), x[n]) for n in history_names]  # (B, L, D) each
-    e_tgt = [embedding_lookup(tbl(n), x[n]) for n in target_names]
+    rows = lambda n: table_rows(sd, "embedding.embed_dict.%s.weight" % shared_with.get(n, n), x[n], dtype)
+    e_feat = [rows(n) for n in feature_names]
+    e_hist = [rows(n) for n in history_names]  # (B, L, D) each
+    e_tgt = [rows(n) for n in target_names]
     pooled, att_caches = [], []
     for i, h in enumerate(e_hist):
         B, L, D = h.shape
