@@ -68,6 +68,10 @@ int         rh_abi_version(void);
 const char* rh_last_error(void);
 /* Number of kernels this library has launched so far in this process (bench.py's gpu_launches). */
 unsigned long long rh_launch_count(void);
+/* L2 fetch granularity of the current device (cudaLimitMaxL2FetchGranularity): bytes L2 pulls from DRAM per sector miss.
+ * set_bytes > 0 sets it first (32 / 64 / 128); returns the value in force, < 0 on a CUDA error.  Random 64-byte embedding rows
+ * (basic/layers.py:83,85 lookups) cost twice their DRAM bytes at 128 — the engine's host side lowers it once per device. */
+int rh_l2_fetch_granularity(int set_bytes);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused multi-field gather (+ FM second-order term + LR first-order term + flattened tile).
@@ -305,6 +309,40 @@ int rh_bn_act_bwd(const float* h, int64_t h_ld, int64_t rows, int cols,
                   float* d_h, int64_t d_h_ld,
                   float* d_gamma, float* d_beta, float* d_act_param, void* stream);
 
+/* Training-mode BatchNorm1d + activation + dropout of one tower layer in ONE launch (rh_colstats + rh_bn_act_fwd fused): every
+ * CTA keeps its rows of h in registers across a grid-wide barrier (column sums published by atomics, then the apply).
+ * Replaces [BatchNorm1d -> activation -> Dropout] of MLP.forward (basic/layers.py:282-285), batch statistics included.
+ *   stats (2 cols + 1): mean | biased variance | step-counter bits (out; the backward's input, same layout as rh_colstats)
+ *   scratch: rh_bn_fused_scratch_floats(cols) floats, zeroed ONCE by the caller; the kernel leaves it zeroed
+ *   running_mean / running_var / num_batches_tracked: updated as nn.BatchNorm1d does (may be NULL)
+ *   head mode (head_w != NULL): the layer is the LAST hidden layer and the tower's output layer Linear(cols, 1) + side terms +
+ *   sigmoid (rh_head_fwd's arithmetic) consumes y in registers: head_out[r] = f(<y[r], head_w> + head_b + extra0[r] + extra1[r]);
+ *   y may then be NULL (the activation never reaches HBM).
+ * Shapes: rh_bn_fused_supported(rows, cols, head) != 0 (cols % 4 == 0, cols <= 512 (256 in head mode), rows <= SMs * 64 / ceil(cols/128)). */
+int64_t rh_bn_fused_scratch_floats(int cols);
+int rh_bn_fused_supported(int64_t rows, int cols, int head);
+int rh_bn_act_fused_fwd(const float* h, int64_t h_ld, int64_t rows, int cols, float bn_eps,
+                        const float* gamma, const float* beta, int act, const float* act_param, float dice_eps,
+                        float p_drop, uint32_t dropout_seed,
+                        float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum,
+                        float* stats, float* scratch, float* y, int64_t y_ld,
+                        const float* head_w, const float* head_b, const float* extra0, const float* extra1,
+                        int apply_sigmoid, float* head_out, void* stream);
+
+/* Backward of rh_bn_act_fused_fwd in ONE launch (both passes of rh_bn_act_bwd; in head mode also rh_head_bwd): d_h is final,
+ * d_gamma / d_beta / d_act_param (/ d_head_w (cols) / d_head_b (1)) are WRITTEN (no zeroing by the caller), d_extra (rows) or NULL
+ * receives the gradient of every side term, d_lin_bias (cols) or NULL is written with the gradient of the Linear bias in front of
+ * the BatchNorm (exactly 0: batch statistics remove any per-column shift).  Plain mode reads d_y (rows, cols); head mode reads d_head_out (rows) and the saved
+ * head_out (sigmoid derivative). */
+int rh_bn_act_fused_bwd(const float* h, int64_t h_ld, int64_t rows, int cols, const float* stats, float bn_eps,
+                        const float* gamma, const float* beta, int act, const float* act_param, float dice_eps,
+                        float p_drop, uint32_t dropout_seed,
+                        const float* d_y, int64_t d_y_ld,
+                        const float* head_w, const float* head_out, const float* d_head_out, int apply_sigmoid,
+                        float* scratch, float* d_h, int64_t d_h_ld,
+                        float* d_gamma, float* d_beta, float* d_act_param,
+                        float* d_head_w, float* d_head_b, float* d_extra, float* d_lin_bias, void* stream);
+
 /* Output head of a ranking tower in one pass: the MLP's output layer nn.Linear(k, 1) (reference basic/layers.py:279-280) fused
  * with the model's tail  sigmoid(y_deep + extra0 + extra1)  — DeepFM's  y_linear + y_fm + y_deep  (models/ranking/deepfm.py:41-43).
  *   x (rows, k) row stride x_ld;  w (k);  bias (1) or NULL;  extra0/extra1 (rows) or NULL;  out (rows)
@@ -355,6 +393,49 @@ int rh_gemm_tf32x3_stats(const float* A, int64_t lda, int a_mn_major,
                          float* stats, float* scratch,
                          float* running_mean, float* running_var, int64_t* num_batches_tracked,
                          float momentum, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * DCN-v2 cross networks: CrossNetMix (mixture of low-rank experts, basic/layers.py:447-506, forward at :470) and
+ * CrossNetV2 (basic/layers.py:423-444).  A CrossNetMix layer is three rh_gemm_tf32x3 products over PACKED operands
+ *     [A | G] = x_l Wcat^T      Wcat (E r + E, W): rows (e, j) = V_e[:, j] (v_list[l][e]), rows E r + e = gating[e].weight
+ *     P       = t1 Cbd^T        Cbd  (E r, E r)  : block diagonal of C_e (c_list[l][e])
+ *     u       = z Ucat^T        Ucat (W, E r)    : [w, (e, j)] = U_e[w, j] (u_list[l][e])
+ * joined by the maps below; CrossNetV2 is one product per layer + rh_crossmix_out_fwd.  All matrices row-major fp32.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Packed operands of ALL layers in one launch.  u/v/c/wcat/cbd/ucat: host arrays of n_layers device pointers
+ * (u, v: (E, W, r); c: (E, r, r)); gate: host array of n_experts device pointers ((W) each, shared by all layers, :466);
+ * wcat rows have stride ld_w >= W (columns >= W are zero-filled).  n_layers <= 8, n_experts <= 8. */
+int rh_crossmix_pack(int n_layers, int n_experts, int width, int rank,
+                     const float* const* u, const float* const* v, const float* const* c, const float* const* gate,
+                     float* const* wcat, int64_t ld_w, float* const* cbd, float* const* ucat, void* stream);
+/* The reverse for the gradients: d_u/d_v/d_c in the reference's parameter layout from the packed d_ucat / d_wcat / d_cbd
+ * (only the diagonal blocks of d_cbd are read); d_gate[e] (W) = sum over layers of d_wcat[l][E r + e, :] (written). */
+int rh_crossmix_unpack_grads(int n_layers, int n_experts, int width, int rank,
+                             const float* const* d_wcat, int64_t ld_dw, const float* const* d_cbd, int64_t ld_dc,
+                             const float* const* d_ucat, int64_t ld_du,
+                             float* const* d_u, float* const* d_v, float* const* d_c, float* const* d_gate, void* stream);
+/* t1 (batch, E r) = tanh(ag[:, :E r]);  s (batch, E) = softmax(ag[:, E r : E r + E])      (layers.py:486-488,496-498) */
+int rh_crossmix_mid1_fwd(const float* ag, int64_t ld_ag, int64_t batch, int n_experts, int rank, float* t1, float* s, void* stream);
+/* t2 (batch, E r) = tanh(P);  z[:, (e, j)] = s[:, e] * t2[:, (e, j)]                      (layers.py:489-490,502) */
+int rh_crossmix_mid2_fwd(const float* P, const float* s, int64_t batch, int n_experts, int rank, float* t2, float* z, void* stream);
+/* out = x0 * (u + bias) + xl  — the cross step of CrossNetMix (:494,503) and CrossNetV2 (:443);  bias (width) or NULL */
+int rh_crossmix_out_fwd(const float* x0, int64_t ld0, const float* xl, int64_t ldl, const float* u, int64_t ldu, const float* bias,
+                        int64_t batch, int width, float* out, int64_t ldo, void* stream);
+/* Backward of the cross step for an incoming gradient g = g1 (+ g2, may be NULL):  g_sum = g (or NULL);  d_u = g * x0;
+ * d_x0_acc += g * (u + bias);  d_bias (width, zeroed by the caller, or NULL) += column sums of d_u. */
+int rh_crossmix_out_bwd(const float* g1, int64_t ldg1, const float* g2, int64_t ldg2, const float* x0, int64_t ld0,
+                        const float* u, int64_t ldu, const float* bias, int64_t batch, int width,
+                        float* g_sum, int64_t ldgs, float* d_u, int64_t lddu, float* d_x0_acc, int64_t ldx, float* d_bias, void* stream);
+/* d_P = d_z * s_e * (1 - t2^2);  d_ag[:, E r + e] = softmax backward of d_s_e = sum_j d_z[(e, j)] t2[(e, j)] */
+int rh_crossmix_mid2_bwd(const float* d_z, int64_t ld_dz, const float* s, const float* t2, int64_t batch, int n_experts, int rank,
+                         float* d_P, float* d_ag, int64_t ld_dag, void* stream);
+/* d_ag[:, :E r] = d_t1 * (1 - t1^2) */
+int rh_crossmix_mid1_bwd(const float* d_t1, int64_t ld_dt1, const float* t1, int64_t batch, int n_experts, int rank,
+                         float* d_ag, int64_t ld_dag, void* stream);
+/* out = a + b + c over (rows, cols) views with their own row strides (b, c may be NULL) */
+int rh_sum3(const float* a, int64_t lda, const float* b, int64_t ldb, const float* c, int64_t ldc, int64_t rows, int cols,
+            float* out, int64_t ldo, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * DIN target attention (models/ranking/din.py:77-93, ActivationUnit.forward).

@@ -32,6 +32,8 @@ def _make(kind):
     sparse = [SparseFeature("C%d" % i, 31 + i, 8, initializer=init) for i in range(5)]
     if kind == "deepfm":
         return DeepFM(dense + sparse, sparse, {"dims": [16, 8], "dropout": 0.0, "activation": "relu"})
+    if kind == "dcn_one_table":  # fewer tables than ranks: rank 1 owns nothing, its exchange backward must still run
+        return DCN(dense + sparse[:1], n_cross_layers=2, mlp_params={"dims": [16, 8]})
     if kind == "din":  # sequence features: the layer stays replicated (data parallel), SURVEY §8e
         from torch_rechub.basic.features import SequenceFeature
         from torch_rechub.models.ranking import DIN
@@ -63,6 +65,9 @@ def _worker(rank, world, port, kind, out):
     assert trainer._dist is not None and trainer._dist.world == world
     if kind == "din":
         assert not trainer._dist.fronts and len(trainer._dist.replicated_ids) == 2 and not trainer._dist.foreign
+    elif kind == "dcn_one_table":
+        n_owned = sum(1 for f in trainer._dist.fronts for n, o in f.owner.items() if o == rank)
+        assert n_owned == (1 if rank == 0 else 0)
     else:
         n_owned = sum(1 for f in trainer._dist.fronts for n, o in f.owner.items() if o == rank)
         assert n_owned in (2, 3) and len(trainer._dist.foreign) == 5 - n_owned
@@ -75,7 +80,7 @@ def _worker(rank, world, port, kind, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kind", ["deepfm", "dcn", "din"])
+@pytest.mark.parametrize("kind", ["deepfm", "dcn", "din", "dcn_one_table"])
 def test_two_rank_sharded_step_matches_dataparallel_semantics(kind):
     world = 2
     out = mp.get_context("spawn").Manager().dict()

@@ -66,12 +66,6 @@ def test_is_more_accurate_than_tf32_and_matches_fp32_level():
     assert e3 < 4 * e32 + 1e-5, (e3, e32)  # same order as cuBLAS fp32; TF32 alone would be ~1e-2 here
 
 
-def _colstats_enabled():
-    from torch_rechub.b200 import config
-    return bool(config.gemm_colstats)
-
-
-@pytest.mark.skipif(not _colstats_enabled(), reason="rh_gemm_tf32x3_stats awaits its first GPU session: run with RECHUB_B200_GEMM_COLSTATS=1")
 @pytest.mark.parametrize("M,N,K,bias", [(4096, 256, 429, True), (4096, 128, 256, True), (300, 72, 52, True), (129, 36, 32, False), (1000, 260, 64, True), (128, 128, 32, True)])
 def test_gemm_with_column_statistics_epilogue(M, N, K, bias):
     """GEMM + BatchNorm training statistics in one launch vs fp64: C, mean, biased variance, running statistics, step counter;
@@ -114,7 +108,6 @@ def test_gemm_with_column_statistics_epilogue(M, N, K, bias):
         assert int(scratch[-((N + 127) // 128):].view(torch.int32).abs().max()) == 0  # tickets back to zero
 
 
-@pytest.mark.skipif(not _colstats_enabled(), reason="rh_gemm_tf32x3_stats awaits its first GPU session: run with RECHUB_B200_GEMM_COLSTATS=1")
 def test_tower_with_fused_statistics_matches_cpu_route():
     import copy
     from torch_rechub.basic.layers import MLP

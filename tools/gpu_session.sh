@@ -6,10 +6,8 @@ set -u
 mkdir -p gpurun_out
 run() { echo "=== $*"; "$@"; echo "=== rc=$?"; }
 run timeout 300 python -m pytest tests -m gpu -q --timeout 120 -p no:cacheprovider
-run env RECHUB_B200_GEMM_COLSTATS=1 timeout 200 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_parity.py tests/test_gpu_golden.py -m gpu -q --timeout 120 -p no:cacheprovider
-run env RECHUB_B200_FUSED_HEAD_ALL=1 RECHUB_B200_BATCHED_CROSSMIX=1 timeout 200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_golden.py -m gpu -q --timeout 120 -p no:cacheprovider
+run env RECHUB_B200_FUSED_HEAD_ALL=1 timeout 200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_golden.py -m gpu -q --timeout 120 -p no:cacheprovider
 run timeout 200 python bench.py --no-cpu-baseline
-run env RECHUB_B200_GEMM_COLSTATS=1 timeout 200 python bench.py --no-cpu-baseline
 run env RECHUB_B200_NEXT_BATCH_PREFETCH=1 timeout 200 python bench.py --no-cpu-baseline
 run timeout 200 python bench.py --no-cpu-baseline --ids zipf
 run timeout 120 python tools/kernel_times.py

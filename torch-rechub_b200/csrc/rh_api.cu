@@ -18,3 +18,26 @@ void set_error(const char* fmt, ...) {
 extern "C" int rh_abi_version(void) { return RH_ABI_VERSION; }
 extern "C" const char* rh_last_error(void) { return rh::g_err; }
 extern "C" unsigned long long rh_launch_count(void) { return rh::g_launches; }
+
+// cudaLimitMaxL2FetchGranularity of the current device: how many bytes L2 pulls from DRAM on a sector miss (32 / 64 / 128).
+// Random 64-byte table rows are the engine's dominant access: at 128 bytes every row costs a second, never-used sector pair
+// (measured with tools/microbench_gather.cu + ncu: 14.4 MB read for 7.7 MB of rows + ids at 128, 7.7 MB at 64 and at 32).
+// `set_bytes` > 0 sets the limit first (a driver hint; the value in force is returned either way, negative on a CUDA error).
+extern "C" int rh_l2_fetch_granularity(int set_bytes) {
+  if (set_bytes > 0) {
+    cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)set_bytes);
+    if (e != cudaSuccess) {
+      rh::set_error("cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, %d): %s", set_bytes, cudaGetErrorString(e));
+      cudaGetLastError();
+      return -1;
+    }
+  }
+  size_t v = 0;
+  cudaError_t e = cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity);
+  if (e != cudaSuccess) {
+    rh::set_error("cudaDeviceGetLimit(cudaLimitMaxL2FetchGranularity): %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return -1;
+  }
+  return (int)v;
+}

@@ -124,7 +124,21 @@ struct GemmP {
   float* running_var;
   long long* num_batches_tracked;
   float momentum;
+#ifdef RH_GEMM_TRACE
+  unsigned long long* trace;  // tools/gemm_trace.cu: [cta][16] clock64 stamps of the pipeline's milestones
+#endif
 };
+
+#ifdef RH_GEMM_TRACE
+#define RH_TR(ev)                                                                                                              \
+  do {                                                                                                                         \
+    if (p.trace != nullptr) p.trace[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (ev)] = clock64(); \
+  } while (0)
+#else
+#define RH_TR(ev) \
+  do {            \
+  } while (0)
+#endif
 
 // Transpose-reduce across a warp: every lane holds 32 values v[j]; afterwards lane j holds sum over lanes of v[j] in v[0].
 // 31 shuffles (16 + 8 + 4 + 2 + 1) instead of 32 x 5 for column-wise warp sums.
@@ -175,6 +189,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   int kb1 = kb0 + p.kblocks_per_split;
   if (kb1 > total_kb) kb1 = total_kb;
   const int n_iter = kb1 - kb0;  // >= 1 by construction of the grid
+  if (threadIdx.x == 0) RH_TR(0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -193,6 +208,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) RH_TR(1);
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -214,6 +230,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         } else {
           tma_load_2d(st + kTileBytes, &map_b, &full[s], k0, n0);
         }
+        if (it == 0) RH_TR(2);
+        if (it == n_iter - 1) RH_TR(3);
       }
     }
   } else if (warp == 1) {
@@ -228,6 +246,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       mbar_wait(&ready[s], ph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (lane == 0) {
+        if (it == 0) RH_TR(6);
         const uint32_t base = smem_u32(smem + (size_t)s * kStageBytes);
         const uint64_t a_hi = make_desc(base, p.a_mn != 0), b_hi = make_desc(base + kTileBytes, p.b_mn != 0);
         const uint64_t a_lo = make_desc(base + 2 * kTileBytes, p.a_mn != 0), b_lo = make_desc(base + 3 * kTileBytes, p.b_mn != 0);
@@ -244,6 +263,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         }
         umma_commit(&empty[s]);                       // stage free once these MMAs have read it
         if (it == n_iter - 1) umma_commit(tmem_full);  // accumulator complete
+        if (it == n_iter - 1) RH_TR(7);
       }
       __syncwarp();
     }
@@ -254,6 +274,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       const int s = it % kStages;
       const uint32_t ph = (it / kStages) & 1;
       mbar_wait(&full[s], ph);
+      if (t == 0 && it == 0) RH_TR(4);
       uint8_t* st = smem + (size_t)s * kStageBytes;
       for (int i = t; i < 2 * kTileBytes / 16; i += kSplitWarps * 32) {
         float4* src = reinterpret_cast<float4*>(st + (size_t)i * 16);
@@ -272,12 +293,15 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor-core (async) proxy
       __syncwarp();
       if (lane == 0) mbar_arrive(&ready[s]);
+      if (t == 0 && it == 0) RH_TR(5);
+      if (t == 0 && it == n_iter - 1) RH_TR(8);
     }
     // ===== epilogue (warps 4..7 own TMEM lane quadrants 0..3) =====
     if (warp >= 4) {
       const int q = warp - 4;
       mbar_wait(tmem_full, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (q == 0 && lane == 0) RH_TR(9);
       const int m = m0 + q * 32 + lane;
       const bool add_bias = p.bias != nullptr && blockIdx.z == 0;
       const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15u) == 0);
@@ -347,6 +371,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           }
         }
       }
+      if (q == 0 && lane == 0) RH_TR(10);
       if constexpr (STATS) {
         // ---- the four epilogue warps merge their row groups, publish the tile's (mean, M2) per column, and the last m-tile of
         // ---- this column block merges all tiles in a fixed order (deterministic) and finalises BatchNorm's statistics
@@ -412,6 +437,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (threadIdx.x == 0) RH_TR(11);
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
@@ -473,6 +499,10 @@ struct StatsArgs {
   float momentum;
 };
 
+#ifdef RH_GEMM_TRACE
+unsigned long long* g_gemm_trace = nullptr;  // set by tools/gemm_trace.cu
+#endif
+
 static int gemm_impl(const float* A, int64_t lda, int a_mn_major, const float* B, int64_t ldb, int b_mn_major, float* C, int64_t ldc, int M, int N,
                      int K, const float* bias, int split_k, void* stream, const StatsArgs* st) {
   RH_REQUIRE(A && B && C, RH_ERR_INVALID_ARG, "rh_gemm_tf32x3: NULL pointer");
@@ -505,6 +535,9 @@ static int gemm_impl(const float* A, int64_t lda, int a_mn_major, const float* B
   p.b_mn = b_mn_major != 0;
   p.kblocks_per_split = per;
   p.reduce = split_k > 1 ? 1 : 0;
+#ifdef RH_GEMM_TRACE
+  p.trace = g_gemm_trace;
+#endif
   dim3 grid((M + kBM - 1) / kBM, (N + kBN - 1) / kBN, split_k);
 
   static bool configured[2] = {false, false};

@@ -35,6 +35,7 @@ PROTOTYPES = {
     "rh_abi_version": [],
     "rh_last_error": [],
     "rh_launch_count": [],
+    "rh_l2_fetch_granularity": [c_i],
     "rh_fields_fwd": [c_p, c_i, c_i, c_p, c_i, c_i, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "rh_fields_fwd_p2p": [c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_i64, c_p, c_p],
     "rh_ids_scatter": [c_p, c_i, c_p, c_i, c_p, c_i, c_i, c_i64, c_i64, c_p],
@@ -58,18 +59,31 @@ PROTOTYPES = {
     "rh_colstats": [c_p, c_i64, c_i64, c_i, c_p, c_p, c_p, c_p, c_p, c_f, c_p],
     "rh_bn_act_fwd": [c_p, c_i64, c_i64, c_i, c_p, c_p, c_f, c_p, c_p, c_i, c_p, c_f, c_f, ctypes.c_uint32, c_p, c_p, c_i64, c_p],
     "rh_bn_act_bwd": [c_p, c_i64, c_i64, c_i, c_p, c_p, c_f, c_p, c_p, c_i, c_p, c_f, c_f, ctypes.c_uint32, c_p, c_p, c_i64, c_i, c_p, c_i64, c_p, c_p, c_p, c_p],
+    "rh_bn_fused_scratch_floats": [c_i],
+    "rh_bn_fused_supported": [c_i64, c_i, c_i],
+    "rh_bn_act_fused_fwd": [c_p, c_i64, c_i64, c_i, c_f, c_p, c_p, c_i, c_p, c_f, c_f, ctypes.c_uint32, c_p, c_p, c_p, c_f, c_p, c_p, c_p, c_i64, c_p, c_p, c_p, c_p, c_i, c_p, c_p],
+    "rh_bn_act_fused_bwd": [c_p, c_i64, c_i64, c_i, c_p, c_f, c_p, c_p, c_i, c_p, c_f, c_f, ctypes.c_uint32, c_p, c_i64, c_p, c_p, c_p, c_i, c_p, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "rh_head_fwd": [c_p, c_i64, c_i64, c_i, c_p, c_p, c_p, c_p, c_i, c_p, c_p],
     "rh_head_bwd": [c_p, c_i64, c_i64, c_i, c_p, c_p, c_p, c_i, c_p, c_i64, c_p, c_p, c_p, c_p],
     "rh_dense_update": [c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_f, c_f, c_f, c_f, c_p],
     "rh_gemm_tf32x3": [c_p, c_i64, c_i, c_p, c_i64, c_i, c_p, c_i64, c_i, c_i, c_i, c_p, c_i, c_p],
     "rh_gemm_stats_scratch_floats": [c_i, c_i],
     "rh_gemm_tf32x3_stats": [c_p, c_i64, c_i, c_p, c_i64, c_i, c_p, c_i64, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_f, c_p],
+    "rh_crossmix_pack": [c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_p, c_p],
+    "rh_crossmix_unpack_grads": [c_i, c_i, c_i, c_i, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_p, c_p, c_p, c_p],
+    "rh_crossmix_mid1_fwd": [c_p, c_i64, c_i64, c_i, c_i, c_p, c_p, c_p],
+    "rh_crossmix_mid2_fwd": [c_p, c_p, c_i64, c_i, c_i, c_p, c_p, c_p],
+    "rh_crossmix_out_fwd": [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_i, c_p, c_i64, c_p],
+    "rh_crossmix_out_bwd": [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_i, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_p],
+    "rh_crossmix_mid2_bwd": [c_p, c_i64, c_p, c_p, c_i64, c_i, c_i, c_p, c_p, c_i64, c_p],
+    "rh_crossmix_mid1_bwd": [c_p, c_i64, c_p, c_i64, c_i, c_i, c_p, c_i64, c_p],
+    "rh_sum3": [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_i64, c_i, c_p, c_i64, c_p],
     "rh_din_attn_input_fwd": [c_p, c_i, c_p, c_i, c_i, c_p, c_p, c_i, c_i64, c_i, c_i, c_p, c_p, c_p, c_p, c_p],
     "rh_din_weighted_sum_fwd": [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p],
     "rh_din_weighted_sum_bwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p],
     "rh_din_attn_input_bwd": [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_p, c_i, c_i64, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
 }
-_RESTYPES = {"rh_last_error": ctypes.c_char_p, "rh_launch_count": ctypes.c_ulonglong, "rh_gemm_stats_scratch_floats": ctypes.c_int64}
+_RESTYPES = {"rh_last_error": ctypes.c_char_p, "rh_launch_count": ctypes.c_ulonglong, "rh_gemm_stats_scratch_floats": ctypes.c_int64, "rh_bn_fused_scratch_floats": ctypes.c_int64}
 
 _lock = threading.Lock()
 _lib = None
@@ -125,6 +139,20 @@ def ptr(t):
 
 # ---- out-of-range id flag --------------------------------------------------------------------------
 _err_flags = {}
+l2_fetch_granularity_seen = {}  # device index -> (bytes in force before the engine touched it, bytes in force now)
+
+
+def _device_init(key):
+    """Once per device, at the engine's first use of it: lower the L2 fetch granularity (config.l2_fetch_granularity; 0 = leave)."""
+    from . import config
+    L = lib()
+    with torch.cuda.device(key):
+        before = int(L.rh_l2_fetch_granularity(0))
+        now = before
+        want = int(config.l2_fetch_granularity)
+        if want > 0 and before > 0 and want != before:
+            now = int(L.rh_l2_fetch_granularity(want))
+    l2_fetch_granularity_seen[key] = (before, now)
 
 
 def err_flag(device):
@@ -132,6 +160,7 @@ def err_flag(device):
     key = device.index if device.index is not None else torch.cuda.current_device()
     t = _err_flags.get(key)
     if t is None:
+        _device_init(key)
         t = torch.zeros(1, dtype=torch.int32, device=device)
         _err_flags[key] = t
     return t

@@ -60,21 +60,23 @@ concurrent_optimizers = _flag("RECHUB_B200_CONCURRENT_OPT", False)  # measured: 
 # Output head (Linear(K,1) + side terms + sigmoid) as one launch each way (rh_head_fwd/bwd) instead of ~10 library launches.
 fused_head = _flag("RECHUB_B200_FUSED_HEAD", True)
 
-# Tower forward: BatchNorm's training-mode column statistics computed in the GEMM epilogue (rh_gemm_tf32x3_stats) instead of a
-# separate rh_colstats pass over the activation.  Off until its GPU validation (tests/test_gpu_gemm.py, gated on this flag).
-gemm_colstats = _flag("RECHUB_B200_GEMM_COLSTATS", False)
-
 # The same head for the other ranking models (DCN / DCNv2: LR over [cross | deep]; WideDeep: wide term + deep head; DIN: the final
 # tower).  Off until its GPU validation: run the GPU suite with RECHUB_B200_FUSED_HEAD_ALL=1.
 fused_head_all = _flag("RECHUB_B200_FUSED_HEAD_ALL", False)
 
-# CrossNetMix (DCN-v2) with the experts batched into three GEMMs per layer instead of a Python loop over experts
-# (basic/layers.py::CrossNetMix._forward_batched; same algebra, ~20x fewer launches).
-batched_crossmix = _flag("RECHUB_B200_BATCHED_CROSSMIX", False)  # CPU-verified against the loop; first GPU run pending -> opt-in
-
 # Pipelined loop: prefetch into L2 the table / gradient / optimiser rows the NEXT batch will touch (rh_fields_prefetch on the copy
 # stream, one step ahead).  Written after the round's last GPU session -> off until measured.
 next_batch_prefetch = _flag("RECHUB_B200_NEXT_BATCH_PREFETCH", False)
+
+# Training-mode BatchNorm + activation + dropout of a tower layer as ONE launch each way (rh_bn_act_fused_fwd/_bwd: rows in
+# registers across a grid barrier) instead of rh_colstats + rh_bn_act_fwd and the two passes of rh_bn_act_bwd ...
+fused_bn = _flag("RECHUB_B200_FUSED_BN", True)
+# ... and the last hidden layer's fused launch also does the tower's output layer + side terms + sigmoid (DeepFM / DIN heads).
+fused_bn_head = _flag("RECHUB_B200_FUSED_BN_HEAD", True)
+
+# cudaLimitMaxL2FetchGranularity the engine sets on every device it touches (bytes; 0 = leave the process default).  Random 64-byte
+# table rows are the dominant DRAM access: measured DRAM reads per 106 k-row gather: 14.4 MB at 128, 7.7 MB (= algorithmic) at 64 / 32.
+l2_fetch_granularity = int(os.environ.get("RECHUB_B200_L2_FETCH_GRANULARITY", "32"))
 
 # Set by the graph runner while inputs live in static buffers that the next batch overwrites.
 static_inputs = False

@@ -27,10 +27,12 @@ def field_owners(names, world):
 
 
 class _AllToAllRows(torch.autograd.Function):
-    """out[s] = what rank s sent me; equal splits.  x: (world, rows, width) -> (world, rows, width).  Backward = the same exchange."""
+    """out[s] = what rank s sent me; equal splits.  x: (world, rows, width) -> (world, rows, width).  Backward = the same exchange.
+    ``anchor`` is a requires-grad scalar that makes autograd run this backward on EVERY rank — also on a rank that owns no
+    trainable table (its ``x`` carries no gradient), which would otherwise skip the collective the other ranks are waiting in."""
 
     @staticmethod
-    def forward(ctx, x, group):
+    def forward(ctx, x, group, anchor):
         ctx.group = group
         x = x.contiguous()
         out = torch.empty_like(x)
@@ -42,7 +44,7 @@ class _AllToAllRows(torch.autograd.Function):
         g = g.contiguous()
         out = torch.empty_like(g)
         dist.all_to_all_single(out, g, group=ctx.group)
-        return out, None
+        return out, None, None
 
 
 class P2PExchange(object):
@@ -95,7 +97,7 @@ class _ShardedP2P(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, front, p, x, fm_features, lr_w, lr_b, *owned_weights):
+    def forward(ctx, front, p, x, fm_features, lr_w, lr_b, anchor, *owned_weights):
         from . import _lib, ops, table as _table
         L = _lib.lib()
         ex, W, me = p["ex"], front.world, front.rank
@@ -229,7 +231,7 @@ class _ShardedP2P(torch.autograd.Function):
                 g, slot = _table.grad_target(r.weight)
                 if g is not None:
                     _table.note_dirty(slot, _snapshot(front, r.ids))
-            return (None, None, None, None, d_lrw, d_lrb) + (None,) * len(ctx.orefs)
+            return (None, None, None, None, d_lrw, d_lrb, None) + (None,) * len(ctx.orefs)
         # B3: the owner scatter-adds what every rank sent into its tables
         if ctx.orefs:
             targets = [_table.grad_target(r.weight) for r in ctx.orefs]
@@ -240,7 +242,7 @@ class _ShardedP2P(torch.autograd.Function):
                 if g is not None:
                     _table.note_dirty(slot, _snapshot(front, r.ids))
         ex.drows.zero_()  # ready for the next step's REDs: they can only start after the next forward's two barriers
-        return (None, None, None, None, d_lrw, d_lrb) + (None,) * len(ctx.orefs)
+        return (None, None, None, None, d_lrw, d_lrb, None) + (None,) * len(ctx.orefs)
 
 
 class ShardedFront(object):
@@ -275,6 +277,14 @@ class ShardedFront(object):
 
     def owner_of(self, fea):
         return self.owner[fea.name if fea.shared_with is None else fea.shared_with]
+
+    def _anchor(self):
+        """A requires-grad scalar handed to the exchange Functions so that their backward (barriers, REDs, collectives) runs on
+        every rank, also on one that owns no trainable table and passes no LR weights (fewer tables than ranks, frozen tables)."""
+        a = getattr(self, "_anchor_t", None)
+        if a is None:
+            a = self._anchor_t = torch.zeros((), dtype=torch.float32, device=self.device, requires_grad=True)
+        return a
 
     def _plan(self, features, batch):
         key = (tuple(id(f) for f in features), batch)
@@ -339,7 +349,7 @@ class ShardedFront(object):
                 p["ex"] = P2PExchange(self.group, self.device, W, b, fmax, dim, with_drows=self.direct is None)
             mine = p["by_owner"][self.rank]
             owned = [self.layer.table_of(f).weight for f in mine]
-            return _ShardedP2P.apply(self, p, x, fm_features, lr[0] if lr else None, lr[1] if lr else None, *owned)
+            return _ShardedP2P.apply(self, p, x, fm_features, lr[0] if lr else None, lr[1] if lr else None, self._anchor(), *owned)
         send = self._pack_ids(x, p, b)
         recv = torch.empty_like(send)
         dist.all_to_all_single(recv, send, group=self.group)  # recv[s, k, i] = id of sample i of rank s for my k-th field
@@ -359,7 +369,7 @@ class ShardedFront(object):
             rows = self.layer._forward_local(xg, mine, squeeze_dim=True) if mine else torch.zeros((W * b, 0))
             if len(mine) < fmax:
                 rows = torch.nn.functional.pad(rows, (0, (fmax - len(mine)) * dim))
-        got = _AllToAllRows.apply(rows.view(W, b, fmax * dim), self.group)  # got[r] = rank r's fields for MY samples
+        got = _AllToAllRows.apply(rows.view(W, b, fmax * dim), self.group, self._anchor())  # got[r] = rank r's fields for MY samples
         if cuda:
             from . import ops
             table = got.view(W * b * fmax, dim)

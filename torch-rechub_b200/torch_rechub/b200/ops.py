@@ -397,6 +397,206 @@ def cross_network(x, weights, biases):
 
 
 # =====================================================================================================
+# DCN-v2 cross networks: CrossNetMix (low-rank mixture of experts) and CrossNetV2 (full rank)
+# =====================================================================================================
+def _buf(rows, cols, dev, zero=False):
+    """(rows, cols) fp32 view of a buffer whose row stride is a multiple of 4 floats (TMA / 16-byte rows)."""
+    ld = _pad4(cols)
+    t = (torch.zeros if zero else torch.empty)((rows, ld), dtype=torch.float32, device=dev)
+    return t if ld == cols else t[:, :cols]
+
+
+def _padded_rows(x):
+    """x as a (rows, cols) fp32 view with unit inner stride, 16-byte aligned rows (copy only when the layout forces it)."""
+    x2 = _rowmajor(x if x.dtype == torch.float32 else x.float())
+    if x2.stride(0) % 4 != 0 or x2.data_ptr() % 16 != 0:
+        b = _buf(x2.shape[0], x2.shape[1], x2.device)
+        b.copy_(x2)
+        x2 = b
+    return x2
+
+
+def _mm(A, a_mn, Bm, b_mn, M, N, K, tc, split_k=1):
+    """C[M, N] = op(A) op(B)^T: rh_gemm_tf32x3 on the tensor cores when ``tc``, else the library GEMM on the same views (thin
+    shapes: fewer than 128 rows or an operand narrower than one 32-float TMA box)."""
+    out = _buf(M, N, A.device, zero=bool(tc and split_k > 1))
+    if tc:
+        gemm3x(A, a_mn, Bm, b_mn, M, N, K, split_k=split_k, out=out)
+    else:
+        Al = A.t() if a_mn else A
+        Bl = Bm.t() if b_mn else Bm
+        out.copy_(Al[:M, :K] @ Bl[:N, :K].t())
+    return out
+
+
+def _ptrs_of(tensors):
+    arr = (ctypes.c_void_p * max(len(tensors), 1))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+class _CrossMix(torch.autograd.Function):
+    """All layers of CrossNetMix (basic/layers.py:470-506) on the packed operands of rh_crossmix_pack: per layer three GEMMs
+    (rh_gemm_tf32x3) + rh_crossmix_mid1_fwd / _mid2_fwd / _out_fwd; backward: six GEMMs + three maps per layer, then
+    rh_crossmix_unpack_grads.  ``params``: u_list (L), v_list (L), c_list (L), gating weights (E), bias (L)."""
+
+    @staticmethod
+    def forward(ctx, x, L_, E, *params):
+        lib = _lib.lib()
+        st = stream_ptr()
+        us, vs, cs = params[:L_], params[L_:2 * L_], params[2 * L_:3 * L_]
+        gates, biases = params[3 * L_:3 * L_ + E], params[3 * L_ + E:]
+        x0 = _padded_rows(x)
+        B, W = x0.shape
+        dev = x0.device
+        r = vs[0].shape[2]
+        Er, N1 = E * r, E * r + E
+        ldw = _pad4(W)
+        wcat = [torch.empty((N1, ldw), dtype=torch.float32, device=dev) for _ in range(L_)]
+        cbd = [torch.empty((Er, Er), dtype=torch.float32, device=dev) for _ in range(L_)]
+        ucat = [torch.empty((W, Er), dtype=torch.float32, device=dev) for _ in range(L_)]
+        uc, vc, cc = [t.contiguous() for t in us], [t.contiguous() for t in vs], [t.contiguous() for t in cs]
+        gc = [g.contiguous() for g in gates]
+        check(lib.rh_crossmix_pack(L_, E, W, r, _ptrs_of(uc), _ptrs_of(vc), _ptrs_of(cc), _ptrs_of(gc), _ptrs_of(wcat), ldw, _ptrs_of(cbd), _ptrs_of(ucat), st), "rh_crossmix_pack")
+        tc = B >= 128 and min(W, Er) >= 32 and Er % 4 == 0 and N1 % 4 == 0 and _tc_ok(B, x0)
+        saved = []
+        xl = x0
+        for l in range(L_):
+            ag = _mm(xl, False, wcat[l][:, :W], False, B, N1, W, tc)
+            t1 = torch.empty((B, Er), dtype=torch.float32, device=dev)
+            s_ = torch.empty((B, E), dtype=torch.float32, device=dev)
+            check(lib.rh_crossmix_mid1_fwd(ag.data_ptr(), ag.stride(0), B, E, r, t1.data_ptr(), s_.data_ptr(), st), "rh_crossmix_mid1_fwd")
+            P = _mm(t1, False, cbd[l], False, B, Er, Er, tc)
+            if P.stride(0) != Er:
+                P = P.contiguous()
+            t2 = torch.empty((B, Er), dtype=torch.float32, device=dev)
+            z = torch.empty((B, Er), dtype=torch.float32, device=dev)
+            check(lib.rh_crossmix_mid2_fwd(P.data_ptr(), s_.data_ptr(), B, E, r, t2.data_ptr(), z.data_ptr(), st), "rh_crossmix_mid2_fwd")
+            u = _mm(z, False, ucat[l], False, B, W, Er, tc)
+            bl = biases[l].contiguous()
+            nxt = _buf(B, W, dev)
+            check(lib.rh_crossmix_out_fwd(x0.data_ptr(), x0.stride(0), xl.data_ptr(), xl.stride(0), u.data_ptr(), u.stride(0), bl.data_ptr(), B, W, nxt.data_ptr(), nxt.stride(0), st), "rh_crossmix_out_fwd")
+            saved.append((xl, t1, s_, t2, z, u, bl))
+            xl = nxt
+        ctx.saved_layers = saved
+        ctx.packed = (wcat, cbd, ucat)
+        ctx.meta = (L_, E, r, W, B, tc)
+        ctx.shapes = ([t.shape for t in us], [t.shape for t in cs], [g.shape for g in gates], [b.shape for b in biases])
+        ctx.x0 = x0
+        return xl
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.lib()
+        st = stream_ptr()
+        L_, E, r, W, B, tc = ctx.meta
+        wcat, cbd, ucat = ctx.packed
+        x0 = ctx.x0
+        dev = x0.device
+        Er, N1 = E * r, E * r + E
+        g1 = _padded_rows(d_out)
+        g2 = None
+        d_x0 = _buf(B, W, dev, zero=True)
+        d_bias = torch.zeros((L_, _pad4(W)), dtype=torch.float32, device=dev)
+        d_wcat, d_cbd, d_ucat = [None] * L_, [None] * L_, [None] * L_
+        split = _split_k_for(2, 4, (B + 31) // 32, budget=128) if tc else 1
+        for l in reversed(range(L_)):
+            xl, t1, s_, t2, z, u, bl = ctx.saved_layers[l]
+            g_sum = _buf(B, W, dev)
+            d_u = _buf(B, W, dev)
+            check(
+                lib.rh_crossmix_out_bwd(g1.data_ptr(), g1.stride(0), ptr(g2), g2.stride(0) if g2 is not None else 0, x0.data_ptr(), x0.stride(0), u.data_ptr(), u.stride(0), bl.data_ptr(), B, W, g_sum.data_ptr(),
+                                        g_sum.stride(0), d_u.data_ptr(), d_u.stride(0), d_x0.data_ptr(), d_x0.stride(0), d_bias[l].data_ptr(), st), "rh_crossmix_out_bwd")
+            d_z = _mm(d_u, False, ucat[l], True, B, Er, W, tc)  # d_z = d_u Ucat
+            d_ucat[l] = _mm(d_u, True, z, True, W, Er, B, tc, split_k=split)  # d_Ucat = d_u^T z
+            d_P = torch.empty((B, Er), dtype=torch.float32, device=dev)
+            d_ag = _buf(B, N1, dev)
+            check(lib.rh_crossmix_mid2_bwd(d_z.data_ptr(), d_z.stride(0), s_.data_ptr(), t2.data_ptr(), B, E, r, d_P.data_ptr(), d_ag.data_ptr(), d_ag.stride(0), st), "rh_crossmix_mid2_bwd")
+            d_t1 = _mm(d_P, False, cbd[l], True, B, Er, Er, tc)  # d_t1 = d_P Cbd
+            d_cbd[l] = _mm(d_P, True, t1, True, Er, Er, B, tc, split_k=split)  # d_Cbd = d_P^T t1
+            check(lib.rh_crossmix_mid1_bwd(d_t1.data_ptr(), d_t1.stride(0), t1.data_ptr(), B, E, r, d_ag.data_ptr(), d_ag.stride(0), st), "rh_crossmix_mid1_bwd")
+            g2 = _mm(d_ag, False, wcat[l][:, :W], True, B, W, N1, tc)  # (d x_l through the projections) = d_ag Wcat
+            d_wcat[l] = _mm(d_ag, True, xl, True, N1, W, B, tc, split_k=split)  # d_Wcat = d_ag^T x_l
+            g1 = g_sum
+        d_x = _buf(B, W, dev)
+        check(lib.rh_sum3(g1.data_ptr(), g1.stride(0), g2.data_ptr(), g2.stride(0), d_x0.data_ptr(), d_x0.stride(0), B, W, d_x.data_ptr(), d_x.stride(0), st), "rh_sum3")
+        u_shapes, c_shapes, g_shapes, b_shapes = ctx.shapes
+        d_us = [torch.empty(tuple(sh), dtype=torch.float32, device=dev) for sh in u_shapes]
+        d_vs = [torch.empty(tuple(sh), dtype=torch.float32, device=dev) for sh in u_shapes]
+        d_cs = [torch.empty(tuple(sh), dtype=torch.float32, device=dev) for sh in c_shapes]
+        d_gs = [torch.empty(W, dtype=torch.float32, device=dev) for _ in g_shapes]
+        check(
+            lib.rh_crossmix_unpack_grads(L_, E, W, r, _ptrs_of(d_wcat), d_wcat[0].stride(0), _ptrs_of(d_cbd), d_cbd[0].stride(0), _ptrs_of(d_ucat), d_ucat[0].stride(0), _ptrs_of(d_us), _ptrs_of(d_vs), _ptrs_of(d_cs),
+                                         _ptrs_of(d_gs), st), "rh_crossmix_unpack_grads")
+        d_bs = [d_bias[l, :W].reshape(tuple(sh)) for l, sh in enumerate(b_shapes)]
+        return (d_x, None, None) + tuple(d_us) + tuple(d_vs) + tuple(d_cs) + tuple(g.view(tuple(sh)) for g, sh in zip(d_gs, g_shapes)) + tuple(d_bs)
+
+
+def cross_net_mix(x, u_list, v_list, c_list, gate_weights, biases):
+    """CrossNetMix.forward on CUDA (returns (B, width); the caller applies the reference's ``squeeze()``)."""
+    L_, E = len(u_list), len(gate_weights)
+    if L_ > 8 or E > 8:
+        raise NotImplementedError("CrossNetMix kernels cover <= 8 layers and <= 8 experts (got %d, %d)" % (L_, E))
+    return _CrossMix.apply(x, L_, E, *u_list, *v_list, *c_list, *gate_weights, *biases)
+
+
+class _CrossV2(torch.autograd.Function):
+    """CrossNetV2 (basic/layers.py:440-444): per layer one width x width GEMM (rh_gemm_tf32x3) + rh_crossmix_out_fwd."""
+
+    @staticmethod
+    def forward(ctx, x, L_, *params):
+        lib = _lib.lib()
+        st = stream_ptr()
+        ws, bs = params[:L_], params[L_:]
+        x0 = _padded_rows(x)
+        B, W = x0.shape
+        dev = x0.device
+        tc = B >= 128 and W >= 32 and _tc_ok(B, x0)
+        wp = [_padded_weight(w) if tc else w for w in ws]
+        saved = []
+        xl = x0
+        for l in range(L_):
+            u = _mm(xl, False, wp[l], False, B, W, W, tc)
+            bl = bs[l].contiguous()
+            nxt = _buf(B, W, dev)
+            check(lib.rh_crossmix_out_fwd(x0.data_ptr(), x0.stride(0), xl.data_ptr(), xl.stride(0), u.data_ptr(), u.stride(0), bl.data_ptr(), B, W, nxt.data_ptr(), nxt.stride(0), st), "rh_crossmix_out_fwd")
+            saved.append((xl, u, bl))
+            xl = nxt
+        ctx.saved_layers, ctx.wp, ctx.meta, ctx.x0 = saved, wp, (L_, W, B, tc), x0
+        return xl
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.lib()
+        st = stream_ptr()
+        L_, W, B, tc = ctx.meta
+        x0 = ctx.x0
+        dev = x0.device
+        g1, g2 = _padded_rows(d_out), None
+        d_x0 = _buf(B, W, dev, zero=True)
+        d_bias = torch.zeros((L_, _pad4(W)), dtype=torch.float32, device=dev)
+        d_ws = [None] * L_
+        split = _split_k_for((W + 127) // 128, (W + 127) // 128, (B + 31) // 32, budget=128) if tc else 1
+        for l in reversed(range(L_)):
+            xl, u, bl = ctx.saved_layers[l]
+            g_sum, d_u = _buf(B, W, dev), _buf(B, W, dev)
+            check(
+                lib.rh_crossmix_out_bwd(g1.data_ptr(), g1.stride(0), ptr(g2), g2.stride(0) if g2 is not None else 0, x0.data_ptr(), x0.stride(0), u.data_ptr(), u.stride(0), bl.data_ptr(), B, W, g_sum.data_ptr(),
+                                        g_sum.stride(0), d_u.data_ptr(), d_u.stride(0), d_x0.data_ptr(), d_x0.stride(0), d_bias[l].data_ptr(), st), "rh_crossmix_out_bwd")
+            g2 = _mm(d_u, False, ctx.wp[l], True, B, W, W, tc)  # d_u W
+            d_ws[l] = _mm(d_u, True, xl, True, W, W, B, tc, split_k=split)  # d_u^T x_l
+            g1 = g_sum
+        d_x = _buf(B, W, dev)
+        check(lib.rh_sum3(g1.data_ptr(), g1.stride(0), g2.data_ptr(), g2.stride(0), d_x0.data_ptr(), d_x0.stride(0), B, W, d_x.data_ptr(), d_x.stride(0), st), "rh_sum3")
+        return (d_x, None) + tuple(d_ws) + tuple(d_bias[l, :W] for l in range(L_))
+
+
+def cross_net_v2(x, weights, biases):
+    return _CrossV2.apply(x, len(weights), *weights, *biases)
+
+
+# =====================================================================================================
 # BatchNorm1d + activation + dropout
 # =====================================================================================================
 ACT_CODES = {"none": 0, "relu": 1, "dice": 2, "prelu": 3, "sigmoid": 4, "leakyrelu": 5}
@@ -461,20 +661,6 @@ def _split_k_for(m_tiles, n_tiles, k_blocks, budget=128):
     return max(1, min(k_blocks, budget // tiles))
 
 
-_gemm_scratch = {}
-
-
-def _gemm_stats_scratch(dev, rows, cols):
-    """Per (device, shape) scratch of rh_gemm_tf32x3_stats: per-tile partial statistics + tickets; zeroed once, the kernel keeps
-    its tickets zero.  Launches that share it are ordered on one stream (the tower's forward)."""
-    key = (dev.index if dev.index is not None else torch.cuda.current_device(), rows, cols)
-    buf = _gemm_scratch.get(key)
-    if buf is None:
-        n = int(_lib.lib().rh_gemm_stats_scratch_floats(rows, cols))
-        buf = _gemm_scratch[key] = torch.zeros(n, dtype=torch.float32, device=dev)
-    return buf
-
-
 _aux_streams = {}
 
 
@@ -499,13 +685,84 @@ def _dropout_seed(module):
     return (torch.initial_seed() * 0x9E3779B1 + salt * 0x85EBCA6B) & 0xFFFFFFFF
 
 
-class _TowerLayer(torch.autograd.Function):
-    """y = dropout(act(bn(x @ W^T + b))): one tower layer (basic/layers.py:282-285) as GEMM + statistics + ONE fused pass.
+_fused_bn_scratch = {}
 
-    The GEMMs run on the tensor cores through rh_gemm_tf32x3 (fp32-accurate 3xTF32; batches under 128 rows use torch.mm);
-    everything between them is rh_colstats / rh_bn_act_fwd / rh_bn_act_bwd.  No activation, mask or normalised copy is
-    stored: backward recomputes from h.  In backward the weight-gradient GEMM runs on a second stream next to the
-    input-gradient GEMM (config.concurrent_tower_bwd).
+
+def _bn_fused_scratch(dev, cols):
+    """Scratch of the fused BatchNorm kernels per (device, width): column sums + barrier counters, zeroed once, left zeroed by
+    every launch.  Launches that share it are ordered on one stream (a tower's layers run one after the other)."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), cols)
+    buf = _fused_bn_scratch.get(key)
+    if buf is None:
+        buf = _fused_bn_scratch[key] = torch.zeros(int(_lib.lib().rh_bn_fused_scratch_floats(cols)), dtype=torch.float32, device=dev)
+    return buf
+
+
+def _linear_fwd(x2, W, b):
+    """h = x2 @ W^T + b -> (h, padded weight view or None, ran on the tensor cores?)."""
+    rows, K = x2.shape
+    cols = W.shape[0]
+    h = torch.empty((rows, cols), dtype=torch.float32, device=x2.device)
+    use_tc = cols % 4 == 0 and cols >= 32 and _tc_ok(rows, x2)
+    Wp = None
+    if use_tc:
+        Wp = _padded_weight(W)  # (cols, K) view with a 16-byte row stride
+        gemm3x(x2, False, Wp, False, rows, cols, K, bias=b, out=h)
+    elif b is not None:
+        torch.addmm(b, x2, W.t(), out=h)
+    else:
+        torch.mm(x2, W.t(), out=h)
+    return h, Wp, use_tc
+
+
+def _linear_bwd(d_h, x2, W, Wp, use_tc, need_dx):
+    """(d_x or None, d_W) of h = x2 @ W^T from d_h; on the tensor cores the weight-gradient GEMM runs on a second stream next to
+    the input-gradient GEMM (config.concurrent_tower_bwd)."""
+    from . import config
+    rows, K = x2.shape
+    cols = W.shape[0]
+    dev = d_h.device
+    fork = None
+    if use_tc:  # dW[cols, K] = d_h^T x: both operands read as stored (MN-major), K = rows split over CTAs
+        concurrent = config.concurrent_tower_bwd and need_dx
+        split = _split_k_for((cols + 127) // 128, (K + 127) // 128, (rows + 31) // 32, budget=64 if concurrent else 128)
+        d_W = torch.zeros((cols, K), dtype=torch.float32, device=dev) if split > 1 else torch.empty((cols, K), dtype=torch.float32, device=dev)
+        if concurrent:
+            # dW and dX only share their input d_h: dW runs on a second stream (half the SMs each), joined before returning
+            cur, fork = torch.cuda.current_stream(), _aux_stream(dev)
+            fork.wait_stream(cur)
+            with torch.cuda.stream(fork):
+                gemm3x(d_h, True, x2, True, cols, K, rows, split_k=split, out=d_W)
+        else:
+            gemm3x(d_h, True, x2, True, cols, K, rows, split_k=split, out=d_W)
+    else:
+        d_W = torch.mm(d_h.t(), x2)
+    d_x = None
+    if need_dx:
+        ld = _pad4(K)
+        buf = torch.empty((rows, ld), dtype=torch.float32, device=dev)
+        d_x = buf if ld == K else buf[:, :K]
+        if use_tc:  # dX[rows, K] = d_h W: W (cols, K) is the MN-major B operand as stored
+            gemm3x(d_h, False, Wp, True, rows, K, cols, out=buf)
+        else:
+            torch.mm(d_h, W, out=d_x)
+    if fork is not None:
+        torch.cuda.current_stream().wait_stream(fork)
+    return d_x, d_W
+
+
+def _fused_bn_ok(rows, cols, training, head):
+    from . import config
+    return bool(training and config.fused_bn and cols % 4 == 0 and _lib.lib().rh_bn_fused_supported(rows, cols, int(head)))
+
+
+class _TowerLayer(torch.autograd.Function):
+    """y = dropout(act(bn(x @ W^T + b))): one tower layer (basic/layers.py:282-285).
+
+    The GEMMs run on the tensor cores through rh_gemm_tf32x3 (fp32-accurate 3xTF32; batches under 128 rows use torch.mm).
+    Training-mode BatchNorm + activation + dropout is ONE launch each way when the layer fits the fused kernels
+    (rh_bn_act_fused_fwd / _bwd: rows in registers across a grid barrier); otherwise rh_colstats + rh_bn_act_fwd and the
+    two passes of rh_bn_act_bwd.  No activation, mask or normalised copy is stored: backward recomputes from h.
     """
 
     @staticmethod
@@ -516,46 +773,37 @@ class _TowerLayer(torch.autograd.Function):
         cols = W.shape[0]
         dev = x2.device
         st = stream_ptr()
-        h = torch.empty((rows, cols), dtype=torch.float32, device=dev)
-        Wp = None
-        use_tc = cols % 4 == 0 and cols >= 32 and _tc_ok(rows, x2)
         training = cfg["training"]
-        stats = None
-        if use_tc:
-            Wp = _padded_weight(W)  # (cols, K) view with a 16-byte row stride
-            from . import config
-            if training and config.gemm_colstats:  # GEMM + BatchNorm column statistics in ONE launch
-                stats = torch.empty(2 * cols + 1, dtype=torch.float32, device=dev)
-                check(L.rh_gemm_tf32x3_stats(x2.data_ptr(), x2.stride(0), 0, Wp.data_ptr(), Wp.stride(0), 0, h.data_ptr(), h.stride(0), rows, cols, K, ptr(b), stats.data_ptr(),
-                                             _gemm_stats_scratch(dev, rows, cols).data_ptr(), ptr(cfg["running_mean"]), ptr(cfg["running_var"]), ptr(cfg["num_batches_tracked"]), float(cfg["momentum"]), st),
-                      "rh_gemm_tf32x3_stats")
-            else:
-                gemm3x(x2, False, Wp, False, rows, cols, K, bias=b, out=h)
-        elif b is not None:
-            torch.addmm(b, x2, W.t(), out=h)
-        else:
-            torch.mm(x2, W.t(), out=h)
-        counter = None
-        if training and stats is not None:
-            mean, var, counter = stats[:cols], stats[cols:2 * cols], stats[2 * cols:]
-        elif training:
-            stats = torch.empty(2 * cols + 1, dtype=torch.float32, device=dev)
-            check(L.rh_colstats(h.data_ptr(), cols, rows, cols, stats.data_ptr(), _colstats_scratch(dev, cols).data_ptr(), ptr(cfg["running_mean"]), ptr(cfg["running_var"]), ptr(cfg["num_batches_tracked"]),
-                                float(cfg["momentum"]), st), "rh_colstats")
-            mean, var, counter = stats[:cols], stats[cols:2 * cols], stats[2 * cols:]
-        else:
-            stats = None
-            mean, var = cfg["running_mean"], cfg["running_var"]
+        h, Wp, use_tc = _linear_fwd(x2, W, b)
         p = float(cfg["p_drop"])
         y = torch.empty((rows, cols), dtype=torch.float32, device=dev)
-        check(
-            L.rh_bn_act_fwd(h.data_ptr(), cols, rows, cols, ptr(mean), ptr(var), float(cfg["eps"]), ptr(gamma), ptr(beta), cfg["act"], ptr(act_param), float(cfg["dice_eps"]), p, cfg["seed"], ptr(counter), y.data_ptr(), cols,
-                            st), "rh_bn_act_fwd")
+        fused = _fused_bn_ok(rows, cols, training, False)
+        stats = None
+        if fused:
+            stats = torch.empty(2 * cols + 1, dtype=torch.float32, device=dev)
+            check(
+                L.rh_bn_act_fused_fwd(h.data_ptr(), cols, rows, cols, float(cfg["eps"]), ptr(gamma), ptr(beta), cfg["act"], ptr(act_param), float(cfg["dice_eps"]), p, cfg["seed"], ptr(cfg["running_mean"]),
+                                      ptr(cfg["running_var"]), ptr(cfg["num_batches_tracked"]), float(cfg["momentum"]), stats.data_ptr(), _bn_fused_scratch(dev, cols).data_ptr(), y.data_ptr(), cols, None, None, None,
+                                      None, 0, None, st), "rh_bn_act_fused_fwd")
+            mean = var = None
+        else:
+            counter = None
+            if training:
+                stats = torch.empty(2 * cols + 1, dtype=torch.float32, device=dev)
+                check(L.rh_colstats(h.data_ptr(), cols, rows, cols, stats.data_ptr(), _colstats_scratch(dev, cols).data_ptr(), ptr(cfg["running_mean"]), ptr(cfg["running_var"]), ptr(cfg["num_batches_tracked"]),
+                                    float(cfg["momentum"]), st), "rh_colstats")
+                mean, var, counter = stats[:cols], stats[cols:2 * cols], stats[2 * cols:]
+            else:
+                mean, var = cfg["running_mean"], cfg["running_var"]
+            check(
+                L.rh_bn_act_fwd(h.data_ptr(), cols, rows, cols, ptr(mean), ptr(var), float(cfg["eps"]), ptr(gamma), ptr(beta), cfg["act"], ptr(act_param), float(cfg["dice_eps"]), p, cfg["seed"], ptr(counter), y.data_ptr(),
+                                cols, st), "rh_bn_act_fwd")
         ctx.cfg = cfg
         ctx.has_param = act_param is not None
         ctx.has_bias = b is not None
         ctx.use_tc = use_tc
         ctx.Wp = Wp
+        ctx.fused = fused
         ctx.save_for_backward(x2, W, h, stats, mean if stats is None else None, var if stats is None else None, gamma, beta, act_param)
         return y
 
@@ -568,55 +816,36 @@ class _TowerLayer(torch.autograd.Function):
         cols = W.shape[0]
         dev = h.device
         training = stats is not None
-        if training:
-            mean, var, counter = stats[:cols], stats[cols:2 * cols], stats[2 * cols:]
-        else:
-            mean, var, counter = rmean, rvar, None
         g = _rowmajor(d_y)
         g_ld = g.stride(0) if rows > 1 else cols
         d_h = torch.empty((rows, cols), dtype=torch.float32, device=dev)
-        gbuf = torch.zeros(3 * cols + 1, dtype=torch.float32, device=dev)
-        d_gamma, d_beta, d_b, d_alpha = gbuf[:cols], gbuf[cols:2 * cols], gbuf[2 * cols:3 * cols], gbuf[3 * cols:]
-        check(
-            L.rh_bn_act_bwd(h.data_ptr(), cols, rows, cols, ptr(mean), ptr(var), float(cfg["eps"]), ptr(gamma), ptr(beta), cfg["act"], ptr(act_param), float(cfg["dice_eps"]), float(cfg["p_drop"]), cfg["seed"],
-                            ptr(counter), g.data_ptr(), g_ld, int(training), d_h.data_ptr(), cols, d_gamma.data_ptr(), d_beta.data_ptr(), d_alpha.data_ptr() if ctx.has_param else None, stream_ptr()), "rh_bn_act_bwd")
-        from . import config
-        fork = None
-        if ctx.use_tc:  # dW[cols, K] = d_h^T x: both operands read as stored (MN-major), K = rows split over CTAs
-            concurrent = config.concurrent_tower_bwd and ctx.needs_input_grad[0]
-            split = _split_k_for((cols + 127) // 128, (K + 127) // 128, (rows + 31) // 32, budget=64 if concurrent else 128)
-            d_W = torch.zeros((cols, K), dtype=torch.float32, device=dev) if split > 1 else torch.empty((cols, K), dtype=torch.float32, device=dev)
-            if concurrent:
-                # dW and dX only share their input d_h: dW runs on a second stream (half the SMs each), joined before returning
-                cur, fork = torch.cuda.current_stream(), _aux_stream(dev)
-                fork.wait_stream(cur)
-                with torch.cuda.stream(fork):
-                    gemm3x(d_h, True, x2, True, cols, K, rows, split_k=split, out=d_W)
-            else:
-                gemm3x(d_h, True, x2, True, cols, K, rows, split_k=split, out=d_W)
+        if ctx.fused and g_ld % 4 == 0 and g.data_ptr() % 16 == 0:
+            gbuf = torch.empty(3 * cols + 4, dtype=torch.float32, device=dev)  # every slice is written by the kernel
+            d_gamma, d_beta, d_b, d_alpha = gbuf[:cols], gbuf[cols:2 * cols], gbuf[2 * cols:3 * cols], gbuf[3 * cols:3 * cols + 1]
+            check(
+                L.rh_bn_act_fused_bwd(h.data_ptr(), cols, rows, cols, stats.data_ptr(), float(cfg["eps"]), ptr(gamma), ptr(beta), cfg["act"], ptr(act_param), float(cfg["dice_eps"]), float(cfg["p_drop"]), cfg["seed"],
+                                      g.data_ptr(), g_ld, None, None, None, 0, _bn_fused_scratch(dev, cols).data_ptr(), d_h.data_ptr(), cols, d_gamma.data_ptr(), d_beta.data_ptr(),
+                                      d_alpha.data_ptr(), None, None, None, d_b.data_ptr(), stream_ptr()), "rh_bn_act_fused_bwd")
         else:
-            d_W = torch.mm(d_h.t(), x2)
-        if not training and ctx.has_bias:  # eval: BN is affine, the Linear bias sees sum_rows d_h = d_beta * gamma * rstd
-            d_b = d_beta * (gamma if gamma is not None else 1.0) / torch.sqrt(var + cfg["eps"])
-        # training: the bias in front of a batch-statistics BN has a gradient of exactly 0 (BN removes any per-column
-        # shift); the reference's autograd produces rounding noise ~1e-8 there.  d_b stays the zero slice of gbuf.
-        d_x = None
-        if ctx.needs_input_grad[0]:
-            ld = _pad4(K)
-            buf = torch.empty((rows, ld), dtype=torch.float32, device=dev)
-            d_x = buf if ld == K else buf[:, :K]
-            if ctx.use_tc:  # dX[rows, K] = d_h W: W (cols, K) is the MN-major B operand as stored
-                gemm3x(d_h, False, ctx.Wp, True, rows, K, cols, out=buf)
+            if training:
+                mean, var, counter = stats[:cols], stats[cols:2 * cols], stats[2 * cols:]
             else:
-                torch.mm(d_h, W, out=d_x)
-        if fork is not None:
-            torch.cuda.current_stream().wait_stream(fork)
+                mean, var, counter = rmean, rvar, None
+            gbuf = torch.zeros(3 * cols + 1, dtype=torch.float32, device=dev)
+            d_gamma, d_beta, d_b, d_alpha = gbuf[:cols], gbuf[cols:2 * cols], gbuf[2 * cols:3 * cols], gbuf[3 * cols:]
+            check(
+                L.rh_bn_act_bwd(h.data_ptr(), cols, rows, cols, ptr(mean), ptr(var), float(cfg["eps"]), ptr(gamma), ptr(beta), cfg["act"], ptr(act_param), float(cfg["dice_eps"]), float(cfg["p_drop"]), cfg["seed"],
+                                ptr(counter), g.data_ptr(), g_ld, int(training), d_h.data_ptr(), cols, d_gamma.data_ptr(), d_beta.data_ptr(), d_alpha.data_ptr() if ctx.has_param else None, stream_ptr()), "rh_bn_act_bwd")
+            if not training and ctx.has_bias:  # eval: BN is affine, the Linear bias sees sum_rows d_h = d_beta * gamma * rstd
+                d_b = d_beta * (gamma if gamma is not None else 1.0) / torch.sqrt(var + cfg["eps"])
+        # training: the bias in front of a batch-statistics BN has a gradient of exactly 0 (BN removes any per-column
+        # shift); the reference's autograd produces rounding noise ~1e-8 there.  d_b is the zero slice of gbuf.
+        d_x, d_W = _linear_bwd(d_h, x2, W, ctx.Wp, ctx.use_tc, ctx.needs_input_grad[0])
         return (d_x, d_W, d_b if ctx.has_bias else None, d_gamma if gamma is not None else None, d_beta if beta is not None else None, d_alpha.view_as(act_param) if ctx.has_param else None, None)
 
 
-def tower_layer(x, linear, bn, act_code, act_param, dice_eps, p_drop, training):
-    """One ``Linear -> BatchNorm1d -> activation -> Dropout`` group of the reference's MLP on CUDA."""
-    cfg = {
+def _layer_cfg(bn, act_code, dice_eps, p_drop, training):
+    return {
         "running_mean": bn.running_mean,
         "running_var": bn.running_var,
         "num_batches_tracked": bn.num_batches_tracked,
@@ -628,7 +857,77 @@ def tower_layer(x, linear, bn, act_code, act_param, dice_eps, p_drop, training):
         "p_drop": float(p_drop),
         "seed": _dropout_seed(bn) if p_drop > 0 else 0,
     }
-    return _TowerLayer.apply(x, linear.weight, linear.bias, bn.weight, bn.bias, act_param, cfg)
+
+
+def tower_layer(x, linear, bn, act_code, act_param, dice_eps, p_drop, training):
+    """One ``Linear -> BatchNorm1d -> activation -> Dropout`` group of the reference's MLP on CUDA."""
+    return _TowerLayer.apply(x, linear.weight, linear.bias, bn.weight, bn.bias, act_param, _layer_cfg(bn, act_code, dice_eps, p_drop, training))
+
+
+class _TowerLayerHead(torch.autograd.Function):
+    """p = f(Linear(K2, 1)(dropout(act(bn(x @ W^T + b)))) + extras...): the LAST hidden layer of a tower together with the output
+    layer and the model's tail (basic/layers.py:279-285 + e.g. models/ranking/deepfm.py:41-43), training mode.
+
+    GEMM + ONE fused launch forward (column statistics, BatchNorm, activation, dropout, the head's dot product, side terms,
+    sigmoid — the activation never reaches HBM), ONE fused launch + the two gradient GEMMs backward."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, gamma, beta, act_param, head_W, head_b, cfg, apply_sigmoid, *extras):
+        L = _lib.lib()
+        x2 = _rowmajor(x if x.dtype == torch.float32 else x.float())
+        rows, K = x2.shape
+        cols = W.shape[0]
+        dev = x2.device
+        h, Wp, use_tc = _linear_fwd(x2, W, b)
+        ex = [e.contiguous() for e in extras]
+        stats = torch.empty(2 * cols + 1, dtype=torch.float32, device=dev)
+        out = torch.empty(rows, dtype=torch.float32, device=dev)
+        check(
+            L.rh_bn_act_fused_fwd(h.data_ptr(), cols, rows, cols, float(cfg["eps"]), ptr(gamma), ptr(beta), cfg["act"], ptr(act_param), float(cfg["dice_eps"]), float(cfg["p_drop"]), cfg["seed"], ptr(cfg["running_mean"]),
+                                  ptr(cfg["running_var"]), ptr(cfg["num_batches_tracked"]), float(cfg["momentum"]), stats.data_ptr(), _bn_fused_scratch(dev, cols).data_ptr(), None, 0, head_W.data_ptr(), ptr(head_b),
+                                  ptr(ex[0]) if len(ex) > 0 else None, ptr(ex[1]) if len(ex) > 1 else None, int(apply_sigmoid), out.data_ptr(), stream_ptr()), "rh_bn_act_fused_fwd")
+        ctx.cfg, ctx.sig, ctx.n_extra = cfg, bool(apply_sigmoid), len(ex)
+        ctx.has_param, ctx.has_bias, ctx.has_head_bias = act_param is not None, b is not None, head_b is not None
+        ctx.use_tc, ctx.Wp = use_tc, Wp
+        ctx.save_for_backward(x2, W, h, stats, gamma, beta, act_param, head_W, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        L = _lib.lib()
+        cfg = ctx.cfg
+        x2, W, h, stats, gamma, beta, act_param, head_W, out = ctx.saved_tensors
+        rows, K = x2.shape
+        cols = W.shape[0]
+        dev = h.device
+        d_out = d_out.contiguous()
+        d_h = torch.empty((rows, cols), dtype=torch.float32, device=dev)
+        gbuf = torch.empty(4 * cols + 4, dtype=torch.float32, device=dev)  # every slice is written by the kernel
+        d_gamma, d_beta, d_b, d_hw = gbuf[:cols], gbuf[cols:2 * cols], gbuf[2 * cols:3 * cols], gbuf[3 * cols:4 * cols]
+        d_alpha, d_hb = gbuf[4 * cols:4 * cols + 1], gbuf[4 * cols + 1:4 * cols + 2]
+        d_e = torch.empty(rows, dtype=torch.float32, device=dev) if ctx.n_extra else None
+        check(
+            L.rh_bn_act_fused_bwd(h.data_ptr(), cols, rows, cols, stats.data_ptr(), float(cfg["eps"]), ptr(gamma), ptr(beta), cfg["act"], ptr(act_param), float(cfg["dice_eps"]), float(cfg["p_drop"]), cfg["seed"], None, 0,
+                                  head_W.data_ptr(), out.data_ptr(), d_out.data_ptr(), int(ctx.sig), _bn_fused_scratch(dev, cols).data_ptr(), d_h.data_ptr(), cols, d_gamma.data_ptr(), d_beta.data_ptr(),
+                                  d_alpha.data_ptr(), d_hw.data_ptr(), d_hb.data_ptr(), ptr(d_e), d_b.data_ptr(), stream_ptr()), "rh_bn_act_fused_bwd")
+        d_x, d_W = _linear_bwd(d_h, x2, W, ctx.Wp, ctx.use_tc, ctx.needs_input_grad[0])
+        return (d_x, d_W, d_b if ctx.has_bias else None, d_gamma if gamma is not None else None, d_beta if beta is not None else None, d_alpha.view_as(act_param) if ctx.has_param else None,
+                d_hw.view_as(head_W), d_hb if ctx.has_head_bias else None, None, None) + (d_e,) * ctx.n_extra
+
+
+def tower_layer_head(x, linear, bn, act_code, act_param, dice_eps, p_drop, head_linear, extras=(), sigmoid=True):
+    """Training-mode last hidden layer + output layer + tail as :class:`_TowerLayerHead`, or None when the shape is outside the
+    fused kernel (callers then run ``tower_layer`` + ``output_head``)."""
+    from . import config
+    Wh = head_linear.weight
+    x2 = x
+    if (not config.fused_bn_head or not x.is_cuda or x.dim() != 2 or Wh.shape[0] != 1 or Wh.dtype != torch.float32 or not Wh.is_contiguous() or Wh.data_ptr() % 16 != 0 or len(extras) > 2
+            or any(e.dim() != 1 or e.shape[0] != x.shape[0] or e.dtype != torch.float32 for e in extras)):
+        return None
+    cols = linear.weight.shape[0]
+    if Wh.shape[1] != cols or not _fused_bn_ok(x2.shape[0], cols, True, True):
+        return None
+    return _TowerLayerHead.apply(x, linear.weight, linear.bias, bn.weight, bn.bias, act_param, Wh, head_linear.bias, _layer_cfg(bn, act_code, dice_eps, p_drop, True), bool(sigmoid), *extras)
 
 
 # =====================================================================================================

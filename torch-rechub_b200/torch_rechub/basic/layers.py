@@ -313,12 +313,26 @@ class MLP(nn.Module):
 
     def forward_head(self, x, extras=(), sigmoid=True):
         """``f(self(x).squeeze(1) + sum(extras))`` with the ``Linear(., 1)`` output layer, the per-sample ``extras`` (``(B,)``
-        tensors) and the sigmoid in ONE launch (``rh_head_fwd``); None when this tower has no such head or ``x`` is not on CUDA."""
+        tensors) and the sigmoid fused: in training mode the LAST hidden layer's BatchNorm + activation + dropout and the head
+        are ONE launch (``rh_bn_act_fused_fwd`` in head mode), otherwise the head alone is (``rh_head_fwd``).  None when this
+        tower has no such head or ``x`` is not on CUDA."""
         mods = list(self.mlp)
         if not x.is_cuda or not mods or not isinstance(mods[-1], nn.Linear) or mods[-1].out_features != 1:
             return None
         from ..b200 import ops
-        h = self._forward_cuda(x, len(mods) - 1)
+        n = len(mods) - 1
+        if (n >= 4 and isinstance(mods[n - 4], nn.Linear) and isinstance(mods[n - 3], nn.BatchNorm1d) and isinstance(mods[n - 1], nn.Dropout) and mods[n - 3].training):
+            h = self._forward_cuda(x, n - 4)
+            lin, bn, act, drop = mods[n - 4], mods[n - 3], mods[n - 2], mods[n - 1]
+            if self._fusable(bn, act, h):
+                name = _FUSED_ACTS[type(act)]
+                param = act.alpha if name == "dice" else (act.weight if name == "prelu" else None)
+                y = ops.tower_layer_head(h, lin, bn, ops.ACT_CODES[name], param, getattr(act, "epsilon", 0.0), drop.p if drop.training else 0.0, mods[-1], extras, sigmoid)
+                if y is not None:
+                    return y
+            h = self._forward_cuda(h, 4, start=n - 4)
+        else:
+            h = self._forward_cuda(x, n)
         y = ops.output_head(h, mods[-1], extras, sigmoid)
         if y is None:  # outside the kernel's shapes: finish with the library route
             y = mods[-1](h).squeeze(1)
@@ -327,9 +341,9 @@ class MLP(nn.Module):
             y = torch.sigmoid(y) if sigmoid else y
         return y
 
-    def _forward_cuda(self, x, n_mods):
+    def _forward_cuda(self, x, n_mods, start=0):
         from ..b200 import ops
-        mods = list(self.mlp)[:n_mods]
+        mods = list(self.mlp)[start:start + n_mods]
         i = 0
         while i < len(mods):
             m = mods[i]
@@ -389,7 +403,7 @@ class CrossNetwork(nn.Module):
 
 class CrossNetV2(nn.Module):
     """DCN-v2 full-rank cross layers ``x0 * (W x) + b + x`` (reference ``layers.py:423-444``).
-    A dense ``width x width`` contraction per layer: tensor-core GEMM work, issued as library GEMMs."""
+    On CUDA: one tensor-core GEMM (``rh_gemm_tf32x3``) + one fused cross step (``rh_crossmix_out_fwd``) per layer."""
 
     def __init__(self, input_dim, num_layers):
         super().__init__()
@@ -398,6 +412,9 @@ class CrossNetV2(nn.Module):
         self.b = torch.nn.ParameterList([torch.nn.Parameter(torch.zeros((input_dim,))) for _ in range(num_layers)])
 
     def forward(self, x):
+        if x.is_cuda and x.dim() == 2 and 0 < self.num_layers <= 8:
+            from ..b200 import ops
+            return ops.cross_net_v2(x, [lin.weight for lin in self.w], list(self.b))
         x0 = x
         for i in range(self.num_layers):
             x = x0 * self.w[i](x) + self.b[i] + x
@@ -409,6 +426,8 @@ class CrossNetMix(nn.Module):
 
     Per layer and expert: ``x0 * (U tanh(C tanh(V^T x_l)) + bias)``, experts mixed by a softmax over
     ``Linear(width,1)`` gates (the gate modules are shared by all layers, reference ``:466``).
+    On CUDA a layer is three tensor-core GEMMs over packed operands + three fused maps (``b200.ops._CrossMix``,
+    ``csrc/rh_crossmix.cu``) instead of the reference's ~60 launches.
     """
 
     def __init__(self, input_dim, num_layers=2, low_rank=32, num_experts=4):
@@ -424,14 +443,14 @@ class CrossNetMix(nn.Module):
         self.bias = torch.nn.ParameterList([nn.Parameter(nn.init.zeros_(torch.empty(input_dim, 1))) for _ in range(self.num_layers)])
 
     def _forward_batched(self, x):
-        """The same map with the experts batched into three GEMMs per layer (the CUDA route; ~60 launches per layer otherwise):
+        """The packed formulation the CUDA kernels implement, written with stock torch ops (the CPU-side statement of the algebra,
+        checked against the reference-order loop in tests/test_cpu_api.py):
 
             [a | g] = x_l [V_1 .. V_E | Wg^T]            one (B, W) x (W, E r + E) product: every expert's projection AND the gates
             t2_e    = tanh(C_e tanh(a_e)),  s = softmax(g)
             x_{l+1} = x_0 * ([s_1 t2_1 .. s_E t2_E] [U_1 .. U_E]^T + b) + x_l
 
-        — the gate-weighted sum over experts moves inside the last product's K dimension (sum_e s_e = 1 keeps the bias whole).
-        Algebraically identical to the loop below; fp32 rounding differs by reassociation only."""
+        — the gate-weighted sum over experts moves inside the last product's K dimension (sum_e s_e = 1 keeps the bias whole)."""
         n, width = x.shape
         E = self.num_experts
         gates = torch.cat([g.weight for g in self.gating], dim=0)  # (E, W)
@@ -448,10 +467,10 @@ class CrossNetMix(nn.Module):
         return x_l.squeeze()  # the reference's squeeze() quirk at B == 1 (layers.py:505), kept on this route too
 
     def forward(self, x):
-        if x.is_cuda and x.dim() == 2:
-            from ..b200 import config
-            if config.batched_crossmix:
-                return self._forward_batched(x)
+        if x.is_cuda and x.dim() == 2 and 0 < self.num_layers <= 8 and self.num_experts <= 8:
+            from ..b200 import ops
+            out = ops.cross_net_mix(x, list(self.u_list), list(self.v_list), list(self.c_list), [g.weight for g in self.gating], list(self.bias))
+            return out.squeeze()  # NOTE reference quirk kept: squeeze() drops the batch axis when B == 1 (layers.py:505)
         x_0 = x.unsqueeze(2)  # (B, width, 1)
         x_l = x_0
         for i in range(self.num_layers):

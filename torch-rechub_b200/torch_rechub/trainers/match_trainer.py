@@ -57,10 +57,16 @@ class MatchTrainer(object):
     ):
         self.model = model
         self.gpus = [] if gpus is None else gpus
+        self.device = torch.device(device)
         if len(self.gpus) > 1:
+            if self.device.type == "cuda":
+                # nn.DataParallel replicas see the tables as non-leaf Broadcast outputs: the engine's scatter-add lands in the
+                # replica's gradient buffer and is never reduced back, so the tables would silently stop training while the
+                # towers keep going (the same configuration CTRTrainer rejects)
+                raise RuntimeError("multi-GPU training of the two-tower path is not wired to the field-sharded engine yet: "
+                                   "run MatchTrainer on one CUDA device (gpus=[i]) — nn.DataParallel cannot carry the engine's table gradients")
             print('parallel running on these gpus:', self.gpus)
             self.model = torch.nn.DataParallel(self.model, device_ids=self.gpus)
-        self.device = torch.device(device)
         self.model.to(self.device)
         self.in_batch_neg = in_batch_neg
         self.in_batch_neg_ratio = in_batch_neg_ratio
