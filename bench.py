@@ -177,7 +177,21 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_run(args.steps, args.warmup, budget_s=float(os.environ.get("RECHUB_BENCH_CPU_BUDGET_S", "150")))
+    budget = float(os.environ.get("RECHUB_BENCH_CPU_BUDGET_S", "150"))
+    if args.workload != "deepfm":
+        import bench_workloads as bw
+        r = bw.reference_run(args.workload, args.steps, budget)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (the installed reference) did not travel with this snapshot; only the DeepFM step has a stock-torch port"}), flush=True)
+            return
+        print(json.dumps({"impl": "reference", "metric": bw.METRIC[args.workload], "value": r["samples_per_s"], "unit": "samples/s", "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup,
+                          "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+                          "config": {"workload": bw.DESCRIBE[args.workload], "global_batch_per_gpu": bw.BATCH, "parallelism": "cpu"},
+                          "cpu_baseline": {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["threads"], "host_cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                                           "thread_sweep_s_per_step": r.get("thread_sweep_s_per_step")},
+                          "e2e": {"value": r["samples_per_s"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
+    r = cpu_reference_run(args.steps, args.warmup, budget_s=budget)
     line = {
         "impl": "reference",
         "metric": "ctr_samples_per_sec_deepfm_criteo_train_step",
@@ -199,14 +213,14 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline_subprocess(budget_s):
+def cpu_baseline_subprocess(budget_s, workload="deepfm"):
     """cpu_baseline of the b200 arm: the reference arm in its own interpreter (the installed reference shares this package's import
     name, so it cannot live in this process), on a bounded sample."""
     env = dict(os.environ, RECHUB_BENCH_CPU_BUDGET_S=str(budget_s))
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
         env.pop(k, None)
     try:
-        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "5", "--warmup", "1"], env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=budget_s * 4 + 120)
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "5", "--warmup", "1", "--workload", workload], env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=budget_s * 4 + 120)
         line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
         d = json.loads(line)
         cb = d["cpu_baseline"]
@@ -658,9 +672,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="skip the sharded-vs-single-GPU parity check of multi-GPU runs")
     ap.add_argument("--ids", default="uniform", choices=["uniform", "zipf"], help="id distribution of the synthetic batches (uniform = the headline workload)")
+    ap.add_argument("--workload", default="deepfm", choices=["deepfm", "dcnv2", "din", "dssm"], help="deepfm = the headline metric of BASELINE.json (default); the others are its configs 3-5 (bench_workloads.py)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload != "deepfm":
+        import bench_workloads
+        bench_workloads.run(args, sys.modules[__name__])
     else:
         run_b200_arm(args)
 

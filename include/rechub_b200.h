@@ -419,13 +419,15 @@ int rh_crossmix_unpack_grads(int n_layers, int n_experts, int width, int rank,
 int rh_crossmix_mid1_fwd(const float* ag, int64_t ld_ag, int64_t batch, int n_experts, int rank, float* t1, float* s, void* stream);
 /* t2 (batch, E r) = tanh(P);  z[:, (e, j)] = s[:, e] * t2[:, (e, j)]                      (layers.py:489-490,502) */
 int rh_crossmix_mid2_fwd(const float* P, const float* s, int64_t batch, int n_experts, int rank, float* t2, float* z, void* stream);
-/* out = x0 * (u + bias) + xl  — the cross step of CrossNetMix (:494,503) and CrossNetV2 (:443);  bias (width) or NULL */
+/* The cross step.  bias_outside == 0: out = x0 * (u + bias) + xl  (CrossNetMix, :494,503);  != 0: out = x0 * u + bias + xl
+ * (CrossNetV2, :443);  bias (width) or NULL */
 int rh_crossmix_out_fwd(const float* x0, int64_t ld0, const float* xl, int64_t ldl, const float* u, int64_t ldu, const float* bias,
-                        int64_t batch, int width, float* out, int64_t ldo, void* stream);
+                        int bias_outside, int64_t batch, int width, float* out, int64_t ldo, void* stream);
 /* Backward of the cross step for an incoming gradient g = g1 (+ g2, may be NULL):  g_sum = g (or NULL);  d_u = g * x0;
- * d_x0_acc += g * (u + bias);  d_bias (width, zeroed by the caller, or NULL) += column sums of d_u. */
+ * d_x0_acc += g * (u + bias);  d_bias (width, zeroed by the caller, or NULL) += column sums of d_u
+ * (bias_outside: d_x0_acc += g * u;  d_bias += column sums of g). */
 int rh_crossmix_out_bwd(const float* g1, int64_t ldg1, const float* g2, int64_t ldg2, const float* x0, int64_t ld0,
-                        const float* u, int64_t ldu, const float* bias, int64_t batch, int width,
+                        const float* u, int64_t ldu, const float* bias, int bias_outside, int64_t batch, int width,
                         float* g_sum, int64_t ldgs, float* d_u, int64_t lddu, float* d_x0_acc, int64_t ldx, float* d_bias, void* stream);
 /* d_P = d_z * s_e * (1 - t2^2);  d_ag[:, E r + e] = softmax backward of d_s_e = sum_j d_z[(e, j)] t2[(e, j)] */
 int rh_crossmix_mid2_bwd(const float* d_z, int64_t ld_dz, const float* s, const float* t2, int64_t batch, int n_experts, int rank,

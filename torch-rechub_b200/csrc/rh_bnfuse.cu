@@ -66,7 +66,21 @@ struct BnFuseP {
   float* d_head_b;
   float* d_extra;
   float* d_lin_bias;
+#ifdef RH_BN_TRACE
+  unsigned long long* trace;  // tools/bnfuse_trace.cu: [cta][8] clock64 stamps
+#endif
 };
+
+#ifdef RH_BN_TRACE
+#define RH_BT(ev)                                                                        \
+  do {                                                                                   \
+    if (p.trace != nullptr && threadIdx.x == 0) p.trace[(size_t)blockIdx.x * 8 + (ev)] = clock64(); \
+  } while (0)
+#else
+#define RH_BT(ev) \
+  do {            \
+  } while (0)
+#endif
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
@@ -159,6 +173,7 @@ __global__ void __launch_bounds__(256) bn_fused_fwd_kernel(const BnFuseP p) {
   // dropout stream id of this forward = num_batches_tracked + 1 (the last CTA stores the incremented value at the very end)
   const long long count = p.nbt != nullptr ? *p.nbt + 1 : 0;
   const uint32_t counter = (uint32_t)(count & 0x7fffffff);
+  RH_BT(0);
 
   // ---- phase 1: rows -> registers, shifted column sums ----
   float hv[RPW][KMAX][4];
@@ -201,13 +216,16 @@ __global__ void __launch_bounds__(256) bn_fused_fwd_kernel(const BnFuseP p) {
     }
   }
   __syncthreads();
+  RH_BT(1);
   for (int i = threadIdx.x; i < 2 * cols; i += blockDim.x) {
     float t = 0.f;
 #pragma unroll
     for (int wv = 0; wv < 8; ++wv) t += smem[(int64_t)wv * 2 * cols + i];
     atomicAdd(p.scratch + i, t);
   }
+  RH_BT(2);
   grid_barrier(arrive, gridDim.x);
+  RH_BT(3);
 
   // ---- phase 2: statistics -> per-column scale / shift, apply from registers ----
   const float n = (float)p.rows;
@@ -276,6 +294,7 @@ __global__ void __launch_bounds__(256) bn_fused_fwd_kernel(const BnFuseP p) {
   }
 
   // ---- the last CTA out publishes the statistics and leaves the scratch zeroed ----
+  RH_BT(4);
   if (!last_to_leave(depart, gridDim.x, &sm_flag)) return;
   for (int c = threadIdx.x; c < cols; c += blockDim.x) {
     const float t1 = __ldcg(p.scratch + c), t2 = __ldcg(p.scratch + cols + c);
@@ -298,6 +317,7 @@ __global__ void __launch_bounds__(256) bn_fused_fwd_kernel(const BnFuseP p) {
     *arrive = 0u;
     *depart = 0u;
   }
+  RH_BT(5);
 }
 
 // =====================================================================================================
@@ -573,6 +593,10 @@ static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) 
 
 using namespace rh;
 
+#ifdef RH_BN_TRACE
+unsigned long long* g_bn_trace = nullptr;
+#endif
+
 extern "C" int64_t rh_bn_fused_scratch_floats(int cols) { return 3 * (int64_t)cols + 8; }
 
 extern "C" int rh_bn_fused_supported(int64_t rows, int cols, int head) {
@@ -620,6 +644,9 @@ extern "C" int rh_bn_act_fused_fwd(const float* h, int64_t h_ld, int64_t rows, i
   p.dice_eps = dice_eps; p.p_drop = p_drop; p.seed = dropout_seed; p.running_mean = running_mean; p.running_var = running_var;
   p.nbt = reinterpret_cast<long long*>(num_batches_tracked); p.momentum = momentum; p.stats = stats; p.scratch = scratch; p.y = y; p.y_ld = y_ld;
   p.head_w = head_w; p.head_b = head_b; p.e0 = extra0; p.e1 = extra1; p.apply_sigmoid = apply_sigmoid; p.head_out = head_out;
+#ifdef RH_BN_TRACE
+  p.trace = g_bn_trace;
+#endif
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = (size_t)8 * 2 * cols * sizeof(float);
   if (head) RH_FUSE_DISPATCH(bn_fused_fwd_kernel, true);

@@ -142,24 +142,26 @@ __global__ void __launch_bounds__(256) crossmix_mid2_fwd_kernel(const float* __r
   }
 }
 
-// out = x0 * (u + bias) + xl     (bias may be NULL)
+// bias_outside == 0: out = x0 * (u + bias) + xl  (CrossNetMix);   != 0: out = x0 * u + bias + xl  (CrossNetV2).   bias may be NULL
 __global__ void __launch_bounds__(256) crossmix_out_fwd_kernel(const float* __restrict__ x0, int64_t ld0, const float* __restrict__ xl, int64_t ldl,
-                                                               const float* __restrict__ u, int64_t ldu, const float* __restrict__ bias, int64_t B, int W,
-                                                               float* __restrict__ out, int64_t ldo) {
+                                                               const float* __restrict__ u, int64_t ldu, const float* __restrict__ bias, int bias_outside,
+                                                               int64_t B, int W, float* __restrict__ out, int64_t ldo) {
   const int64_t total = B * W;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t b = i / W;
     const int w = (int)(i - b * W);
     const float bb = bias != nullptr ? __ldg(bias + w) : 0.f;
-    out[b * ldo + w] = fmaf(__ldg(x0 + b * ld0 + w), __ldg(u + b * ldu + w) + bb, __ldg(xl + b * ldl + w));
+    const float uv = __ldg(u + b * ldu + w);
+    out[b * ldo + w] = bias_outside ? fmaf(__ldg(x0 + b * ld0 + w), uv, bb + __ldg(xl + b * ldl + w)) : fmaf(__ldg(x0 + b * ld0 + w), uv + bb, __ldg(xl + b * ldl + w));
   }
 }
 
 // g = g1 (+ g2);  g_sum = g;  d_u = g * x0;  d_x0_acc += g * (u + bias);  d_bias[w] += sum_b d_u[b, w]
-// block = 32 rows; thread = column w, w + 256, ...
+// (bias_outside: d_x0_acc += g * u;  d_bias[w] += sum_b g[b, w]).   block = 32 rows; thread = column w, w + 256, ...
 __global__ void __launch_bounds__(256) crossmix_out_bwd_kernel(const float* __restrict__ g1, int64_t ldg1, const float* __restrict__ g2, int64_t ldg2,
                                                                const float* __restrict__ x0, int64_t ld0, const float* __restrict__ u, int64_t ldu,
-                                                               const float* __restrict__ bias, int64_t B, int W, float* __restrict__ g_sum, int64_t ldgs,
+                                                               const float* __restrict__ bias, int bias_outside, int64_t B, int W, float* __restrict__ g_sum,
+                                                               int64_t ldgs,
                                                                float* __restrict__ d_u, int64_t lddu, float* __restrict__ d_x0_acc, int64_t ldx,
                                                                float* __restrict__ d_bias) {
   const int64_t r0 = (int64_t)blockIdx.x * 32;
@@ -173,8 +175,8 @@ __global__ void __launch_bounds__(256) crossmix_out_bwd_kernel(const float* __re
       if (g_sum != nullptr) g_sum[b * ldgs + w] = g;
       const float du = g * __ldg(x0 + b * ld0 + w);
       d_u[b * lddu + w] = du;
-      acc += du;
-      d_x0_acc[b * ldx + w] += g * (__ldg(u + b * ldu + w) + bb);
+      acc += bias_outside ? g : du;
+      d_x0_acc[b * ldx + w] += g * (__ldg(u + b * ldu + w) + (bias_outside ? 0.f : bb));
     }
     if (d_bias != nullptr) atomicAdd(d_bias + w, acc);
   }
@@ -318,26 +320,26 @@ extern "C" int rh_crossmix_mid2_fwd(const float* P, const float* s, int64_t batc
 }
 
 extern "C" int rh_crossmix_out_fwd(const float* x0, int64_t ld0, const float* xl, int64_t ldl, const float* u, int64_t ldu, const float* bias,
-                                   int64_t batch, int width, float* out, int64_t ldo, void* stream) {
+                                   int bias_outside, int64_t batch, int width, float* out, int64_t ldo, void* stream) {
   RH_REQUIRE(x0 && xl && u && out && width > 0 && ld0 >= width && ldl >= width && ldu >= width && ldo >= width, RH_ERR_INVALID_ARG,
              "rh_crossmix_out_fwd: bad arguments");
   if (batch <= 0) return RH_OK;
-  crossmix_out_fwd_kernel<<<ew_grid(batch * width), 256, 0, (cudaStream_t)stream>>>(x0, ld0, xl, ldl, u, ldu, bias, batch, width, out, ldo);
+  crossmix_out_fwd_kernel<<<ew_grid(batch * width), 256, 0, (cudaStream_t)stream>>>(x0, ld0, xl, ldl, u, ldu, bias, bias_outside, batch, width, out, ldo);
   RH_LAUNCH_CHECK();
   return RH_OK;
 }
 
 extern "C" int rh_crossmix_out_bwd(const float* g1, int64_t ldg1, const float* g2, int64_t ldg2, const float* x0, int64_t ld0, const float* u,
-                                   int64_t ldu, const float* bias, int64_t batch, int width, float* g_sum, int64_t ldgs, float* d_u, int64_t lddu,
-                                   float* d_x0_acc, int64_t ldx, float* d_bias, void* stream) {
+                                   int64_t ldu, const float* bias, int bias_outside, int64_t batch, int width, float* g_sum, int64_t ldgs, float* d_u,
+                                   int64_t lddu, float* d_x0_acc, int64_t ldx, float* d_bias, void* stream) {
   RH_REQUIRE(g1 && x0 && u && d_u && d_x0_acc && width > 0, RH_ERR_INVALID_ARG, "rh_crossmix_out_bwd: NULL pointer");
   RH_REQUIRE(ldg1 >= width && ld0 >= width && ldu >= width && lddu >= width && ldx >= width && (g2 == nullptr || ldg2 >= width) &&
                  (g_sum == nullptr || ldgs >= width),
              RH_ERR_INVALID_ARG, "rh_crossmix_out_bwd: leading dimension < width");
   if (batch <= 0) return RH_OK;
   const int grid = (int)((batch + 31) / 32);
-  crossmix_out_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g1, ldg1, g2, ldg2, x0, ld0, u, ldu, bias, batch, width, g_sum, ldgs, d_u, lddu, d_x0_acc,
-                                                                   ldx, d_bias);
+  crossmix_out_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g1, ldg1, g2, ldg2, x0, ld0, u, ldu, bias, bias_outside, batch, width, g_sum, ldgs, d_u, lddu,
+                                                                   d_x0_acc, ldx, d_bias);
   RH_LAUNCH_CHECK();
   return RH_OK;
 }

@@ -73,8 +73,8 @@ PROTOTYPES = {
     "rh_crossmix_unpack_grads": [c_i, c_i, c_i, c_i, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_p, c_p, c_p, c_p],
     "rh_crossmix_mid1_fwd": [c_p, c_i64, c_i64, c_i, c_i, c_p, c_p, c_p],
     "rh_crossmix_mid2_fwd": [c_p, c_p, c_i64, c_i, c_i, c_p, c_p, c_p],
-    "rh_crossmix_out_fwd": [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_i, c_p, c_i64, c_p],
-    "rh_crossmix_out_bwd": [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_i, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_p],
+    "rh_crossmix_out_fwd": [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i, c_i64, c_i, c_p, c_i64, c_p],
+    "rh_crossmix_out_bwd": [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i, c_i64, c_i, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_p],
     "rh_crossmix_mid2_bwd": [c_p, c_i64, c_p, c_p, c_i64, c_i, c_i, c_p, c_p, c_i64, c_p],
     "rh_crossmix_mid1_bwd": [c_p, c_i64, c_p, c_i64, c_i, c_i, c_p, c_i64, c_p],
     "rh_sum3": [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_i64, c_i, c_p, c_i64, c_p],

@@ -476,7 +476,7 @@ class _CrossMix(torch.autograd.Function):
             u = _mm(z, False, ucat[l], False, B, W, Er, tc)
             bl = biases[l].contiguous()
             nxt = _buf(B, W, dev)
-            check(lib.rh_crossmix_out_fwd(x0.data_ptr(), x0.stride(0), xl.data_ptr(), xl.stride(0), u.data_ptr(), u.stride(0), bl.data_ptr(), B, W, nxt.data_ptr(), nxt.stride(0), st), "rh_crossmix_out_fwd")
+            check(lib.rh_crossmix_out_fwd(x0.data_ptr(), x0.stride(0), xl.data_ptr(), xl.stride(0), u.data_ptr(), u.stride(0), bl.data_ptr(), 0, B, W, nxt.data_ptr(), nxt.stride(0), st), "rh_crossmix_out_fwd")
             saved.append((xl, t1, s_, t2, z, u, bl))
             xl = nxt
         ctx.saved_layers = saved
@@ -506,7 +506,7 @@ class _CrossMix(torch.autograd.Function):
             g_sum = _buf(B, W, dev)
             d_u = _buf(B, W, dev)
             check(
-                lib.rh_crossmix_out_bwd(g1.data_ptr(), g1.stride(0), ptr(g2), g2.stride(0) if g2 is not None else 0, x0.data_ptr(), x0.stride(0), u.data_ptr(), u.stride(0), bl.data_ptr(), B, W, g_sum.data_ptr(),
+                lib.rh_crossmix_out_bwd(g1.data_ptr(), g1.stride(0), ptr(g2), g2.stride(0) if g2 is not None else 0, x0.data_ptr(), x0.stride(0), u.data_ptr(), u.stride(0), bl.data_ptr(), 0, B, W, g_sum.data_ptr(),
                                         g_sum.stride(0), d_u.data_ptr(), d_u.stride(0), d_x0.data_ptr(), d_x0.stride(0), d_bias[l].data_ptr(), st), "rh_crossmix_out_bwd")
             d_z = _mm(d_u, False, ucat[l], True, B, Er, W, tc)  # d_z = d_u Ucat
             d_ucat[l] = _mm(d_u, True, z, True, W, Er, B, tc, split_k=split)  # d_Ucat = d_u^T z
@@ -560,7 +560,7 @@ class _CrossV2(torch.autograd.Function):
             u = _mm(xl, False, wp[l], False, B, W, W, tc)
             bl = bs[l].contiguous()
             nxt = _buf(B, W, dev)
-            check(lib.rh_crossmix_out_fwd(x0.data_ptr(), x0.stride(0), xl.data_ptr(), xl.stride(0), u.data_ptr(), u.stride(0), bl.data_ptr(), B, W, nxt.data_ptr(), nxt.stride(0), st), "rh_crossmix_out_fwd")
+            check(lib.rh_crossmix_out_fwd(x0.data_ptr(), x0.stride(0), xl.data_ptr(), xl.stride(0), u.data_ptr(), u.stride(0), bl.data_ptr(), 1, B, W, nxt.data_ptr(), nxt.stride(0), st), "rh_crossmix_out_fwd")
             saved.append((xl, u, bl))
             xl = nxt
         ctx.saved_layers, ctx.wp, ctx.meta, ctx.x0 = saved, wp, (L_, W, B, tc), x0
@@ -582,7 +582,7 @@ class _CrossV2(torch.autograd.Function):
             xl, u, bl = ctx.saved_layers[l]
             g_sum, d_u = _buf(B, W, dev), _buf(B, W, dev)
             check(
-                lib.rh_crossmix_out_bwd(g1.data_ptr(), g1.stride(0), ptr(g2), g2.stride(0) if g2 is not None else 0, x0.data_ptr(), x0.stride(0), u.data_ptr(), u.stride(0), bl.data_ptr(), B, W, g_sum.data_ptr(),
+                lib.rh_crossmix_out_bwd(g1.data_ptr(), g1.stride(0), ptr(g2), g2.stride(0) if g2 is not None else 0, x0.data_ptr(), x0.stride(0), u.data_ptr(), u.stride(0), bl.data_ptr(), 1, B, W, g_sum.data_ptr(),
                                         g_sum.stride(0), d_u.data_ptr(), d_u.stride(0), d_x0.data_ptr(), d_x0.stride(0), d_bias[l].data_ptr(), st), "rh_crossmix_out_bwd")
             g2 = _mm(d_u, False, ctx.wp[l], True, B, W, W, tc)  # d_u W
             d_ws[l] = _mm(d_u, True, xl, True, W, W, B, tc, split_k=split)  # d_u^T x_l
