@@ -366,6 +366,30 @@ int rh_dense_update(int n_tensors, float* const* params, const float* const* gra
                     float beta1, float beta2, float eps, float weight_decay, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Multi-GPU dense step over NVLink peer memory (replaces nn.DataParallel's gradient reduction + optimizer.step() for the
+ * replicated parameters, trainers/ctr_trainer.py:53-55,97-99): all-reduce of the tower gradients fused with the optimiser update.
+ *   staging buffer of a rank: 2 slots of rh_dense_stage_floats(n_tensors, numel) floats (peer-mapped, double-buffered by step parity)
+ *   flags of a rank: 8 int32 (peer-mapped, zero-initialised): flags[s] = last step rank s has published
+ *   epoch_dev: device int32, number of completed reductions (zero-initialised; advanced by rh_dense_reduce_update)
+ *   ticket_dev: device uint32, zero-initialised, left zero
+ * ------------------------------------------------------------------------------------------- */
+int64_t rh_dense_stage_floats(int n_tensors, const int64_t* numel);
+/* Copy this rank's gradients (grads[i] NULL = zeros) and up to 4 extra device scalars into ITS staging slot of this step, then
+ * publish the step number to every rank's flags (peer_flags[s] = rank s's flags array). */
+int rh_dense_pack_signal(int n_tensors, const float* const* grads, const int64_t* numel,
+                         const float* const* extra, int n_extra, float* stage,
+                         int32_t* const* peer_flags, int rank, int world,
+                         const int32_t* epoch_dev, int32_t* ticket_dev, void* stream);
+/* Wait for every rank's publication of this step, sum the W staging slots element-wise in rank order (peer_stage[s] = rank s's staging
+ * buffer) and apply the SGD / Adam / Adagrad update (kinds and device scalars as rh_dense_update); extra_out (n_extra) receives the
+ * summed extras.  Every rank ends with bit-identical parameters. */
+int rh_dense_reduce_update(int n_tensors, float* const* params, float* const* state1, float* const* state2, const int64_t* numel,
+                           int n_extra, float* extra_out, const float* const* peer_stage, const int32_t* flags,
+                           int rank, int world, int32_t* epoch_dev, int32_t* ticket_dev,
+                           int kind, const float* lr_dev, const float* bias_corr_dev,
+                           float beta1, float beta2, float eps, float weight_decay, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Tower GEMM on the tcgen05 tensor cores, fp32-accurate (3xTF32: hi*hi + hi*lo + lo*hi, fp32 accumulators in TMEM).
  *   C[M, N] (+)= A[M, K] * B[N, K]^T (+ bias[N])          — the Linear layers of MLP.forward / backward
  *   (reference basic/layers.py:281-292; ATen addmm / mm there).

@@ -111,3 +111,49 @@ def test_two_gpu_sharded_step(kind, variant):
         if "running_" in k or "num_batches" in k:
             continue
         assert torch.equal(v, out[0]["sd"][k]), k
+
+
+def _worker_hybrid(rank, world, port, allreduce, out):
+    if PKG not in sys.path:
+        sys.path.insert(0, PKG)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), RECHUB_B200_ROWWISE_OPT="1", RECHUB_B200_P2P_ALLREDUCE=allreduce)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from torch_rechub.b200 import _lib
+    from torch_rechub.trainers import CTRTrainer
+    model = _make("deepfm")
+    trainer = CTRTrainer(model, device=str(dev))  # Adam lr 1e-3 weight_decay 1e-5 -> row-wise Adam on the tables + fused dense step
+    assert trainer._dist is not None and (trainer._dist.peer_reduce is not None) == (allreduce == "1")
+    model.train()
+    losses = []
+    for step in range(3):
+        x, y = _batch(rank, step)
+        losses.append(float(trainer._train_step({k: v.to(dev) for k, v in x.items()}, y.to(dev))))
+    _lib.check_errors(dev)
+    sd = trainer._dist.full_state_dict()
+    out[(allreduce, rank)] = {"losses": losses, "sd": {k: v.detach().cpu().clone() for k, v in sd.items()}}
+    dist.barrier()
+    torch.cuda.synchronize()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_peer_memory_allreduce_matches_nccl_route():
+    """Three sharded steps with the hybrid optimiser: the engine's own all-reduce + fused dense update over NVLink peer memory
+    (rh_dense_pack_signal / rh_dense_reduce_update) against the NCCL all-reduce + rh_dense_update route — same losses, same weights
+    (sums in rank order vs a ring: fp32 reassociation only), and bit-identical replicated weights on both ranks."""
+    world = 2
+    out = mp.get_context("spawn").Manager().dict()
+    for variant in ("1", "0"):
+        mp.spawn(_worker_hybrid, args=(world, _free_port(), variant, out), nprocs=world, join=True)
+    a, b = out[("1", 0)], out[("0", 0)]
+    assert all(abs(x - y) <= 1e-6 for x, y in zip(a["losses"], b["losses"])), (a["losses"], b["losses"])
+    for k, v in a["sd"].items():
+        if "num_batches" in k:
+            continue
+        assert torch.allclose(v, b["sd"][k], rtol=1e-4, atol=2e-6), (k, (v - b["sd"][k]).abs().max())
+    for k, v in out[("1", 1)]["sd"].items():
+        if "running_" in k or "num_batches" in k:
+            continue
+        assert torch.equal(v, a["sd"][k]), k

@@ -1,0 +1,228 @@
+// rh_dist.cu — the dense half of the multi-GPU step without a collective library: all-reduce of the replicated parameters'
+// gradients over NVLink peer memory FUSED with the optimiser update.
+//
+// Reference semantics replaced: nn.DataParallel's gradient reduction to device 0 + optimizer.step() (trainers/ctr_trainer.py:53-55,
+// 97-99).  The sharded engine (b200/dist.py) needs, once per step, the SUM over ranks of ~0.6 MB of tower gradients (+ the loss
+// scalar).  NCCL's ring all-reduce spends 21.6 us on it at 2 GPUs — pure latency (profiles/r01c_warm_kernel_times_n2_direct.txt).
+// Here:
+//   rh_dense_pack_signal        every rank copies its gradients (and extra device scalars) into ITS peer-mapped staging buffer
+//                               (double-buffered by step parity), then the last CTA to finish stores the step number into its flag
+//                               slot on every peer (st.release.sys after __threadfence_system).
+//   rh_dense_reduce_update      waits until every peer's flag shows this step (ld.acquire.sys spins on LOCAL memory), then each
+//                               element is the sum over ranks IN RANK ORDER of the peers' staging buffers (ld.global over NVLink) —
+//                               identical bits on every rank — and goes straight into the SGD / Adam / Adagrad update of the
+//                               parameter (rh_dense_update's arithmetic).  The summed extras are written out for the host.
+// One-shot (every rank reads all W copies): (W - 1) x 0.6 MB inbound per GPU — 4 MB at 8 ranks, ~6 us at NVLink rates, no second
+// exchange.  Step numbers only grow, so flags never need resetting; a buffer of parity p is rewritten two steps later, after this
+// rank has seen every peer's NEXT signal, which the peer issues after its reads of step p completed (stream order).
+// Everything is static-shaped and reads its step number from device memory: CUDA-graph capturable.
+#include "rh_common.cuh"
+
+namespace rh {
+
+constexpr int kMaxPackTensors = 96;
+constexpr int kMaxRanks = 8;
+
+struct PackP {
+  const float* g[kMaxPackTensors];   // gradient of tensor i or NULL (contributes zeros)
+  int32_t n[kMaxPackTensors];
+  int32_t off[kMaxPackTensors];      // float offset inside a staging slot
+  const float* extra[4];
+  int32_t n_tensors, n_extra, total;  // total = floats per slot (tensors + extras), padded to 4
+  float* stage;                       // MY staging buffer: 2 slots of `total` floats
+  int32_t* peer_flags[kMaxRanks];     // flags array (kMaxRanks ints) of every rank (peer-mapped); I write element [rank]
+  int32_t rank, world;
+  const int32_t* epoch;               // completed all-reduces so far (device)
+  unsigned* ticket;                   // zero on entry, left zero
+};
+
+__device__ __forceinline__ void st_release_sys(int32_t* p, int32_t v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int32_t ld_acquire_sys(const int32_t* p) {
+  int32_t v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(256) dense_pack_signal_kernel(const __grid_constant__ PackP p) {
+  __shared__ int is_last;
+  const int e = *p.epoch + 1;
+  float* slot = p.stage + (size_t)(e & 1) * p.total;
+  for (int ti = blockIdx.y; ti < p.n_tensors; ti += gridDim.y) {
+    const float* g = p.g[ti];
+    float* dst = slot + p.off[ti];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n[ti]; i += gridDim.x * blockDim.x) dst[i] = g != nullptr ? g[i] : 0.f;
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0 && (int)threadIdx.x < p.n_extra) slot[p.total - 4 + threadIdx.x] = *p.extra[threadIdx.x];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(p.ticket, 1u) == gridDim.x * gridDim.y - 1) ? 1 : 0;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence_system();
+  if ((int)threadIdx.x < p.world) st_release_sys(p.peer_flags[threadIdx.x] + p.rank, e);
+  if (threadIdx.x == 0) *p.ticket = 0u;
+}
+
+struct ReduceP {
+  float* w[kMaxPackTensors];
+  float* s1[kMaxPackTensors];
+  float* s2[kMaxPackTensors];
+  int32_t n[kMaxPackTensors];
+  int32_t off[kMaxPackTensors];
+  int32_t n_tensors, n_extra, total;
+  const float* peer_stage[kMaxRanks];  // staging buffer (2 slots) of every rank, in rank order (peer-mapped; [rank] is local)
+  const int32_t* flags;                // MY flags array: flags[s] = last step rank s has published
+  int32_t rank, world;
+  int32_t* epoch;
+  unsigned* ticket;
+  float* extra_out;                    // (n_extra) summed extras
+  int kind;
+  float beta1, beta2, eps, wd;
+  const float* lr_dev;
+  const float* bc_dev;
+};
+
+__global__ void __launch_bounds__(256) dense_reduce_update_kernel(const __grid_constant__ ReduceP p) {
+  __shared__ int is_last;
+  const int e = *p.epoch + 1;
+  if ((int)threadIdx.x < p.world) {
+    while (ld_acquire_sys(p.flags + threadIdx.x) < e) __nanosleep(64);
+  }
+  __syncthreads();
+  const size_t slot = (size_t)(e & 1) * p.total;
+  const float lr = *p.lr_dev;
+  const float bc1 = p.kind == 1 ? p.bc_dev[0] : 1.f, bc2s = p.kind == 1 ? p.bc_dev[1] : 1.f;
+  for (int ti = blockIdx.y; ti < p.n_tensors; ti += gridDim.y) {
+    float* w = p.w[ti];
+    float* s1 = p.s1[ti];
+    float* s2 = p.s2[ti];
+    const size_t base = slot + p.off[ti];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n[ti]; i += gridDim.x * blockDim.x) {
+      float g = 0.f;
+      for (int s = 0; s < p.world; ++s) g += __ldcg(p.peer_stage[s] + base + i);  // rank order: identical sums everywhere
+      float wv = w[i];
+      float gr = fmaf(p.wd, wv, g);
+      if (p.kind == 0) {
+        wv -= lr * gr;
+      } else if (p.kind == 1) {
+        const float m = p.beta1 * s1[i] + (1.f - p.beta1) * gr;
+        const float v = p.beta2 * s2[i] + (1.f - p.beta2) * gr * gr;
+        s1[i] = m;
+        s2[i] = v;
+        wv -= (lr / bc1) * (m / (sqrtf(v) / bc2s + p.eps));
+      } else {
+        const float acc = s1[i] + gr * gr;
+        s1[i] = acc;
+        wv -= lr * gr / (sqrtf(acc) + p.eps);
+      }
+      w[i] = wv;
+    }
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0 && (int)threadIdx.x < p.n_extra) {
+    float t = 0.f;
+    for (int s = 0; s < p.world; ++s) t += __ldcg(p.peer_stage[s] + slot + p.total - 4 + threadIdx.x);
+    p.extra_out[threadIdx.x] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(p.ticket, 1u) == gridDim.x * gridDim.y - 1) ? 1 : 0;
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    *p.epoch = e;  // every CTA of this launch has read the old value (it is past its loops)
+    *p.ticket = 0u;
+  }
+}
+
+}  // namespace rh
+
+using namespace rh;
+
+extern "C" int64_t rh_dense_stage_floats(int n_tensors, const int64_t* numel) {
+  int64_t t = 0;
+  for (int i = 0; i < n_tensors; ++i) t += (numel[i] + 3) / 4 * 4;
+  return t + 4;  // + up to 4 extra scalars
+}
+
+static int layout(int n_tensors, const int64_t* numel, int32_t* n, int32_t* off, int32_t* total) {
+  RH_REQUIRE(n_tensors > 0 && n_tensors <= kMaxPackTensors, RH_ERR_UNSUPPORTED, "rh_dense_*: %d tensors not in [1,%d]", n_tensors, kMaxPackTensors);
+  int64_t t = 0;
+  for (int i = 0; i < n_tensors; ++i) {
+    RH_REQUIRE(numel[i] >= 0 && numel[i] < ((int64_t)1 << 30), RH_ERR_INVALID_ARG, "rh_dense_*: tensor %d too large", i);
+    n[i] = (int32_t)numel[i];
+    off[i] = (int32_t)t;
+    t += (numel[i] + 3) / 4 * 4;
+  }
+  RH_REQUIRE(t + 4 < ((int64_t)1 << 31), RH_ERR_UNSUPPORTED, "rh_dense_*: staging slot too large");
+  *total = (int32_t)(t + 4);
+  return RH_OK;
+}
+
+extern "C" int rh_dense_pack_signal(int n_tensors, const float* const* grads, const int64_t* numel, const float* const* extra, int n_extra, float* stage,
+                                    int32_t* const* peer_flags, int rank, int world, const int32_t* epoch_dev, int32_t* ticket_dev, void* stream) {
+  RH_REQUIRE(grads && numel && stage && peer_flags && epoch_dev && ticket_dev, RH_ERR_INVALID_ARG, "rh_dense_pack_signal: NULL pointer");
+  RH_REQUIRE(world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world && n_extra >= 0 && n_extra <= 4, RH_ERR_INVALID_ARG, "rh_dense_pack_signal: bad rank/world/extras");
+  static thread_local PackP p;
+  memset(&p, 0, sizeof(p));
+  int rc = layout(n_tensors, numel, p.n, p.off, &p.total);
+  if (rc != RH_OK) return rc;
+  int64_t biggest = 1;
+  for (int i = 0; i < n_tensors; ++i) {
+    p.g[i] = grads[i];
+    if (numel[i] > biggest) biggest = numel[i];
+  }
+  for (int i = 0; i < n_extra; ++i) {
+    RH_REQUIRE(extra != nullptr && extra[i] != nullptr, RH_ERR_INVALID_ARG, "rh_dense_pack_signal: extra %d NULL", i);
+    p.extra[i] = extra[i];
+  }
+  for (int s = 0; s < world; ++s) {
+    RH_REQUIRE(peer_flags[s] != nullptr, RH_ERR_INVALID_ARG, "rh_dense_pack_signal: flags of rank %d NULL", s);
+    p.peer_flags[s] = peer_flags[s];
+  }
+  p.n_tensors = n_tensors; p.n_extra = n_extra; p.stage = stage; p.rank = rank; p.world = world; p.epoch = epoch_dev;
+  p.ticket = reinterpret_cast<unsigned*>(ticket_dev);
+  int gx = (int)((biggest + 255) / 256);
+  if (gx > 256) gx = 256;
+  const int gy = n_tensors < 32 ? n_tensors : 32;
+  dense_pack_signal_kernel<<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>(p);
+  RH_LAUNCH_CHECK();
+  return RH_OK;
+}
+
+extern "C" int rh_dense_reduce_update(int n_tensors, float* const* params, float* const* state1, float* const* state2, const int64_t* numel, int n_extra,
+                                      float* extra_out, const float* const* peer_stage, const int32_t* flags, int rank, int world, int32_t* epoch_dev,
+                                      int32_t* ticket_dev, int kind, const float* lr_dev, const float* bias_corr_dev, float beta1, float beta2, float eps,
+                                      float weight_decay, void* stream) {
+  RH_REQUIRE(params && numel && peer_stage && flags && epoch_dev && ticket_dev && lr_dev, RH_ERR_INVALID_ARG, "rh_dense_reduce_update: NULL pointer");
+  RH_REQUIRE(world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world && n_extra >= 0 && n_extra <= 4 && (n_extra == 0 || extra_out), RH_ERR_INVALID_ARG,
+             "rh_dense_reduce_update: bad rank/world/extras");
+  RH_REQUIRE(kind >= 0 && kind <= 2 && (kind != 1 || bias_corr_dev != nullptr) && (kind == 0 || state1 != nullptr) && (kind != 1 || state2 != nullptr), RH_ERR_INVALID_ARG,
+             "rh_dense_reduce_update: optimiser kind / state");
+  static thread_local ReduceP p;
+  memset(&p, 0, sizeof(p));
+  int rc = layout(n_tensors, numel, p.n, p.off, &p.total);
+  if (rc != RH_OK) return rc;
+  int64_t biggest = 1;
+  for (int i = 0; i < n_tensors; ++i) {
+    RH_REQUIRE(params[i] != nullptr, RH_ERR_INVALID_ARG, "rh_dense_reduce_update: param %d NULL", i);
+    p.w[i] = params[i];
+    p.s1[i] = state1 ? state1[i] : nullptr;
+    p.s2[i] = state2 ? state2[i] : nullptr;
+    RH_REQUIRE(kind == 0 || p.s1[i], RH_ERR_INVALID_ARG, "rh_dense_reduce_update: state1[%d] NULL", i);
+    RH_REQUIRE(kind != 1 || p.s2[i], RH_ERR_INVALID_ARG, "rh_dense_reduce_update: state2[%d] NULL", i);
+    if (numel[i] > biggest) biggest = numel[i];
+  }
+  for (int s = 0; s < world; ++s) {
+    RH_REQUIRE(peer_stage[s] != nullptr, RH_ERR_INVALID_ARG, "rh_dense_reduce_update: staging buffer of rank %d NULL", s);
+    p.peer_stage[s] = peer_stage[s];
+  }
+  p.n_tensors = n_tensors; p.n_extra = n_extra; p.flags = flags; p.rank = rank; p.world = world; p.epoch = epoch_dev;
+  p.ticket = reinterpret_cast<unsigned*>(ticket_dev); p.extra_out = extra_out; p.kind = kind; p.beta1 = beta1; p.beta2 = beta2; p.eps = eps;
+  p.wd = weight_decay; p.lr_dev = lr_dev; p.bc_dev = bias_corr_dev;
+  int gx = (int)((biggest + 255) / 256);
+  if (gx > 512) gx = 512;
+  const int gy = n_tensors < 32 ? n_tensors : 32;
+  dense_reduce_update_kernel<<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>(p);
+  RH_LAUNCH_CHECK();
+  return RH_OK;
+}

@@ -66,6 +66,9 @@ PROTOTYPES = {
     "rh_head_fwd": [c_p, c_i64, c_i64, c_i, c_p, c_p, c_p, c_p, c_i, c_p, c_p],
     "rh_head_bwd": [c_p, c_i64, c_i64, c_i, c_p, c_p, c_p, c_i, c_p, c_i64, c_p, c_p, c_p, c_p],
     "rh_dense_update": [c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_f, c_f, c_f, c_f, c_p],
+    "rh_dense_stage_floats": [c_i, c_p],
+    "rh_dense_pack_signal": [c_i, c_p, c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p],
+    "rh_dense_reduce_update": [c_i, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_i, c_p, c_p, c_f, c_f, c_f, c_f, c_p],
     "rh_gemm_tf32x3": [c_p, c_i64, c_i, c_p, c_i64, c_i, c_p, c_i64, c_i, c_i, c_i, c_p, c_i, c_p],
     "rh_gemm_stats_scratch_floats": [c_i, c_i],
     "rh_gemm_tf32x3_stats": [c_p, c_i64, c_i, c_p, c_i64, c_i, c_p, c_i64, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_f, c_p],
@@ -83,7 +86,7 @@ PROTOTYPES = {
     "rh_din_weighted_sum_bwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p],
     "rh_din_attn_input_bwd": [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_p, c_i, c_i64, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
 }
-_RESTYPES = {"rh_last_error": ctypes.c_char_p, "rh_launch_count": ctypes.c_ulonglong, "rh_gemm_stats_scratch_floats": ctypes.c_int64, "rh_bn_fused_scratch_floats": ctypes.c_int64}
+_RESTYPES = {"rh_last_error": ctypes.c_char_p, "rh_launch_count": ctypes.c_ulonglong, "rh_gemm_stats_scratch_floats": ctypes.c_int64, "rh_bn_fused_scratch_floats": ctypes.c_int64, "rh_dense_stage_floats": ctypes.c_int64}
 
 _lock = threading.Lock()
 _lib = None

@@ -35,6 +35,10 @@ p2p_direct_grads = _flag("RECHUB_B200_P2P_DIRECT_GRADS", True)
 # every rank's executor orders the two branches the same way.  Measured on 2 GPUs only -> off by default.
 p2p_defer_barrier = _flag("RECHUB_B200_P2P_DEFER_BARRIER", False)
 
+# Sharded step: all-reduce the replicated parameters' gradients over NVLink peer memory inside the engine's own kernels, fused with
+# the dense optimiser update (rh_dense_pack_signal + rh_dense_reduce_update) instead of NCCL's all-reduce + rh_dense_update.
+p2p_allreduce = _flag("RECHUB_B200_P2P_ALLREDUCE", True)
+
 # Check the device-side out-of-range-id flag after every forward (one D2H sync per step).  When off the
 # flag is checked at the trainer's existing sync points (``loss.item()``) and by ``check_errors()``.
 eager_bounds_check = _flag("RECHUB_B200_EAGER_BOUNDS_CHECK", False)

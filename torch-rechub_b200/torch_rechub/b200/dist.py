@@ -455,6 +455,8 @@ class DistEngine(object):
         for b in model.buffers():
             if b.dtype.is_floating_point:
                 dist.broadcast(b.data, src=0, group=self.group)
+        self.peer_reduce = None
+        self._setup_peer_reduce()
         n = sum(p.numel() for p in self.dense_params)
         self.n_dense = n
         self.flat = torch.zeros(n + 1, dtype=torch.float32, device=self.device)  # [+1]: the loss rides along
@@ -462,6 +464,67 @@ class DistEngine(object):
         for p in self.dense_params:
             self.views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
+
+    def _setup_peer_reduce(self):
+        """Peer-mapped staging buffers + flags of the engine's own all-reduce (rh_dense_pack_signal / rh_dense_reduce_update)."""
+        from . import _lib, config
+        if self.device.type != "cuda" or not config.p2p_allreduce or not config.p2p_exchange or self.world > 8 or not self.dense_params or len(self.dense_params) > 96:
+            return
+        if any(p.dtype != torch.float32 or not p.is_contiguous() for p in self.dense_params):
+            return
+        import ctypes
+        import torch.distributed._symmetric_memory as symm
+        n = len(self.dense_params)
+        numel = (ctypes.c_int64 * n)(*[p.numel() for p in self.dense_params])
+        total = int(_lib.lib().rh_dense_stage_floats(n, numel))
+        stage = symm.empty(2 * total, dtype=torch.float32, device=self.device)
+        flags = symm.empty(8, dtype=torch.int32, device=self.device)
+        stage.zero_()
+        flags.zero_()
+        h_stage, h_flags = symm.rendezvous(stage, self.group), symm.rendezvous(flags, self.group)
+        self.peer_reduce = {
+            "stage": stage, "flags": flags, "handles": (h_stage, h_flags), "numel": numel, "n": n,
+            "stage_ptrs": (ctypes.c_void_p * self.world)(*[int(p) for p in h_stage.buffer_ptrs]),
+            "flag_ptrs": (ctypes.c_void_p * self.world)(*[int(p) for p in h_flags.buffer_ptrs]),
+            "epoch": torch.zeros(1, dtype=torch.int32, device=self.device), "ticket": torch.zeros(1, dtype=torch.int32, device=self.device),
+            "extra_out": torch.zeros(4, dtype=torch.float32, device=self.device),
+        }
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)  # nobody publishes into flags that are still being zeroed
+
+    def _peer_reduce_step(self, opt, loss):
+        """Pack + publish my gradients, run the owned tables' row-wise update while the peers publish theirs, then the fused
+        wait + sum-in-rank-order + dense optimiser update.  Returns the global mean loss (device scalar)."""
+        import ctypes
+        from . import _lib
+        L, pr, st = _lib.lib(), self.peer_reduce, _lib.stream_ptr()
+        n = pr["n"]
+        grads = (ctypes.c_void_p * n)(*[None if p.grad is None else (p.grad if p.grad.is_contiguous() else p.grad.contiguous()).data_ptr() for p in self.dense_params])
+        keep = [p.grad for p in self.dense_params]  # alive until the launch is queued
+        lw = (loss.detach() * self._inv_world).reshape(1)
+        extra = (ctypes.c_void_p * 1)(lw.data_ptr())
+        _lib.check(L.rh_dense_pack_signal(n, grads, pr["numel"], extra, 1, pr["stage"].data_ptr(), pr["flag_ptrs"], self.rank, self.world, pr["epoch"].data_ptr(), pr["ticket"].data_ptr(), st), "rh_dense_pack_signal")
+        del keep
+        for f in self.fronts:  # every rank's row-gradient REDs must have landed before the owners consume their buffers
+            if f.deferred is not None:
+                f.deferred.barrier()
+                f.deferred = None
+                break
+        for f in self.fronts:
+            f.deferred = None
+        rw, eng = opt.rowwise, opt.dense_engine
+        rw.set_lr(float(opt.dense.param_groups[0]["lr"]))
+        rw.step()  # the owned tables' update does not need the peers' gradients: it overlaps their publication
+        for p in self.dense_params:
+            if id(p) not in eng.state:
+                eng.state[id(p)] = (torch.zeros_like(p, memory_format=torch.contiguous_format) if rw.kind != 0 else None, torch.zeros_like(p, memory_format=torch.contiguous_format) if rw.kind == 1 else None)
+        ptrs = lambda ts: (ctypes.c_void_p * n)(*[None if t is None else t.data_ptr() for t in ts])
+        s1 = ptrs([eng.state[id(p)][0] for p in self.dense_params]) if rw.kind != 0 else None
+        s2 = ptrs([eng.state[id(p)][1] for p in self.dense_params]) if rw.kind == 1 else None
+        _lib.check(
+            L.rh_dense_reduce_update(n, ptrs(self.dense_params), s1, s2, pr["numel"], 1, pr["extra_out"].data_ptr(), pr["stage_ptrs"], pr["flags"].data_ptr(), self.rank, self.world, pr["epoch"].data_ptr(),
+                                     pr["ticket"].data_ptr(), rw.kind, rw._lr_dev.data_ptr(), rw._bc_dev.data_ptr(), rw.betas[0], rw.betas[1], rw.eps, rw.weight_decay, st), "rh_dense_reduce_update")
+        return pr["extra_out"][0]
 
     def _map_gradient_buffers(self):
         """Direct gradients: carve every owned table's persistent gradient buffer out of ONE symmetric-memory pool per rank, so
@@ -515,6 +578,8 @@ class DistEngine(object):
         loss.backward(self._inv_world)  # d(loss / world): the all-reduce SUM then yields the gradient of the global-batch mean
         for f in self.fronts:
             f.defer_barrier = False
+        if split and self.peer_reduce is not None:
+            return self._peer_reduce_step(opt, loss)
         # ONE bucket: [dense gradients ..., loss]; a parameter that got no gradient contributes zeros
         pieces = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in self.dense_params]
         pieces.append((loss.detach() / self.world).reshape(1))
