@@ -147,10 +147,10 @@ def test_reference_own_tests_pass_against_this_package(tmp_path):
     import shutil
     tdir = tmp_path / "suite" / "tests"
     tdir.mkdir(parents=True)
-    for name in ("test_regularization.py", "test_e2e_ranking.py"):
+    for name in ("test_regularization.py", "test_e2e_ranking.py", "test_parquet_dataset.py", "test_pa_array_to_tensor.py"):
         shutil.copy(os.path.join(live.REFERENCE_ROOT, "tests", name), tdir / name)
     env = dict(os.environ, PYTHONPATH=PKG)
-    cmd = [sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", str(tdir), "-k", "regularization or WideDeep or (DCN and not EDCN)"]
+    cmd = [sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", str(tdir), "-k", "regularization or WideDeep or (DCN and not EDCN) or parquet or pa_array or tensor or dataset or Parquet"]
     res = subprocess.run(cmd, env=env, cwd=str(tdir), capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
     assert "passed" in res.stdout
