@@ -464,6 +464,28 @@ int rh_sum3(const float* a, int64_t lda, const float* b, int64_t ldb, const floa
             float* out, int64_t ldo, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Two-tower in-batch negatives (trainers/match_trainer.py:118-140; utils/match.py:104-161).
+ * ------------------------------------------------------------------------------------------- */
+
+/* picks (batch, k) int64: for every row k DISTINCT columns other than the row's own, uniformly at random (order included) —
+ * utils/match.py:136-145's one randperm(B - 1) per row, for all rows in one launch.  The stream is keyed by *seed_dev (device int64: the
+ * caller draws it from its torch Generator, no host sync).  k == batch - 1 lists every other column; otherwise k <= 128. */
+int rh_inbatch_sample_random(int batch, int k, const int64_t* seed_dev, int64_t* picks, void* stream);
+/* Hard negatives (utils/match.py:131-135): the k best-scoring off-diagonal columns of every row of scores (batch, batch; row stride ld),
+ * best first, ties to the lower column. */
+int rh_inbatch_sample_hard(const float* scores, int64_t ld, int batch, int k, int64_t* picks, void* stream);
+/* Cross entropy over [positive | sampled negatives] with the logits taken as dot products of the tower outputs
+ * (gather_inbatch_logits + CrossEntropyLoss(mean), utils/match.py:150-161 + match_trainer.py:137-140):
+ *   prob (batch, 1 + k) = softmax([<u_i, v_i>, <u_i, v_picks[i, :]>]);  loss_rows (batch) = -log prob[:, 0]. */
+int rh_inbatch_ce_fwd(const float* user, int64_t ldu, const float* item, int64_t ldv, int dim, const int64_t* picks,
+                      int batch, int k, float* prob, float* loss_rows, void* stream);
+/* Backward for loss = mean(loss_rows) with upstream gradient *d_loss (device scalar): d_user (batch, dim) is written, d_item
+ * (batch, dim, ZEROED by the caller) accumulates by REDs; the (batch, batch) score gradient is never formed.  dim <= 256. */
+int rh_inbatch_ce_bwd(const float* user, int64_t ldu, const float* item, int64_t ldv, int dim, const int64_t* picks,
+                      const float* prob, const float* d_loss, int batch, int k,
+                      float* d_user, int64_t lddu, float* d_item, int64_t lddv, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * DIN target attention (models/ranking/din.py:77-93, ActivationUnit.forward).
  * ------------------------------------------------------------------------------------------- */
 

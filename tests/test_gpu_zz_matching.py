@@ -130,3 +130,68 @@ def test_match_trainer_inbatch_epoch_on_cuda():
     assert any(not torch.equal(before[k].to(DEV), after[k]) for k in before if k.endswith("weight"))
     emb = model.user_tower({k: v.to(DEV) for k, v in data[0][0].items()})
     assert torch.allclose(emb.norm(dim=1), torch.ones(32, device=DEV), atol=1e-5)
+
+
+@pytest.mark.parametrize("hard,K", [(False, 20), (True, 20), (False, None), (True, 5)])
+def test_fused_inbatch_loss_equals_the_composition(hard, K):
+    """MatchTrainer's in-batch branch on the engine's kernels (one sampling launch, cross entropy + backward from the tower outputs,
+    no dense (B, B) score gradient) against the reference-order composition (matmul -> gather_inbatch_logits -> CrossEntropyLoss)
+    evaluated on the SAME picks: loss and every parameter gradient."""
+    import copy
+    import torch_rechub.basic.features as F
+    import torch_rechub.models.matching as M
+    from torch_rechub.basic.initializers import RandomNormal
+    from torch_rechub.trainers import MatchTrainer
+    from torch_rechub.utils.match import gather_inbatch_logits
+    torch.manual_seed(11)
+    B, L, n_users, n_items = 512, 8, 2000, 3000
+    init = RandomNormal(0, 0.3)
+    user = [F.SparseFeature("user_id", n_users, embed_dim=16, initializer=init), F.SequenceFeature("hist_item_id", n_items, embed_dim=16, pooling="mean", shared_with="item_id")]
+    item = [F.SparseFeature("item_id", n_items, embed_dim=16, initializer=init)]
+    model = M.DSSM(user, item, user_params={"dims": [64, 32]}, item_params={"dims": [64, 32]})
+    ref = copy.deepcopy(model).to(DEV).train()
+    g = torch.Generator().manual_seed(4)
+    x = {"user_id": torch.randint(0, n_users, (B,), generator=g).to(DEV), "item_id": torch.randperm(n_items, generator=g)[:B].to(DEV), "hist_item_id": torch.randint(0, n_items, (B, L), generator=g).to(DEV)}
+    t = MatchTrainer(model, mode=0, in_batch_neg=True, in_batch_neg_ratio=K, hard_negative=hard, sampler_seed=7, n_epoch=1, device=DEV)
+    t.model.train()
+    loss = t._inbatch_loss(x)
+    picks = t.last_picks
+    kk = K if K is not None else B - 1
+    assert picks.shape == (B, kk) and picks.dtype == torch.int64
+    diag = torch.arange(B, device=DEV).unsqueeze(1)
+    assert int(picks.min()) >= 0 and int(picks.max()) < B and not bool((picks == diag).any())
+    assert all(len(set(r)) == kk for r in picks[:64].cpu().tolist())  # without replacement
+    t.model.zero_grad()
+    loss.backward()
+    ue, ie = ref.user_tower(x), ref.item_tower(x)
+    scores = ue @ ie.t()
+    if hard:  # the picks are a hard-negative set of the reference scores (ties within rounding may order either way)
+        masked = scores.detach().clone()
+        masked.fill_diagonal_(float("-inf"))
+        picked = torch.gather(masked, 1, picks)
+        rest = masked.clone()
+        rest.scatter_(1, picks, float("-inf"))
+        assert bool((picked.min(dim=1).values >= rest.max(dim=1).values - 1e-5).all())
+    logits = gather_inbatch_logits(scores, picks)
+    want = torch.nn.CrossEntropyLoss()(logits, torch.zeros(B, dtype=torch.long, device=DEV))
+    assert abs(float(loss) - float(want)) <= 2e-5 * abs(float(want)) + 1e-6
+    want.backward()
+    for (n, p), q in zip(t.model.named_parameters(), ref.parameters()):
+        if q.grad is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, n
+            continue
+        scale = max(float(q.grad.abs().max()), 1e-6)
+        if n.endswith(".bias"):
+            scale = max(scale, 1e-4)
+        assert float((p.grad - q.grad).abs().max()) <= 1e-3 * scale, (n, float((p.grad - q.grad).abs().max()), scale)
+    # the sampler replays under the same seed and moves under another
+    t2 = MatchTrainer(copy.deepcopy(model), mode=0, in_batch_neg=True, in_batch_neg_ratio=K, hard_negative=hard, sampler_seed=7, n_epoch=1, device=DEV)
+    t2.model.train()
+    t2._inbatch_loss(x)
+    if not hard and K is not None:
+        t3 = MatchTrainer(copy.deepcopy(model), mode=0, in_batch_neg=True, in_batch_neg_ratio=K, hard_negative=hard, sampler_seed=8, n_epoch=1, device=DEV)
+        t3.model.train()
+        t3._inbatch_loss(x)
+        assert not torch.equal(t3.last_picks, picks)
+        counts = torch.bincount(picks.flatten(), minlength=B)
+        assert int(counts.min()) > 0 and int(counts.max()) < 4 * kk  # every column is drawn, none dominates

@@ -81,6 +81,10 @@ PROTOTYPES = {
     "rh_crossmix_mid2_bwd": [c_p, c_i64, c_p, c_p, c_i64, c_i, c_i, c_p, c_p, c_i64, c_p],
     "rh_crossmix_mid1_bwd": [c_p, c_i64, c_p, c_i64, c_i, c_i, c_p, c_i64, c_p],
     "rh_sum3": [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_i64, c_i, c_p, c_i64, c_p],
+    "rh_inbatch_sample_random": [c_i, c_i, c_p, c_p, c_p],
+    "rh_inbatch_sample_hard": [c_p, c_i64, c_i, c_i, c_p, c_p],
+    "rh_inbatch_ce_fwd": [c_p, c_i64, c_p, c_i64, c_i, c_p, c_i, c_i, c_p, c_p, c_p],
+    "rh_inbatch_ce_bwd": [c_p, c_i64, c_p, c_i64, c_i, c_p, c_p, c_p, c_i, c_i, c_p, c_i64, c_p, c_i64, c_p],
     "rh_din_attn_input_fwd": [c_p, c_i, c_p, c_i, c_i, c_p, c_p, c_i, c_i64, c_i, c_i, c_p, c_p, c_p, c_p, c_p],
     "rh_din_weighted_sum_fwd": [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p],
     "rh_din_weighted_sum_bwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p],

@@ -1057,3 +1057,88 @@ class _DinWeightedSum(torch.autograd.Function):
 def din_weighted_sum(att_w, hist, use_softmax):
     """``sum_l w[b,l] * hist[b,l,:]`` with optional softmax over l (din.py:86-92)."""
     return _DinWeightedSum.apply(att_w, hist, bool(use_softmax))
+
+
+# =====================================================================================================
+# two-tower in-batch negatives (MatchTrainer's in-batch branch)
+# =====================================================================================================
+class _ScoresNT(torch.autograd.Function):
+    """scores = U V^T (B x B) on the tensor cores (rh_gemm_tf32x3); backward: d_U = dS V, d_V = dS^T U with dS read as stored."""
+
+    @staticmethod
+    def forward(ctx, u, v):
+        u2, v2 = _padded_rows(u), _padded_rows(v)
+        B, D = u2.shape
+        out = _buf(B, v2.shape[0], u2.device)
+        gemm3x(u2, False, v2, False, B, v2.shape[0], D, out=out)
+        ctx.save_for_backward(u2, v2)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_s):
+        u2, v2 = ctx.saved_tensors
+        B, D = u2.shape
+        N = v2.shape[0]
+        g = _padded_rows(d_s)
+        d_u = _mm(g, False, v2, True, B, D, N, True)  # d_U[B, D] = dS[B, N] V[N, D]: V is the MN-major operand as stored
+        d_v = _mm(g, True, u2, True, N, D, B, True, split_k=_split_k_for((N + 127) // 128, 1, (B + 31) // 32, budget=128))  # d_V = dS^T U
+        return d_u, d_v
+
+
+def scores_nt(u, v):
+    """``u @ v.T`` for the in-batch score matrix, or None when the shape is outside the tensor-core kernel."""
+    if not (u.is_cuda and u.dim() == 2 and v.dim() == 2 and u.dtype == torch.float32 and u.shape[0] >= 128 and v.shape[0] >= 128 and u.shape[1] >= 32 and _tc_ok(u.shape[0], _padded_rows(u.detach()))):
+        return None
+    return _ScoresNT.apply(u, v)
+
+
+def inbatch_sample(scores, k, hard, seed_dev):
+    """(B, k) int64 picks by the engine's samplers (``scores`` is only read for hard negatives), or None outside their range."""
+    B = scores.shape[0]
+    if not scores.is_cuda or (not hard and k != B - 1 and k > 128):
+        return None
+    L = _lib.lib()
+    picks = torch.empty((B, k), dtype=torch.int64, device=scores.device)
+    if hard:
+        s2 = _rowmajor(scores.detach())
+        check(L.rh_inbatch_sample_hard(s2.data_ptr(), s2.stride(0), B, k, picks.data_ptr(), stream_ptr()), "rh_inbatch_sample_hard")
+    else:
+        check(L.rh_inbatch_sample_random(B, k, seed_dev.data_ptr(), picks.data_ptr(), stream_ptr()), "rh_inbatch_sample_random")
+    return picks
+
+
+class _InbatchCE(torch.autograd.Function):
+    """mean cross entropy over [positive | picks] with logits = <u_i, v_c> (rh_inbatch_ce_fwd / _bwd): no gathered logits tensor, no
+    dense (B, B) score gradient."""
+
+    @staticmethod
+    def forward(ctx, u, v, picks):
+        L = _lib.lib()
+        u2, v2 = _rowmajor(u), _rowmajor(v)
+        B, D = u2.shape
+        K = picks.shape[1]
+        prob = torch.empty((B, K + 1), dtype=torch.float32, device=u2.device)
+        rows = torch.empty(B, dtype=torch.float32, device=u2.device)
+        check(L.rh_inbatch_ce_fwd(u2.data_ptr(), u2.stride(0), v2.data_ptr(), v2.stride(0), D, picks.data_ptr(), B, K, prob.data_ptr(), rows.data_ptr(), stream_ptr()), "rh_inbatch_ce_fwd")
+        ctx.save_for_backward(u2, v2, picks, prob)
+        return rows.mean()
+
+    @staticmethod
+    def backward(ctx, d_loss):
+        L = _lib.lib()
+        u2, v2, picks, prob = ctx.saved_tensors
+        B, D = u2.shape
+        K = picks.shape[1]
+        d_u = torch.empty((B, D), dtype=torch.float32, device=u2.device)
+        d_v = torch.zeros((v2.shape[0], D), dtype=torch.float32, device=u2.device)
+        g = d_loss.detach().reshape(1).float().contiguous()
+        check(L.rh_inbatch_ce_bwd(u2.data_ptr(), u2.stride(0), v2.data_ptr(), v2.stride(0), D, picks.data_ptr(), prob.data_ptr(), g.data_ptr(), B, K, d_u.data_ptr(), D, d_v.data_ptr(), D, stream_ptr()),
+              "rh_inbatch_ce_bwd")
+        return d_u, d_v, None
+
+
+def inbatch_cross_entropy(u, v, picks):
+    """CrossEntropyLoss(mean) over ``[<u_i, v_i> | <u_i, v_picks[i, :]>]`` (positive in column 0), fused; None outside the kernel's range."""
+    if not (u.is_cuda and u.dim() == 2 and v.dim() == 2 and u.dtype == torch.float32 and v.dtype == torch.float32 and u.shape[1] == v.shape[1] and u.shape[1] <= 256 and u.shape[0] == v.shape[0]):
+        return None
+    return _InbatchCE.apply(u, v, picks.contiguous())

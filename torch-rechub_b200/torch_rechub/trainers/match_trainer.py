@@ -120,12 +120,39 @@ class MatchTrainer(object):
         user, item = towers
         if user.dim() != 2 or item.dim() != 2:
             raise ValueError(f"In-batch negative sampling requires 2D embeddings, got shapes {user.shape} and {item.shape}")
+        if user.is_cuda and self.mode != 1:
+            fused = self._inbatch_loss_cuda(user, item)
+            if fused is not None:
+                return fused
         scores = torch.matmul(user, item.t())
         picks = inbatch_negative_sampling(scores, neg_ratio=self.in_batch_neg_ratio, hard_negative=self.hard_negative, generator=self._sampler_generator)
         logits = gather_inbatch_logits(scores, picks)
         if self.mode == 1:
             return self.criterion(logits[:, 0], logits[:, 1:], in_batch_neg=True)
         return self.criterion(logits, torch.zeros(logits.size(0), dtype=torch.long, device=self.device))  # the positive is column 0
+
+    def _inbatch_loss_cuda(self, user, item):
+        """The same loss on the engine's kernels: the (B, B) scores only when hard negatives need them (tensor-core GEMM), one
+        sampling launch for all rows, cross entropy + its backward straight from the tower outputs (no gathered logits, no dense
+        score gradient).  None when a shape is outside the kernels (the composition above runs then)."""
+        from ..b200 import ops
+        n = user.size(0)
+        if n <= 1 or item.size(0) != n:
+            return None
+        k = self.in_batch_neg_ratio if (self.in_batch_neg_ratio is not None and 0 < self.in_batch_neg_ratio <= n - 1) else n - 1
+        seed = None
+        scores = user.detach()
+        if self.hard_negative:
+            scores = ops.scores_nt(user.detach(), item.detach())
+            if scores is None:
+                scores = torch.matmul(user.detach(), item.detach().t())
+        else:
+            seed = torch.randint(0, 2**62, (1,), device=user.device, generator=self._sampler_generator)  # advances the sampler's stream
+        picks = ops.inbatch_sample(scores if self.hard_negative else user, k, self.hard_negative, seed)
+        if picks is None:
+            return None
+        self.last_picks = picks
+        return ops.inbatch_cross_entropy(user, item, picks)
 
     def _loss(self, x_dict, y):
         if self.in_batch_neg:
