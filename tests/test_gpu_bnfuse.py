@@ -62,11 +62,10 @@ def test_fused_forward_and_backward_against_float64(rows, cols, act):
     gd, bd = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
     ad = alpha.double().requires_grad_(True) if alpha is not None else None
     ref = _ref_forward(hd, gd, bd, act, ad)
-    for launch in range(2):  # twice: the scratch (sums + barrier counters) must come back to zero
+    for launch in range(3):  # three times: the two parity buffers of the scratch take turns, arrivals keep counting
         rm, rv, nbt = rm0.clone(), rv0.clone(), torch.tensor(6 + launch, device=DEV)
         y, stats, scratch = _call_fwd(h, gamma, beta, act, alpha, 0.0, 0, rm, rv, nbt)
         torch.cuda.synchronize()
-        assert float(scratch.abs().max()) == 0.0
         scale = ref.detach().abs().max().item()
         assert (y.double() - ref.detach()).abs().max().item() <= 2e-5 * scale + 2e-6 * (2000.0 if cols > 0 else 1.0)
         mean_ref, var_ref = hd.detach().mean(0), hd.detach().var(0, unbiased=False)
@@ -87,7 +86,6 @@ def test_fused_forward_and_backward_against_float64(rows, cols, act):
                               ops._bn_fused_scratch(h.device, cols).data_ptr(), d_h.data_ptr(), cols, gb.data_ptr(), gb[cols:].data_ptr(), gb[3 * cols:].data_ptr() if alpha is not None else None, None, None, None,
                               gb[2 * cols:].data_ptr(), _lib.stream_ptr()), "rh_bn_act_fused_bwd")
     torch.cuda.synchronize()
-    assert float(ops._bn_fused_scratch(h.device, cols).abs().max()) == 0.0
     s = hd.grad.abs().max().item()
     assert (d_h.double() - hd.grad).abs().max().item() <= 3e-4 * s + 1e-7, (d_h.double() - hd.grad).abs().max().item() / s
     assert (gb[:cols].double() - gd.grad).abs().max().item() <= 3e-4 * gd.grad.abs().max().item() + 1e-5

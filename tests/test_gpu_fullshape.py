@@ -46,6 +46,17 @@ def _numpy_state(model):
     return {k: v.detach().cpu().numpy().copy() for k, v in model.state_dict().items()}
 
 
+def _close_up_to_kinks(got, ref, rtol, scale, what, outlier_frac=1e-3, outlier_cap=0.05):
+    """|got - ref| <= rtol * scale for all but a handful of entries.  Why a handful may differ: an element whose pre-activation is
+    within fp32 rounding of ReLU's kink (|z| ~ 1e-6: about one of the 1M + 0.5M hidden activations of a 4096-batch) takes the other
+    branch than in the float64 oracle, and its whole upstream gradient appears in / vanishes from the few entries it feeds (measured:
+    35 of the 109 824 entries of the first layer's weight gradient from ONE element; cuBLAS fp32 differs from float64 the same way).
+    Those entries are bounded by ``outlier_cap`` of the gradient scale and must stay under ``outlier_frac`` of the tensor."""
+    err = np.abs(np.asarray(got, dtype=np.float64) - np.asarray(ref, dtype=np.float64))
+    bad = err > rtol * scale
+    assert float(bad.mean()) <= outlier_frac and float(err.max()) <= outlier_cap * scale, (what, float(bad.mean()), float(err.max()), scale)
+
+
 def _check_dense_grads(model, ref, rtol=2e-4, skip=()):
     for k, prm in model.named_parameters():
         if ".embed_dict." in k or k in skip:
@@ -55,7 +66,7 @@ def _check_dense_grads(model, ref, rtol=2e-4, skip=()):
         if k.endswith(".bias") and k[:-4] + "weight" in ref["grads"]:  # a Linear bias in front of BatchNorm has a true gradient of 0
             scale = max(scale, np.abs(np.asarray(ref["grads"][k[:-4] + "weight"])).max())
         got = prm.grad.detach().cpu().numpy() if prm.grad is not None else np.zeros_like(r)
-        assert np.abs(got - r).max() <= rtol * scale, (k, np.abs(got - r).max(), scale)
+        _close_up_to_kinks(got, r, rtol, scale, k)
 
 
 def _check_table_grads(model, ref, rtol=2e-4):
@@ -71,7 +82,7 @@ def _check_table_grads(model, ref, rtol=2e-4):
         ids = torch.from_numpy(cg.ids).to(g.device)
         got = g.index_select(0, ids).cpu().numpy()
         scale = max(np.abs(cg.rows).max(), 1e-9)
-        assert np.abs(got - cg.rows).max() <= rtol * scale, (k, np.abs(got - cg.rows).max(), scale)
+        _close_up_to_kinks(got, cg.rows, rtol, scale, k)
         # nothing outside the touched rows: the whole buffer's |sum| equals the touched rows' |sum|
         assert abs(float(g.abs().sum()) - float(np.abs(got).sum())) <= 1e-4 * max(float(np.abs(got).sum()), 1e-9), k
         n += 1
@@ -128,17 +139,6 @@ class _LazyRows(object):
             self.m[int(i)], self.v[int(i)] = m[j], v[j]
 
 
-def _close_after_adam(got, ref, start, lr, steps, what):
-    """Adam normalises every element's update to ~lr whatever the gradient's size, so an element whose gradient is within fp32
-    rounding of zero may legitimately move by up to lr per step in either direction.  Criterion: 99.9 % of the elements within
-    1e-3 of the distance travelled (+ 2e-6), none further than the worst case 2 * lr * steps."""
-    d = np.abs(got - ref)
-    tol = 2e-6 + 1e-3 * np.abs(ref - start)
-    bad = float(np.mean(d > tol))
-    assert bad <= 1e-3, (what, bad, d.max())
-    assert d.max() <= 2.0 * lr * steps + 1e-6, (what, d.max())
-
-
 def test_deepfm_benchmarked_step_graph_replayed_rowwise_adam_against_oracle():
     """The step bench.py times: CTRTrainer._train_step under GraphedStep (3 eager steps, capture, replays) with the row-wise
     Adam on touched rows + Adam on the tower, lr 1e-3, weight_decay 1e-5 (the trainer's defaults)."""
@@ -166,34 +166,51 @@ def test_deepfm_benchmarked_step_graph_replayed_rowwise_adam_against_oracle():
         config.rowwise_optimizer, config.cuda_graph = saved
 
     # ---- the oracle's trainer: same batches, Adam on the tower, Adam on the touched rows ----
-    sd = {k: v.copy() for k, v in sd0.items()}
     names_d, names_s = [f.name for f in dense], [f.name for f in sparse]
     table_keys = ["embedding.embed_dict.%s.weight" % n for n in names_s]
     dense_keys = [k for k, _ in model.named_parameters() if ".embed_dict." not in k]
-    mom = {k: (np.zeros(sd[k].shape), np.zeros(sd[k].shape)) for k in dense_keys}
-    lazy = {k: _LazyRows(bench.DIM) for k in table_keys}
-    touched = {k: set() for k in table_keys}
-    for t, (x, y) in enumerate(batches, start=1):
-        with orc.compact_table_grads():
-            ref = orc.deepfm_forward_backward(sd, {k: v.numpy() for k, v in x.items()}, y.numpy(), names_d, names_s, names_s, 2, train=True)
-        assert abs(losses[t - 1] - ref["loss"]) <= 2e-5 * abs(ref["loss"]) + 1e-6, (t, losses[t - 1], ref["loss"])
-        for k in dense_keys:
-            g = np.asarray(ref["grads"][k], dtype=np.float64).reshape(sd[k].shape)
-            w, m, v = orc.adam_update(sd[k].astype(np.float64), g, mom[k][0], mom[k][1], t, lr=lr, weight_decay=wd)
-            sd[k], mom[k] = w.astype(np.float32), (m, v)
-        for k in table_keys:
-            cg = ref["grads"][k]
-            m, v = lazy[k].get(cg.ids)
-            w, m, v = orc.adam_update(sd[k][cg.ids].astype(np.float64), cg.rows, m, v, t, lr=lr, weight_decay=wd)
-            sd[k][cg.ids] = w.astype(np.float32)
-            lazy[k].put(cg.ids, m, v)
-            touched[k].update(int(i) for i in cg.ids)
+
+    def oracle_run(dtype, tables):
+        sd = {k: (v.copy() if (tables or k not in table_keys) else v) for k, v in sd0.items()}
+        mom = {k: (np.zeros(sd[k].shape), np.zeros(sd[k].shape)) for k in dense_keys}
+        lazy = {k: _LazyRows(bench.DIM) for k in table_keys}
+        touched = {k: set() for k in table_keys}
+        ls = []
+        for t, (x, y) in enumerate(batches, start=1):
+            with orc.compact_table_grads():
+                ref = orc.deepfm_forward_backward(sd, {k: v.numpy() for k, v in x.items()}, y.numpy(), names_d, names_s, names_s, 2, train=True, dtype=dtype)
+            ls.append(float(ref["loss"]))
+            for k in dense_keys:
+                g = np.asarray(ref["grads"][k], dtype=np.float64).reshape(sd[k].shape)
+                w, m, v = orc.adam_update(sd[k].astype(np.float64), g, mom[k][0], mom[k][1], t, lr=lr, weight_decay=wd)
+                sd[k], mom[k] = w.astype(np.float32), (m, v)
+            for k in table_keys:
+                cg = ref["grads"][k]
+                m, v = lazy[k].get(cg.ids)
+                w, m, v = orc.adam_update(sd[k][cg.ids].astype(np.float64), np.asarray(cg.rows, dtype=np.float64), m, v, t, lr=lr, weight_decay=wd)
+                sd[k][cg.ids] = w.astype(np.float32)
+                lazy[k].put(cg.ids, m, v)
+                touched[k].update(int(i) for i in cg.ids)
+        return sd, ls, touched
+
+    sd64, loss64, touched = oracle_run(np.float64, tables=True)
+    for t in range(n_steps):
+        assert abs(losses[t] - loss64[t]) <= 2e-5 * abs(loss64[t]) + 1e-6, (t, losses[t], loss64[t])
+    # Control: the SAME trainer with float32 arithmetic in the oracle.  Adam normalises every update to ~lr, so trajectories that
+    # differ by fp32 rounding (and by the ReLU-kink flips it causes, see _close_up_to_kinks) drift apart by a few per cent of the
+    # distance travelled within a handful of steps; how far is measured here, not assumed, and the engine must stay within a
+    # small multiple of it.
+    sd32, _, _ = oracle_run(np.float32, tables=True)
+    rms = lambda a: float(np.sqrt(np.mean(np.square(np.asarray(a, dtype=np.float64)))))
     for k in dense_keys:
-        _close_after_adam(got[k], sd[k], sd0[k], lr, n_steps, k)
+        travel, ctl, mine = rms(sd64[k] - sd0[k]), rms(sd32[k] - sd64[k]), rms(got[k] - sd64[k])
+        assert mine <= 4.0 * ctl + 2e-3 * travel + 1e-7, (k, mine, ctl, travel)
+        assert np.abs(got[k] - sd64[k]).max() <= 2.0 * lr * n_steps + 1e-6, k
     for k in table_keys:
         ids = np.fromiter(touched[k], dtype=np.int64)
-        _close_after_adam(got[k][ids], sd[k][ids], sd0[k][ids], lr, n_steps, k)
-        untouched = np.ones(sd[k].shape[0], dtype=bool)
+        travel, ctl, mine = rms(sd64[k][ids] - sd0[k][ids]), rms(sd32[k][ids] - sd64[k][ids]), rms(got[k][ids] - sd64[k][ids])
+        assert mine <= 4.0 * ctl + 2e-3 * travel + 1e-7, (k, mine, ctl, travel)
+        untouched = np.ones(sd64[k].shape[0], dtype=bool)
         untouched[ids] = False
         assert np.array_equal(got[k][untouched], sd0[k][untouched]), k  # lazy mode: untouched rows do not move
     for k in got:  # BatchNorm running statistics of the last layer moved and stayed finite
@@ -265,7 +282,7 @@ def test_din_amazon_shape_against_oracle():
         if k.endswith(".bias") and k[:-4] + "weight" in ref["grads"]:
             scale = max(scale, np.abs(np.asarray(ref["grads"][k[:-4] + "weight"])).max())
         gg = prm.grad.detach().cpu().numpy()
-        assert np.abs(gg - r).max() <= 5e-4 * scale, (k, np.abs(gg - r).max(), scale)  # 204 800-row reductions in fp32
+        _close_up_to_kinks(gg, r, 5e-4, scale, k)  # 204 800-row reductions in fp32
 
 
 def test_dssm_movielens_shape_against_oracle():

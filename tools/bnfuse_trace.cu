@@ -35,7 +35,7 @@ int main() {
       cudaEventSynchronize(e1);
       float ms = 0;
       cudaEventElapsedTime(&ms, e0, e1);
-      const int ctas = (int)((rows + 31) / 32);
+      const int ctas = (int)((rows + 31) / 32);  // 16 warps x 2 rows per CTA
       std::vector<unsigned long long> t((size_t)148 * 8);
       cudaMemcpy(t.data(), trace, t.size() * 8, cudaMemcpyDeviceToHost);
       printf("bn_fused_fwd rows=%lld cols=%d p_drop=%.1f rc=%d ctas=%d event time %.2f us\n", (long long)rows, cols, pdrop, rc, ctas, ms * 1e3);

@@ -13,14 +13,18 @@
 // atomicAdd per column per CTA), the barrier waits until every CTA has published, phase 2 finishes from registers.  The
 // activation `y` of the last hidden layer never exists in HBM in head mode: the head's dot product consumes it in registers.
 //
-// Grid barrier: grid <= number of SMs, one 256-thread CTA each, so all CTAs are co-resident whatever else runs (a spinning
+// Grid barrier: grid <= number of SMs, one 512-thread CTA each, so all CTAs are co-resident whatever else runs (a spinning
 // CTA can only wait for CTAs of its own grid that are resident or about to be placed; nothing queued behind this kernel in
-// its stream can start before it ends).  arrive/depart counters live in the caller's scratch; the last CTA to leave
-// finalises the outputs and re-zeroes the scratch, so graph replays need no memset.
+// its stream can start before it ends).  The scratch holds a launch counter, a never-reset arrival counter and TWO sum buffers
+// used alternately: launch g accumulates into buffer g & 1 and CTA 0 zeroes the other one for launch g + 1, so no CTA has to
+// be "the last one out" and graph replays need no memset.
 //
-// Mapping: warp = row (RPW rows per warp, interleaved by 8), lane = 4 consecutive columns per step, KMAX steps per row:
-// RPW * KMAX * 4 floats of h per thread (x2 in backward).  Shapes beyond that budget (rows > SMs * 8 * RPW) report
+// Mapping: warp = row (RPW rows per warp, interleaved by 16), lane = 4 consecutive columns per step, KMAX steps per row:
+// RPW * KMAX * 4 floats of h per thread (x2 in backward).  Shapes beyond that budget (rows > SMs * 16 * RPW) report
 // rh_bn_fused_supported() == 0 and callers stay on the two-kernel route (DIN's 204 800-row attention MLP).
+// Tuning history (tools/bnfuse_trace.cu, ncu): the first version (256 threads, run-time activation switch inside the unrolled
+// element loops, last-CTA finalisation) spent 8 us in its apply phase at 10 % issue-active — 90 instructions per element, 8 warps
+// per SM — and 2.8 us in the serial tail; 16 warps, a compile-time activation and the parity buffers address exactly those.
 #include "rh_bn_common.cuh"
 
 namespace rh {
@@ -88,30 +92,46 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   return v;
 }
 
+constexpr int kFuseThreads = 512;  // 16 warps: at 8 warps / SM the kernel was bound by instruction latency (ncu: 10 % issue-active)
+constexpr int kFuseWarps = kFuseThreads / 32;
+
+// Scratch layout (floats): [0] generation (launches so far, uint) | [1] arrivals (uint, never reset) | [2..3] spare |
+// two parity buffers of (3 cols + 4) floats: sums | sums | sums | alpha, head bias, spare, spare.
+// Launch g uses buffer g & 1 (zero on entry) and, after its barrier, CTA 0 zeroes buffer (g + 1) & 1 — dirty since launch g - 1 —
+// and stores g + 1.  Nothing has to wait for "the last CTA out".
+struct FuseScratch {
+  unsigned gen;
+  unsigned* arrive;
+  float* sums;   // this launch's buffer
+  float* other;  // the buffer the next launch will use
+};
+__device__ __forceinline__ FuseScratch fuse_scratch(float* scratch, int cols) {
+  FuseScratch f;
+  unsigned* hdr = reinterpret_cast<unsigned*>(scratch);
+  f.gen = hdr[0];
+  f.arrive = hdr + 1;
+  const int per = 3 * cols + 4;
+  f.sums = scratch + 4 + (size_t)(f.gen & 1u) * per;
+  f.other = scratch + 4 + (size_t)((f.gen + 1u) & 1u) * per;
+  return f;
+}
+
 // every CTA of the grid has executed everything before this call once any CTA returns from it
-__device__ __forceinline__ void grid_barrier(unsigned* arrive, unsigned n_ctas) {
+__device__ __forceinline__ void grid_barrier(const FuseScratch& f, unsigned n_ctas) {
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    atomicAdd(arrive, 1u);
-    while (ld_acquire_u32(arrive) < n_ctas) __nanosleep(32);
+    atomicAdd(f.arrive, 1u);
+    const unsigned target = (f.gen + 1u) * n_ctas;  // arrivals only grow: generation g is complete at (g + 1) * n_ctas
+    while ((int)(ld_acquire_u32(f.arrive) - target) < 0) __nanosleep(20);
     __threadfence();
   }
   __syncthreads();
 }
 
-// true in exactly one CTA: the last one to get here (all others are past their last read of the scratch)
-__device__ __forceinline__ bool last_to_leave(unsigned* depart, unsigned n_ctas, int* sm_flag) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    *sm_flag = (atomicAdd(depart, 1u) == n_ctas - 1) ? 1 : 0;
-  }
-  __syncthreads();
-  return *sm_flag != 0;
-}
-
-__device__ __forceinline__ float act_value(int act, float z, float alpha, float ps) {
+template <int ACT>
+__device__ __forceinline__ float act_value(int act_rt, float z, float alpha, float ps) {
+  const int act = ACT >= 0 ? ACT : act_rt;
   switch (act) {
     case ACT_RELU: return fmaxf(z, 0.f);
     case ACT_DICE: return ps * z + (1.f - ps) * alpha * z;
@@ -159,18 +179,18 @@ __device__ __forceinline__ void dice_row_stats(const float (&z)[KMAX][4], int la
 }
 
 // =====================================================================================================
-// forward
+// forward.   ACT: compile-time activation (ACT_RELU / ACT_DICE), or -1 = read p.act (the rarer ones share one instantiation:
+// with the activation a run-time switch inside the fully unrolled element loops the kernel executed ~90 instructions per element)
 // =====================================================================================================
-template <int KMAX, int RPW, bool HEAD>
-__global__ void __launch_bounds__(256) bn_fused_fwd_kernel(const BnFuseP p) {
-  extern __shared__ float smem[];  // [8 warps][2 cols]
-  __shared__ int sm_flag;
+template <int KMAX, int RPW, int ACT, bool HEAD>
+__global__ void __launch_bounds__(kFuseThreads) bn_fused_fwd_kernel(const BnFuseP p) {
+  extern __shared__ float smem[];  // [16 warps][2 cols]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cols = p.cols;
-  const int64_t row0 = (int64_t)blockIdx.x * 8 * RPW;
-  unsigned* arrive = reinterpret_cast<unsigned*>(p.scratch + 3 * cols + 2);
-  unsigned* depart = arrive + 1;
-  // dropout stream id of this forward = num_batches_tracked + 1 (the last CTA stores the incremented value at the very end)
+  const int act = ACT >= 0 ? ACT : p.act;
+  const int64_t row0 = (int64_t)blockIdx.x * kFuseWarps * RPW;
+  const FuseScratch fs = fuse_scratch(p.scratch, cols);
+  // dropout stream id of this forward = num_batches_tracked + 1 (CTA 0 stores the incremented value after the barrier)
   const long long count = p.nbt != nullptr ? *p.nbt + 1 : 0;
   const uint32_t counter = (uint32_t)(count & 0x7fffffff);
   RH_BT(0);
@@ -181,7 +201,7 @@ __global__ void __launch_bounds__(256) bn_fused_fwd_kernel(const BnFuseP p) {
   load_colconst<KMAX>(p.h, lane, cols, sh, 0.f);  // shift = row 0 (keeps fp32 accurate when |mean| >> std)
 #pragma unroll
   for (int i = 0; i < RPW; ++i) {
-    const int64_t row = row0 + warp + 8 * i;
+    const int64_t row = row0 + warp + kFuseWarps * i;
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
       const int c0 = (k * 32 + lane) * 4;
@@ -203,7 +223,7 @@ __global__ void __launch_bounds__(256) bn_fused_fwd_kernel(const BnFuseP p) {
           float s1 = 0.f, s2 = 0.f;
 #pragma unroll
           for (int i = 0; i < RPW; ++i) {
-            if (row0 + warp + 8 * i < p.rows) {
+            if (row0 + warp + kFuseWarps * i < p.rows) {
               const float d = hv[i][k][j] - sh[k][j];
               s1 += d;
               s2 = fmaf(d, d, s2);
@@ -220,11 +240,11 @@ __global__ void __launch_bounds__(256) bn_fused_fwd_kernel(const BnFuseP p) {
   for (int i = threadIdx.x; i < 2 * cols; i += blockDim.x) {
     float t = 0.f;
 #pragma unroll
-    for (int wv = 0; wv < 8; ++wv) t += smem[(int64_t)wv * 2 * cols + i];
-    atomicAdd(p.scratch + i, t);
+    for (int wv = 0; wv < kFuseWarps; ++wv) t += smem[(int64_t)wv * 2 * cols + i];
+    atomicAdd(fs.sums + i, t);
   }
   RH_BT(2);
-  grid_barrier(arrive, gridDim.x);
+  grid_barrier(fs, gridDim.x);
   RH_BT(3);
 
   // ---- phase 2: statistics -> per-column scale / shift, apply from registers ----
@@ -236,16 +256,18 @@ __global__ void __launch_bounds__(256) bn_fused_fwd_kernel(const BnFuseP p) {
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) {
     const int c0 = (k * 32 + lane) * 4;
+    float4 t1 = f4_zero(), t2 = f4_zero();
+    if (c0 < cols) {
+      t1 = __ldcg(reinterpret_cast<const float4*>(fs.sums + c0));
+      t2 = __ldcg(reinterpret_cast<const float4*>(fs.sums + cols + c0));
+    }
+    const float a1[4] = {t1.x, t1.y, t1.z, t1.w}, a2[4] = {t2.x, t2.y, t2.z, t2.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      mu[k][j] = 0.f;
-      if (c0 < cols) {
-        const float t1 = __ldcg(p.scratch + c0 + j), t2 = __ldcg(p.scratch + cols + c0 + j);
-        float v = (t2 - t1 * t1 / n) / n;
-        if (v < 0.f) v = 0.f;
-        mu[k][j] = sh[k][j] + t1 / n;
-        sc[k][j] *= 1.f / sqrtf(v + p.bn_eps);
-      }
+      float v = (a2[j] - a1[j] * a1[j] / n) / n;
+      if (v < 0.f) v = 0.f;
+      mu[k][j] = sh[k][j] + a1[j] / n;
+      sc[k][j] *= 1.f / sqrtf(v + p.bn_eps);
     }
   }
   const float alpha = p.alpha != nullptr ? __ldg(p.alpha) : 0.f;
@@ -254,7 +276,7 @@ __global__ void __launch_bounds__(256) bn_fused_fwd_kernel(const BnFuseP p) {
   const float hb = (HEAD && p.head_b != nullptr) ? __ldg(p.head_b) : 0.f;
 #pragma unroll
   for (int i = 0; i < RPW; ++i) {
-    const int64_t row = row0 + warp + 8 * i;
+    const int64_t row = row0 + warp + kFuseWarps * i;
     if (row >= p.rows) continue;  // warp-uniform
     float z[KMAX][4];
 #pragma unroll
@@ -264,7 +286,7 @@ __global__ void __launch_bounds__(256) bn_fused_fwd_kernel(const BnFuseP p) {
       for (int j = 0; j < 4; ++j) z[k][j] = on ? fmaf(hv[i][k][j] - mu[k][j], sc[k][j], bt[k][j]) : 0.f;
     }
     float m = 0.f, inv_s = 0.f;
-    if (p.act == ACT_DICE) dice_row_stats<KMAX>(z, lane, cols, p.dice_eps, m, inv_s);
+    if (act == ACT_DICE) dice_row_stats<KMAX>(z, lane, cols, p.dice_eps, m, inv_s);
     float acc = 0.f;
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
@@ -274,8 +296,8 @@ __global__ void __launch_bounds__(256) bn_fused_fwd_kernel(const BnFuseP p) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float zz = z[k][j];
-        const float ps = p.act == ACT_DICE ? sigmoidf_precise((zz - m) * inv_s) : 0.f;
-        float v = act_value(p.act, zz, alpha, ps);
+        const float ps = act == ACT_DICE ? sigmoidf_precise((zz - m) * inv_s) : 0.f;
+        float v = act_value<ACT>(p.act, zz, alpha, ps);
         if (drop) v = dropout_keep(p.seed, counter, (uint64_t)row * cols + c0 + j, p.p_drop) ? v * keep_scale : 0.f;
         o[j] = v;
         if (HEAD) acc = fmaf(v, hw[k][j], acc);
@@ -292,12 +314,12 @@ __global__ void __launch_bounds__(256) bn_fused_fwd_kernel(const BnFuseP p) {
       }
     }
   }
-
-  // ---- the last CTA out publishes the statistics and leaves the scratch zeroed ----
   RH_BT(4);
-  if (!last_to_leave(depart, gridDim.x, &sm_flag)) return;
+
+  // ---- CTA 0 publishes the statistics and prepares the scratch of the next launch (concurrently with the other CTAs' phase 2) ----
+  if (blockIdx.x != 0) return;
   for (int c = threadIdx.x; c < cols; c += blockDim.x) {
-    const float t1 = __ldcg(p.scratch + c), t2 = __ldcg(p.scratch + cols + c);
+    const float t1 = __ldcg(fs.sums + c), t2 = __ldcg(fs.sums + cols + c);
     const float mean = __ldg(p.h + c) + t1 / n;
     float v = (t2 - t1 * t1 / n) / n;
     if (v < 0.f) v = 0.f;
@@ -308,14 +330,12 @@ __global__ void __launch_bounds__(256) bn_fused_fwd_kernel(const BnFuseP p) {
       const float unbiased = p.rows > 1 ? v * (n / (n - 1.f)) : v;
       p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * unbiased;
     }
-    p.scratch[c] = 0.f;
-    p.scratch[cols + c] = 0.f;
   }
+  for (int c = threadIdx.x; c < 3 * cols + 4; c += blockDim.x) fs.other[c] = 0.f;
   if (threadIdx.x == 0) {
     if (p.nbt != nullptr) *p.nbt = count;
     p.stats[2 * cols] = __int_as_float((int)counter);
-    *arrive = 0u;
-    *depart = 0u;
+    reinterpret_cast<unsigned*>(p.scratch)[0] = fs.gen + 1u;
   }
   RH_BT(5);
 }
@@ -323,17 +343,16 @@ __global__ void __launch_bounds__(256) bn_fused_fwd_kernel(const BnFuseP p) {
 // =====================================================================================================
 // backward
 // =====================================================================================================
-template <int KMAX, int RPW, bool HEAD>
-__global__ void __launch_bounds__(256) bn_fused_bwd_kernel(const BnFuseP p) {
-  extern __shared__ float smem[];  // [8 warps][NS cols], NS = 3 in head mode else 2
-  __shared__ float sm_alpha[8], sm_hb[8];
-  __shared__ int sm_flag;
+template <int KMAX, int RPW, int ACT, bool HEAD>
+__global__ void __launch_bounds__(kFuseThreads) bn_fused_bwd_kernel(const BnFuseP p) {
+  extern __shared__ float smem[];  // [16 warps][NS cols], NS = 3 in head mode else 2
+  __shared__ float sm_alpha[kFuseWarps], sm_hb[kFuseWarps];
   constexpr int NS = HEAD ? 3 : 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cols = p.cols;
-  const int64_t row0 = (int64_t)blockIdx.x * 8 * RPW;
-  unsigned* arrive = reinterpret_cast<unsigned*>(p.scratch + 3 * cols + 2);
-  unsigned* depart = arrive + 1;
+  const int act = ACT >= 0 ? ACT : p.act;
+  const int64_t row0 = (int64_t)blockIdx.x * kFuseWarps * RPW;
+  const FuseScratch fs = fuse_scratch(p.scratch, cols);
   const uint32_t counter = (uint32_t)__float_as_int(__ldg(p.stats + 2 * cols));
 
   float mu[KMAX][4], rstd[KMAX][4], gam[KMAX][4], bet[KMAX][4], hw[KMAX][4];
@@ -362,7 +381,7 @@ __global__ void __launch_bounds__(256) bn_fused_bwd_kernel(const BnFuseP p) {
   // all loads first
 #pragma unroll
   for (int i = 0; i < RPW; ++i) {
-    const int64_t row = row0 + warp + 8 * i;
+    const int64_t row = row0 + warp + kFuseWarps * i;
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
       const int c0 = (k * 32 + lane) * 4;
@@ -380,7 +399,7 @@ __global__ void __launch_bounds__(256) bn_fused_bwd_kernel(const BnFuseP p) {
   }
 #pragma unroll
   for (int i = 0; i < RPW; ++i) {
-    const int64_t row = row0 + warp + 8 * i;
+    const int64_t row = row0 + warp + kFuseWarps * i;
     if (row >= p.rows) continue;  // warp-uniform
     float g_row = 0.f;
     if (HEAD) {
@@ -406,7 +425,7 @@ __global__ void __launch_bounds__(256) bn_fused_bwd_kernel(const BnFuseP p) {
       }
     }
     float m = 0.f, inv_s = 0.f;
-    if (p.act == ACT_DICE) dice_row_stats<KMAX>(z, lane, cols, p.dice_eps, m, inv_s);
+    if (act == ACT_DICE) dice_row_stats<KMAX>(z, lane, cols, p.dice_eps, m, inv_s);
     // upstream gradient of the activation output (through dropout)
     float da[KMAX][4], pj[KMAX][4];
     float a1 = 0.f, a2 = 0.f;
@@ -423,12 +442,12 @@ __global__ void __launch_bounds__(256) bn_fused_bwd_kernel(const BnFuseP p) {
         g = keep ? g * keep_scale : 0.f;
         da[k][j] = g;
         const float zz = z[k][j];
-        if (p.act == ACT_DICE) pj[k][j] = sigmoidf_precise((zz - m) * inv_s);
+        if (act == ACT_DICE) pj[k][j] = sigmoidf_precise((zz - m) * inv_s);
         if (HEAD) {  // d_w3 += g_row * y, y = dropout(act(z))
-          const float yv = keep ? act_value(p.act, zz, alpha, pj[k][j]) * keep_scale : 0.f;
+          const float yv = keep ? act_value<ACT>(p.act, zz, alpha, pj[k][j]) * keep_scale : 0.f;
           acc_w[k][j] = fmaf(g_row, yv, acc_w[k][j]);
         }
-        if (p.act == ACT_DICE) {
+        if (act == ACT_DICE) {
           const float aj = g * zz * (1.f - alpha) * pj[k][j] * (1.f - pj[k][j]);
           a1 += aj;
           a2 = fmaf(aj, zz - m, a2);
@@ -437,7 +456,7 @@ __global__ void __launch_bounds__(256) bn_fused_bwd_kernel(const BnFuseP p) {
       }
     }
     float k1 = 0.f, k2 = 0.f;
-    if (p.act == ACT_DICE) {
+    if (act == ACT_DICE) {
       a1 = warp_sum(a1);
       a2 = warp_sum(a2);
       k1 = a1 * inv_n * inv_s;
@@ -450,7 +469,7 @@ __global__ void __launch_bounds__(256) bn_fused_bwd_kernel(const BnFuseP p) {
       for (int j = 0; j < 4; ++j) {
         const float zz = z[k][j], g = da[k][j];
         float d;
-        switch (p.act) {
+        switch (act) {
           case ACT_RELU: d = zz > 0.f ? g : 0.f; break;
           case ACT_DICE: {
             const float aj = g * zz * (1.f - alpha) * pj[k][j] * (1.f - pj[k][j]);
@@ -498,20 +517,20 @@ __global__ void __launch_bounds__(256) bn_fused_bwd_kernel(const BnFuseP p) {
   for (int i = threadIdx.x; i < NS * cols; i += blockDim.x) {
     float t = 0.f;
 #pragma unroll
-    for (int wv = 0; wv < 8; ++wv) t += smem[(int64_t)wv * NS * cols + i];
-    atomicAdd(p.scratch + i, t);
+    for (int wv = 0; wv < kFuseWarps; ++wv) t += smem[(int64_t)wv * NS * cols + i];
+    atomicAdd(fs.sums + i, t);
   }
   if (threadIdx.x == 0) {
     float ta = 0.f, tb = 0.f;
 #pragma unroll
-    for (int wv = 0; wv < 8; ++wv) {
+    for (int wv = 0; wv < kFuseWarps; ++wv) {
       ta += sm_alpha[wv];
       tb += sm_hb[wv];
     }
-    if (p.act == ACT_DICE || p.act == ACT_PRELU) atomicAdd(p.scratch + 3 * cols, ta);
-    if (HEAD) atomicAdd(p.scratch + 3 * cols + 1, tb);
+    if (act == ACT_DICE || act == ACT_PRELU) atomicAdd(fs.sums + 3 * cols, ta);
+    if (HEAD) atomicAdd(fs.sums + 3 * cols + 1, tb);
   }
-  grid_barrier(arrive, gridDim.x);
+  grid_barrier(fs, gridDim.x);
 
   // ---- phase 2: d_h = gamma * rstd * (dz - mean(dz) - xhat * mean(dz * xhat)) from registers ----
   const float inv_rows = 1.f / (float)p.rows;
@@ -519,18 +538,17 @@ __global__ void __launch_bounds__(256) bn_fused_bwd_kernel(const BnFuseP p) {
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) {
     const int c0 = (k * 32 + lane) * 4;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      mb[k][j] = mg[k][j] = 0.f;
-      if (c0 < cols) {
-        mb[k][j] = __ldcg(p.scratch + c0 + j) * inv_rows;
-        mg[k][j] = __ldcg(p.scratch + cols + c0 + j) * inv_rows;
-      }
+    float4 t1 = f4_zero(), t2 = f4_zero();
+    if (c0 < cols) {
+      t1 = __ldcg(reinterpret_cast<const float4*>(fs.sums + c0));
+      t2 = __ldcg(reinterpret_cast<const float4*>(fs.sums + cols + c0));
     }
+    mb[k][0] = t1.x * inv_rows; mb[k][1] = t1.y * inv_rows; mb[k][2] = t1.z * inv_rows; mb[k][3] = t1.w * inv_rows;
+    mg[k][0] = t2.x * inv_rows; mg[k][1] = t2.y * inv_rows; mg[k][2] = t2.z * inv_rows; mg[k][3] = t2.w * inv_rows;
   }
 #pragma unroll
   for (int i = 0; i < RPW; ++i) {
-    const int64_t row = row0 + warp + 8 * i;
+    const int64_t row = row0 + warp + kFuseWarps * i;
     if (row >= p.rows) continue;
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
@@ -543,23 +561,19 @@ __global__ void __launch_bounds__(256) bn_fused_bwd_kernel(const BnFuseP p) {
     }
   }
 
-  if (!last_to_leave(depart, gridDim.x, &sm_flag)) return;
+  // ---- CTA 0 writes the parameter gradients and prepares the scratch of the next launch ----
+  if (blockIdx.x != 0) return;
   for (int c = threadIdx.x; c < cols; c += blockDim.x) {
-    if (p.d_beta != nullptr) p.d_beta[c] = __ldcg(p.scratch + c);
-    if (p.d_gamma != nullptr) p.d_gamma[c] = __ldcg(p.scratch + cols + c);
-    if (HEAD && p.d_head_w != nullptr) p.d_head_w[c] = __ldcg(p.scratch + 2 * cols + c);
+    if (p.d_beta != nullptr) p.d_beta[c] = __ldcg(fs.sums + c);
+    if (p.d_gamma != nullptr) p.d_gamma[c] = __ldcg(fs.sums + cols + c);
+    if (HEAD && p.d_head_w != nullptr) p.d_head_w[c] = __ldcg(fs.sums + 2 * cols + c);
     if (p.d_lin_bias != nullptr) p.d_lin_bias[c] = 0.f;  // a Linear bias in front of a batch-statistics BatchNorm: gradient exactly 0
-    p.scratch[c] = 0.f;
-    p.scratch[cols + c] = 0.f;
-    p.scratch[2 * cols + c] = 0.f;
   }
+  for (int c = threadIdx.x; c < 3 * cols + 4; c += blockDim.x) fs.other[c] = 0.f;
   if (threadIdx.x == 0) {
-    if (p.d_alpha != nullptr) *p.d_alpha = __ldcg(p.scratch + 3 * cols);
-    if (HEAD && p.d_head_b != nullptr) *p.d_head_b = __ldcg(p.scratch + 3 * cols + 1);
-    p.scratch[3 * cols] = 0.f;
-    p.scratch[3 * cols + 1] = 0.f;
-    *arrive = 0u;
-    *depart = 0u;
+    if (p.d_alpha != nullptr) *p.d_alpha = __ldcg(fs.sums + 3 * cols);
+    if (HEAD && p.d_head_b != nullptr) *p.d_head_b = __ldcg(fs.sums + 3 * cols + 1);
+    reinterpret_cast<unsigned*>(p.scratch)[0] = fs.gen + 1u;
   }
 }
 
@@ -568,15 +582,18 @@ struct FusePlan {
   int kmax, rpw, grid;
 };
 
+// instantiated (KMAX, RPW): (1, 2) (1, 4) (2, 2) (4, 1) — RPW * KMAX * 8 floats of row data per thread in backward
 static bool plan_for(int64_t rows, int cols, bool head, FusePlan* out) {
   if (rows <= 0 || cols <= 0 || cols % 4 != 0) return false;
   const int steps = (cols + 127) / 128;
   const int kmax = steps <= 1 ? 1 : (steps <= 2 ? 2 : (steps <= 4 ? 4 : 0));
   if (kmax == 0) return false;
-  if (head && cols > 256) return false;  // shared-memory slab of the backward reduction: 8 x 3 x cols floats
+  if (head && cols > 256) return false;  // shared-memory slab of the backward reduction: 16 x 3 x cols floats
   const int sms = num_sms();
-  for (int rpw = 1; rpw * kmax <= 8; rpw *= 2) {
-    const int64_t grid = (rows + 8 * rpw - 1) / (8 * rpw);
+  const int choices[3] = {kmax == 4 ? 1 : 2, kmax == 1 ? 4 : 0, 0};
+  for (int t = 0; t < 3 && choices[t] > 0; ++t) {
+    const int rpw = choices[t];
+    const int64_t grid = (rows + kFuseWarps * rpw - 1) / (kFuseWarps * rpw);
     if (grid <= sms) {
       out->kmax = kmax;
       out->rpw = rpw;
@@ -593,32 +610,38 @@ static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) 
 
 using namespace rh;
 
-#ifdef RH_BN_TRACE
-unsigned long long* g_bn_trace = nullptr;
-#endif
-
-extern "C" int64_t rh_bn_fused_scratch_floats(int cols) { return 3 * (int64_t)cols + 8; }
+extern "C" int64_t rh_bn_fused_scratch_floats(int cols) { return 4 + 2 * (3 * (int64_t)cols + 4); }
 
 extern "C" int rh_bn_fused_supported(int64_t rows, int cols, int head) {
   FusePlan pl;
   return plan_for(rows, cols, head != 0, &pl) ? 1 : 0;
 }
 
-#define RH_FUSE_DISPATCH(KERNEL, HEADV)                                                        \
-  do {                                                                                         \
-    const int key__ = pl.kmax * 16 + pl.rpw;                                                   \
-    switch (key__) {                                                                           \
-      case 1 * 16 + 1: KERNEL<1, 1, HEADV><<<pl.grid, 256, smem, st>>>(p); break;              \
-      case 1 * 16 + 2: KERNEL<1, 2, HEADV><<<pl.grid, 256, smem, st>>>(p); break;              \
-      case 1 * 16 + 4: KERNEL<1, 4, HEADV><<<pl.grid, 256, smem, st>>>(p); break;              \
-      case 1 * 16 + 8: KERNEL<1, 8, HEADV><<<pl.grid, 256, smem, st>>>(p); break;              \
-      case 2 * 16 + 1: KERNEL<2, 1, HEADV><<<pl.grid, 256, smem, st>>>(p); break;              \
-      case 2 * 16 + 2: KERNEL<2, 2, HEADV><<<pl.grid, 256, smem, st>>>(p); break;              \
-      case 2 * 16 + 4: KERNEL<2, 4, HEADV><<<pl.grid, 256, smem, st>>>(p); break;              \
-      case 4 * 16 + 1: KERNEL<4, 1, HEADV><<<pl.grid, 256, smem, st>>>(p); break;              \
-      case 4 * 16 + 2: KERNEL<4, 2, HEADV><<<pl.grid, 256, smem, st>>>(p); break;              \
+#ifdef RH_BN_TRACE
+unsigned long long* g_bn_trace = nullptr;
+#endif
+
+#define RH_FUSE_SHAPES(KERNEL, ACTV, HEADV)                                                                  \
+  do {                                                                                                       \
+    const int key__ = pl.kmax * 16 + pl.rpw;                                                                 \
+    switch (key__) {                                                                                         \
+      case 1 * 16 + 2: KERNEL<1, 2, ACTV, HEADV><<<pl.grid, kFuseThreads, smem, st>>>(p); break;             \
+      case 1 * 16 + 4: KERNEL<1, 4, ACTV, HEADV><<<pl.grid, kFuseThreads, smem, st>>>(p); break;             \
+      case 2 * 16 + 2: KERNEL<2, 2, ACTV, HEADV><<<pl.grid, kFuseThreads, smem, st>>>(p); break;             \
+      case 4 * 16 + 1: KERNEL<4, 1, ACTV, HEADV><<<pl.grid, kFuseThreads, smem, st>>>(p); break;             \
       default: set_error("bn_fused: no instantiation for kmax %d rpw %d", pl.kmax, pl.rpw); return RH_ERR_UNSUPPORTED; \
-    }                                                                                          \
+    }                                                                                                        \
+  } while (0)
+
+#define RH_FUSE_DISPATCH(KERNEL, HEADV)                                      \
+  do {                                                                       \
+    if (smem > 48 * 1024) {                                                  \
+      set_error("bn_fused: %zu bytes of shared memory", smem);               \
+      return RH_ERR_UNSUPPORTED;                                             \
+    }                                                                        \
+    if (act == ACT_RELU) RH_FUSE_SHAPES(KERNEL, ACT_RELU, HEADV);            \
+    else if (act == ACT_DICE) RH_FUSE_SHAPES(KERNEL, ACT_DICE, HEADV);       \
+    else RH_FUSE_SHAPES(KERNEL, -1, HEADV);                                  \
   } while (0)
 
 extern "C" int rh_bn_act_fused_fwd(const float* h, int64_t h_ld, int64_t rows, int cols, float bn_eps, const float* gamma, const float* beta, int act,
@@ -648,7 +671,7 @@ extern "C" int rh_bn_act_fused_fwd(const float* h, int64_t h_ld, int64_t rows, i
   p.trace = g_bn_trace;
 #endif
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t smem = (size_t)8 * 2 * cols * sizeof(float);
+  const size_t smem = (size_t)kFuseWarps * 2 * cols * sizeof(float);
   if (head) RH_FUSE_DISPATCH(bn_fused_fwd_kernel, true);
   else RH_FUSE_DISPATCH(bn_fused_fwd_kernel, false);
   RH_LAUNCH_CHECK();
@@ -679,7 +702,7 @@ extern "C" int rh_bn_act_fused_bwd(const float* h, int64_t h_ld, int64_t rows, i
   p.d_y = d_y; p.d_y_ld = d_y_ld; p.d_h = d_h; p.d_h_ld = d_h_ld; p.d_gamma = d_gamma; p.d_beta = d_beta; p.d_alpha = d_act_param;
   p.d_head_w = d_head_w; p.d_head_b = d_head_b; p.d_extra = d_extra; p.d_lin_bias = d_lin_bias;
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t smem = (size_t)8 * (head ? 3 : 2) * cols * sizeof(float);
+  const size_t smem = (size_t)kFuseWarps * (head ? 3 : 2) * cols * sizeof(float);
   if (head) RH_FUSE_DISPATCH(bn_fused_bwd_kernel, true);
   else RH_FUSE_DISPATCH(bn_fused_bwd_kernel, false);
   RH_LAUNCH_CHECK();

@@ -101,8 +101,9 @@ __device__ __forceinline__ void st_tile4(float* p, const float4& v, bool vec) {
 // What the memory system sees per warp and pass: the ids of S consecutive fields of ONE sample (one 64-byte run of a
 // packed (B, F) id block), S random 64-byte rows, and ONE contiguous S * 64-byte piece of the sample's tile row.
 // FM / LR: registers -> (log2 S + log2 LPR) xor-shuffles; no shared-memory round trip, no block barrier after the loop.
-// The per-field descriptors are staged in shared memory once per block (lanes of a warp index DIFFERENT fields, which
-// would serialise on the constant bank).
+// The per-field descriptors are read from the kernel parameters with a per-lane index (the S field slots of a warp read S
+// different descriptors: an indexed constant load replays S times — measured cheaper than staging them in shared memory
+// behind a block barrier, which cost 17 % of the kernel's stall samples, profiles/r02_ncu_fields_fwd.md).
 // History: v4 (warp = field group x 8 samples, partials through shared memory) ran at 9.6 us for 4096 x 26 rows; the
 // microbenchmark (tools/microbench_gather.cu) does the bare gather + tile store of the same rows in 4.9 us, 2.3 us of
 // which is an empty launch of the same grid.
@@ -110,20 +111,6 @@ __device__ __forceinline__ void st_tile4(float* p, const float4& v, bool vec) {
 template <int LPR>
 __global__ void __launch_bounds__(256) fields_fwd_v5(const __grid_constant__ FwdParams p, const int S) {
   constexpr int CH = 4;  // row loads in flight per lane per chunk
-  __shared__ FieldDev sf[RH_MAX_FIELDS];
-  __shared__ DenseDev sd[RH_MAX_DENSE];
-  {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(p.f);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(sf);
-    const int nw = p.n_fields * (int)(sizeof(FieldDev) / 4);
-    for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
-    const uint32_t* src2 = reinterpret_cast<const uint32_t*>(p.d);
-    uint32_t* dst2 = reinterpret_cast<uint32_t*>(sd);
-    const int nw2 = p.n_dense * (int)(sizeof(DenseDev) / 4);
-    for (int i = threadIdx.x; i < nw2; i += blockDim.x) dst2[i] = src2[i];
-  }
-  __syncthreads();
-
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int q = lane % LPR;
@@ -148,7 +135,7 @@ __global__ void __launch_bounds__(256) fields_fwd_v5(const __grid_constant__ Fwd
       const int f = f0 + j * S;
       rid[j] = -1;
       if (f < p.n_fields && live) {
-        const FieldDev& fd = sf[f];
+        const FieldDev& fd = p.f[f];
         const int64_t id = load_id(fd.ids, (int64_t)b * fd.id_stride, fd.is_i32 != 0);
         if ((uint64_t)id < (uint64_t)fd.vocab) {
           rid[j] = (int32_t)id;
@@ -161,13 +148,13 @@ __global__ void __launch_bounds__(256) fields_fwd_v5(const __grid_constant__ Fwd
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
       v[j] = f4_zero();
-      if (rid[j] >= 0 && lane_on) v[j] = ldg_row16(sf[f0 + j * S].table + (int64_t)rid[j] * dim + 4 * q);
+      if (rid[j] >= 0 && lane_on) v[j] = ldg_row16(p.f[f0 + j * S].table + (int64_t)rid[j] * dim + 4 * q);
     }
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
       const int f = f0 + j * S;
       if (f < p.n_fields && lane_on) {
-        const FieldDev& fd = sf[f];
+        const FieldDev& fd = p.f[f];
         if (fd.tile_col >= 0 && trow != nullptr) st_tile4(trow + fd.tile_col + 4 * q, v[j], p.tile_vec != 0);
         if (fd.fm_slot >= 0 && want_fm) {
           s = f4_add(s, v[j]);
@@ -186,7 +173,7 @@ __global__ void __launch_bounds__(256) fields_fwd_v5(const __grid_constant__ Fwd
     const int gl = slot * LPR + q, G = LPR * S;
     float* drow = p.tile + (int64_t)b * p.tile_ld;
     for (int j = gl; j < p.n_dense; j += G) {
-      const DenseDev& dd = sd[j];
+      const DenseDev& dd = p.d[j];
       for (int k = 0; k < dd.width; ++k) drow[dd.tile_col + k] = load_dense_value(dd.src, (int64_t)b * dd.stride + k, dd.dtype);
     }
   }

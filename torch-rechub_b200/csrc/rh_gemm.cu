@@ -347,52 +347,38 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           sm_stats[(q * 2 + 0) * 128 + c * 32 + lane] = wmean;
           sm_stats[(q * 2 + 1) * 128 + c * 32 + lane] = dsq[0];
         }
-        // ---- coalesced write-out: the warp's 32 x 32 block goes through a shared-memory slab (the stage ring is idle by now) so that
-        // ---- one store instruction covers 4 rows x 128 contiguous bytes instead of 32 rows x 16 bytes (8x fewer L1 wavefronts);
-        // ---- the bias is read once per chunk, ahead of the stores (a load behind every store serialised on memory ordering:
-        // ---- measured 15.7 k cycles for this epilogue with bias against 4.7 k without, tools/gemm_trace.cu)
-        {
-          float* slab = reinterpret_cast<float*>(smem + 8192) + q * (32 * 36);
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(slab + lane * 36 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-          __syncwarp();
+        // ---- write-out: lane = row, 16-byte stores.  The bias of the chunk is read into registers AHEAD of the stores: with a load
+        // ---- behind every store (same loop body) the compiler must keep them in order and each load waits out its latency —
+        // ---- measured 15.7 k cycles for this epilogue with bias against 4.7 k without (tools/gemm_trace.cu).  (Staging the block
+        // ---- through shared memory for row-contiguous stores was measured too: 5.6 k cycles — the TMEM reads, not the store
+        // ---- pattern, set the pace: 2 x 64 KB per CTA at 64 B/cycle.)
+        if (m < p.M) {
           const int nb = n0 + c * 32;
-          const int cg = lane & 7, rsub = lane >> 3;
-          const int col = nb + 4 * cg;
-          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          float* crow = p.C + (int64_t)m * p.ldc + nb;
           if (add_bias) {
-            if (col < p.N) bv.x = __ldg(p.bias + col);
-            if (col + 1 < p.N) bv.y = __ldg(p.bias + col + 1);
-            if (col + 2 < p.N) bv.z = __ldg(p.bias + col + 2);
-            if (col + 3 < p.N) bv.w = __ldg(p.bias + col + 3);
-          }
-          float4 vals[8];
+            float bv[32];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            vals[t] = *reinterpret_cast<const float4*>(slab + (t * 4 + rsub) * 36 + 4 * cg);
-            vals[t].x += bv.x; vals[t].y += bv.y; vals[t].z += bv.z; vals[t].w += bv.w;
+            for (int j = 0; j < 32; ++j) bv[j] = (nb + j < p.N) ? __ldg(p.bias + nb + j) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + bv[j]);
           }
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            const int mrow = m0 + q * 32 + t * 4 + rsub;
-            if (mrow >= p.M || col >= p.N) continue;
-            float* dst = p.C + (int64_t)mrow * p.ldc + col;
-            if (vec_ok && col + 3 < p.N) {
-              if (p.reduce) red_add_row16(dst, vals[t]);
-              else *reinterpret_cast<float4*>(dst) = vals[t];
+          for (int j = 0; j < 32; j += 4) {
+            const float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            if (vec_ok && nb + j + 3 < p.N) {
+              if (p.reduce) red_add_row16(crow + j, v);
+              else *reinterpret_cast<float4*>(crow + j) = v;
             } else {
-              const float vv[4] = {vals[t].x, vals[t].y, vals[t].z, vals[t].w};
+              const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                if (col + e < p.N) {
-                  if (p.reduce) atomicAdd(dst + e, vv[e]);
-                  else dst[e] = vv[e];
+                if (nb + j + e < p.N) {
+                  if (p.reduce) atomicAdd(crow + j + e, vv[e]);
+                  else crow[j + e] = vv[e];
                 }
               }
             }
           }
-          __syncwarp();
         }
       }
       if (q == 0 && lane == 0) RH_TR(10);
