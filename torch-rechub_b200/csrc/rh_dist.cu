@@ -134,9 +134,41 @@ __global__ void __launch_bounds__(256) dense_reduce_update_kernel(const __grid_c
   }
 }
 
+// Cross-GPU barrier of the sharded exchange: one warp publishes this rank's next step number into its slot of every peer's flags
+// (st.release.sys after __threadfence_system: everything this GPU wrote before — rows stored into the peers' tiles, gradient REDs —
+// is visible to a peer that acquires the flag) and spins on its own flags until every rank has published.  ~2 us; replaces a
+// library barrier kernel of 4.9 us at three places per step.
+struct PeerFlagPtrs {
+  int32_t* p[kMaxRanks];
+};
+__global__ void __launch_bounds__(32) peer_barrier_kernel_v(const __grid_constant__ PeerFlagPtrs peers, const int32_t* my_flags, int rank, int world, int32_t* epoch) {
+  const int e = *epoch + 1;
+  __syncwarp();
+  if ((int)threadIdx.x < world) {
+    __threadfence_system();
+    st_release_sys(peers.p[threadIdx.x] + rank, e);
+    while (ld_acquire_sys(my_flags + threadIdx.x) < e) __nanosleep(40);
+  }
+  __syncwarp();
+  if (threadIdx.x == 0) *epoch = e;
+}
+
 }  // namespace rh
 
 using namespace rh;
+
+extern "C" int rh_peer_barrier(int32_t* const* peer_flags, const int32_t* my_flags, int rank, int world, int32_t* epoch_dev, void* stream) {
+  RH_REQUIRE(peer_flags && my_flags && epoch_dev && world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world, RH_ERR_INVALID_ARG, "rh_peer_barrier: bad arguments");
+  PeerFlagPtrs pf;
+  memset(&pf, 0, sizeof(pf));
+  for (int s = 0; s < world; ++s) {
+    RH_REQUIRE(peer_flags[s] != nullptr, RH_ERR_INVALID_ARG, "rh_peer_barrier: flags of rank %d NULL", s);
+    pf.p[s] = peer_flags[s];
+  }
+  peer_barrier_kernel_v<<<1, 32, 0, (cudaStream_t)stream>>>(pf, my_flags, rank, world, epoch_dev);
+  RH_LAUNCH_CHECK();
+  return RH_OK;
+}
 
 extern "C" int64_t rh_dense_stage_floats(int n_tensors, const int64_t* numel) {
   int64_t t = 0;

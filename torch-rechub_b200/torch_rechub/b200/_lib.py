@@ -67,6 +67,7 @@ PROTOTYPES = {
     "rh_head_bwd": [c_p, c_i64, c_i64, c_i, c_p, c_p, c_p, c_i, c_p, c_i64, c_p, c_p, c_p, c_p],
     "rh_dense_update": [c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_f, c_f, c_f, c_f, c_p],
     "rh_dense_stage_floats": [c_i, c_p],
+    "rh_peer_barrier": [c_p, c_p, c_i, c_i, c_p, c_p],
     "rh_dense_pack_signal": [c_i, c_p, c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p],
     "rh_dense_reduce_update": [c_i, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_i, c_p, c_p, c_f, c_f, c_f, c_f, c_p],
     "rh_gemm_tf32x3": [c_p, c_i64, c_i, c_p, c_i64, c_i, c_p, c_i64, c_i, c_i, c_i, c_p, c_i, c_p],

@@ -39,6 +39,10 @@ p2p_defer_barrier = _flag("RECHUB_B200_P2P_DEFER_BARRIER", False)
 # the dense optimiser update (rh_dense_pack_signal + rh_dense_reduce_update) instead of NCCL's all-reduce + rh_dense_update.
 p2p_allreduce = _flag("RECHUB_B200_P2P_ALLREDUCE", True)
 
+# ... and order the exchange's hand-overs with the engine's own flag barrier (rh_peer_barrier, one warp) instead of the symmetric-memory
+# library's barrier kernel.
+p2p_own_barrier = _flag("RECHUB_B200_P2P_OWN_BARRIER", True)
+
 # Check the device-side out-of-range-id flag after every forward (one D2H sync per step).  When off the
 # flag is checked at the trainer's existing sync points (``loss.item()``) and by ``check_errors()``.
 eager_bounds_check = _flag("RECHUB_B200_EAGER_BOUNDS_CHECK", False)

@@ -74,9 +74,24 @@ class P2PExchange(object):
             self.drows_ptrs = [int(p) for p in self.h_drows.buffer_ptrs]
             self.drows.zero_()
         self.ids_local = torch.zeros_like(self.ids)
+        self.own = None
+        if config.p2p_own_barrier and W <= 8:
+            import ctypes
+            flags = symm.empty(8, dtype=torch.int32, device=device)
+            flags.zero_()
+            h_flags = symm.rendezvous(flags, group)
+            self.own = {"flags": flags, "handle": h_flags, "ptrs": (ctypes.c_void_p * W)(*[int(p) for p in h_flags.buffer_ptrs]), "epoch": torch.zeros(1, dtype=torch.int32, device=device),
+                        "rank": dist.get_rank(group), "world": W}
+            torch.cuda.synchronize(device)
+            dist.barrier(group=group)  # nobody publishes into flags that are still being zeroed
 
     def barrier(self):
-        self.h_rows.barrier(channel=0)
+        if self.own is not None:
+            from . import _lib
+            o = self.own
+            _lib.check(_lib.lib().rh_peer_barrier(o["ptrs"], o["flags"].data_ptr(), o["rank"], o["world"], o["epoch"].data_ptr(), _lib.stream_ptr()), "rh_peer_barrier")
+        else:
+            self.h_rows.barrier(channel=0)
 
 
 def _snapshot(front, ids):
