@@ -68,6 +68,10 @@ int         rh_abi_version(void);
 const char* rh_last_error(void);
 /* Number of kernels this library has launched so far in this process (bench.py's gpu_launches). */
 unsigned long long rh_launch_count(void);
+/* Programmatic dependent launch for the hot-path kernels (GEMM, fused gather / scatter, fused BatchNorm, optimiser updates): with
+ * on != 0 they are launched so that their scheduling and memory-free prologue overlap the drain of the preceding kernel in the stream
+ * (each waits with griddepcontrol.wait before its first global access).  on < 0 only queries.  Returns the previous setting. */
+int rh_set_pdl(int on);
 /* L2 fetch granularity of the current device (cudaLimitMaxL2FetchGranularity): bytes L2 pulls from DRAM per sector miss.
  * set_bytes > 0 sets it first (32 / 64 / 128); returns the value in force, < 0 on a CUDA error.  Random 64-byte embedding rows
  * (basic/layers.py:83,85 lookups) cost twice their DRAM bytes at 128 — the engine's host side lowers it once per device. */

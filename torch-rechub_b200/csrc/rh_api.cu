@@ -6,6 +6,7 @@
 namespace rh {
 static thread_local char g_err[512] = "";
 unsigned long long g_launches = 0;
+int g_pdl = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -18,6 +19,11 @@ void set_error(const char* fmt, ...) {
 extern "C" int rh_abi_version(void) { return RH_ABI_VERSION; }
 extern "C" const char* rh_last_error(void) { return rh::g_err; }
 extern "C" unsigned long long rh_launch_count(void) { return rh::g_launches; }
+extern "C" int rh_set_pdl(int on) {
+  const int old = rh::g_pdl;
+  if (on >= 0) rh::g_pdl = on != 0;
+  return old;
+}
 
 // cudaLimitMaxL2FetchGranularity of the current device: how many bytes L2 pulls from DRAM on a sector miss (32 / 64 / 128).
 // Random 64-byte table rows are the engine's dominant access: at 128 bytes every row costs a second, never-used sector pair

@@ -189,6 +189,7 @@ __global__ void __launch_bounds__(kFuseThreads) bn_fused_fwd_kernel(const BnFuse
   const int cols = p.cols;
   const int act = ACT >= 0 ? ACT : p.act;
   const int64_t row0 = (int64_t)blockIdx.x * kFuseWarps * RPW;
+  pdl_wait();
   const FuseScratch fs = fuse_scratch(p.scratch, cols);
   // dropout stream id of this forward = num_batches_tracked + 1 (CTA 0 stores the incremented value after the barrier)
   const long long count = p.nbt != nullptr ? *p.nbt + 1 : 0;
@@ -352,6 +353,7 @@ __global__ void __launch_bounds__(kFuseThreads) bn_fused_bwd_kernel(const BnFuse
   const int cols = p.cols;
   const int act = ACT >= 0 ? ACT : p.act;
   const int64_t row0 = (int64_t)blockIdx.x * kFuseWarps * RPW;
+  pdl_wait();
   const FuseScratch fs = fuse_scratch(p.scratch, cols);
   const uint32_t counter = (uint32_t)__float_as_int(__ldg(p.stats + 2 * cols));
 
@@ -625,10 +627,10 @@ unsigned long long* g_bn_trace = nullptr;
   do {                                                                                                       \
     const int key__ = pl.kmax * 16 + pl.rpw;                                                                 \
     switch (key__) {                                                                                         \
-      case 1 * 16 + 2: KERNEL<1, 2, ACTV, HEADV><<<pl.grid, kFuseThreads, smem, st>>>(p); break;             \
-      case 1 * 16 + 4: KERNEL<1, 4, ACTV, HEADV><<<pl.grid, kFuseThreads, smem, st>>>(p); break;             \
-      case 2 * 16 + 2: KERNEL<2, 2, ACTV, HEADV><<<pl.grid, kFuseThreads, smem, st>>>(p); break;             \
-      case 4 * 16 + 1: KERNEL<4, 1, ACTV, HEADV><<<pl.grid, kFuseThreads, smem, st>>>(p); break;             \
+      case 1 * 16 + 2: launch_k(KERNEL<1, 2, ACTV, HEADV>, dim3(pl.grid), dim3(kFuseThreads), smem, st, p); break;             \
+      case 1 * 16 + 4: launch_k(KERNEL<1, 4, ACTV, HEADV>, dim3(pl.grid), dim3(kFuseThreads), smem, st, p); break;             \
+      case 2 * 16 + 2: launch_k(KERNEL<2, 2, ACTV, HEADV>, dim3(pl.grid), dim3(kFuseThreads), smem, st, p); break;             \
+      case 4 * 16 + 1: launch_k(KERNEL<4, 1, ACTV, HEADV>, dim3(pl.grid), dim3(kFuseThreads), smem, st, p); break;             \
       default: set_error("bn_fused: no instantiation for kmax %d rpw %d", pl.kmax, pl.rpw); return RH_ERR_UNSUPPORTED; \
     }                                                                                                        \
   } while (0)

@@ -21,6 +21,27 @@ void set_error(const char* fmt, ...);   // rh_api.cu (thread-local message)
   } while (0)
 
 extern unsigned long long g_launches;  // rh_api.cu: kernels launched by this library (rh_launch_count)
+extern int g_pdl;                      // rh_api.cu: launch the hot-path kernels with programmatic dependent launch (rh_set_pdl)
+
+// Launch with the programmatic-stream-serialization attribute when rh_set_pdl(1): the kernel may be scheduled while its predecessor
+// in the stream drains; it calls pdl_wait() (griddepcontrol.wait) before its first global access, which returns once the predecessor
+// has completed and flushed — so only launch latency and the memory-free prologue overlap.  Captured by CUDA graphs as a
+// programmatic edge.  Without the attribute pdl_wait() is a no-op.
+template <typename... KArgs, typename... Args>
+static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 #define RH_LAUNCH_CHECK()                                                        \
   do {                                                                           \
@@ -50,6 +71,7 @@ static inline int pow2_ceil(int v) {
 }
 
 // ---- device helpers ----------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // 128-bit read-only load that does not allocate in L1: embedding rows are touched once per launch.
 __device__ __forceinline__ float4 ldg_row16(const float* p) {

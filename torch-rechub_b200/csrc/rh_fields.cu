@@ -111,6 +111,7 @@ __device__ __forceinline__ void st_tile4(float* p, const float4& v, bool vec) {
 template <int LPR>
 __global__ void __launch_bounds__(256) fields_fwd_v5(const __grid_constant__ FwdParams p, const int S) {
   constexpr int CH = 4;  // row loads in flight per lane per chunk
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int q = lane % LPR;
@@ -247,6 +248,7 @@ template <int LPR, int ITER>
 __global__ void __launch_bounds__(128) fields_bwd_v4(const __grid_constant__ BwdParams p) {
   __shared__ float4 sm_dw[4][32];
   __shared__ float sm_db[4];
+  pdl_wait();
 
   const int f = blockIdx.y;
   const FieldDev& fd = p.f[f];
@@ -413,7 +415,7 @@ static void launch_fwd_v5(const FwdParams& p, cudaStream_t st) {
   const int warps = (p.batch + spw - 1) / spw;
   const int wpb = 8;                             // 256 threads
   const int grid = (warps + wpb - 1) / wpb;
-  fields_fwd_v5<LPR><<<grid, wpb * 32, 0, st>>>(p, S);
+  launch_k(fields_fwd_v5<LPR>, dim3(grid), dim3(wpb * 32), 0, st, p, S);
 }
 
 template <int LPR>
@@ -422,7 +424,7 @@ static void launch_bwd_v4(const BwdParams& p, cudaStream_t st) {
   const int threads = 128;
   const int spb = threads / LPR * ITER;
   dim3 grid((p.batch + spb - 1) / spb, p.n_fields);
-  fields_bwd_v4<LPR, ITER><<<grid, threads, 0, st>>>(p);
+  launch_k(fields_bwd_v4<LPR, ITER>, grid, dim3(threads), 0, st, p);
 }
 
 }  // namespace rh

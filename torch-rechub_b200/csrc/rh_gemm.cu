@@ -213,6 +213,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) RH_TR(1);
+  pdl_wait();  // barriers, TMEM and the descriptor prefetch are set up; the operands (and C, for split-K) belong to the predecessor until here
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -568,9 +569,9 @@ static int gemm_impl(const float* A, int64_t lda, int a_mn_major, const float* B
     p.running_var = st->running_var;
     p.num_batches_tracked = reinterpret_cast<long long*>(st->num_batches_tracked);
     p.momentum = st->momentum;
-    gemm_tf32x3_kernel<true><<<grid, kGemmThreads, kGemmSmem, (cudaStream_t)stream>>>(map_a, map_b, p);
+    launch_k(gemm_tf32x3_kernel<true>, grid, dim3(kGemmThreads), kGemmSmem, (cudaStream_t)stream, map_a, map_b, p);
   } else {
-    gemm_tf32x3_kernel<false><<<grid, kGemmThreads, kGemmSmem, (cudaStream_t)stream>>>(map_a, map_b, p);
+    launch_k(gemm_tf32x3_kernel<false>, grid, dim3(kGemmThreads), kGemmSmem, (cudaStream_t)stream, map_a, map_b, p);
   }
   RH_LAUNCH_CHECK();
   return RH_OK;

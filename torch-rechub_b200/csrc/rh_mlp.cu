@@ -530,6 +530,7 @@ struct DenseOptP {
 
 __global__ void __launch_bounds__(256) dense_update_kernel(const __grid_constant__ DenseOptP t, int kind, float beta1, float beta2, float eps,
                                                            float wd, const float* __restrict__ lr_dev, const float* __restrict__ bc_dev) {
+  pdl_wait();
   const int ti = blockIdx.y;
   const int n = t.n[ti];
   const float lr = *lr_dev;
@@ -706,7 +707,7 @@ extern "C" int rh_dense_update(int n_tensors, float* const* params, const float*
     int gx = (int)((biggest + 255) / 256);  // one element per thread for tower-sized tensors: the update is a latency chain, not a stream
     if (gx > 1024) gx = 1024;
     if (gx < 1) gx = 1;
-    dense_update_kernel<<<dim3(gx, cnt), 256, 0, (cudaStream_t)stream>>>(t, kind, beta1, beta2, eps, weight_decay, lr_dev, bias_corr_dev);
+    launch_k(dense_update_kernel, dim3(gx, cnt), dim3(256), 0, (cudaStream_t)stream, t, kind, beta1, beta2, eps, weight_decay, lr_dev, bias_corr_dev);
     RH_LAUNCH_CHECK();
   }
   return RH_OK;

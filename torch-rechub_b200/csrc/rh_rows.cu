@@ -339,6 +339,7 @@ __global__ void __launch_bounds__(128) fields_rowwise_update_kernel(const __grid
   // same claim protocol as rowwise_update_kernel; 16-byte lanes only (dim % 4 == 0).
   // Latency shape: ids -> {claim atomic, g, w, m, v loads} -> stores.  The row loads are issued BEFORE the claim's verdict
   // is known (duplicates are rare and a wasted read is harmless), which removes one dependent DRAM round trip.
+  pdl_wait();
   const int f = blockIdx.y;
   const int step = *step_dev;
   const float lr = *lr_dev;
@@ -409,6 +410,7 @@ __global__ void __launch_bounds__(128) fields_prefetch_kernel(const __grid_const
 }
 
 __global__ void opt_advance_kernel(int32_t* step_dev, float* bc_dev, float beta1, float beta2) {
+  pdl_wait();
   const int step = *step_dev + 1;
   *step_dev = step;
   if (bc_dev != nullptr) {
@@ -539,7 +541,7 @@ extern "C" int rh_rowwise_update(float* table, float* table_grad, float* state1,
 
 extern "C" int rh_opt_advance(int32_t* step_dev, float* bias_corr_dev, float beta1, float beta2, void* stream) {
   RH_REQUIRE(step_dev != nullptr, RH_ERR_INVALID_ARG, "rh_opt_advance: NULL");
-  opt_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, bias_corr_dev, beta1, beta2);
+  launch_k(opt_advance_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, step_dev, bias_corr_dev, beta1, beta2);
   RH_LAUNCH_CHECK();
   return RH_OK;
 }
@@ -597,7 +599,7 @@ extern "C" int rh_fields_rowwise_update(const rh_field* fields, int n_fields, in
   OptArgs a{kind, beta1, beta2, eps, weight_decay};
   const int threads = 128;
   dim3 grid((unsigned)(((int64_t)batch * G + threads - 1) / threads), n_fields);
-  fields_rowwise_update_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(p, a, step_dev, lr_dev, bias_corr_dev, G, state_row_stride);
+  launch_k(fields_rowwise_update_kernel, grid, dim3(threads), 0, (cudaStream_t)stream, p, a, step_dev, lr_dev, bias_corr_dev, G, state_row_stride);
   RH_LAUNCH_CHECK();
   return RH_OK;
 }

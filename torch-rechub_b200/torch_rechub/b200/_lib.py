@@ -36,6 +36,7 @@ PROTOTYPES = {
     "rh_last_error": [],
     "rh_launch_count": [],
     "rh_l2_fetch_granularity": [c_i],
+    "rh_set_pdl": [c_i],
     "rh_fields_fwd": [c_p, c_i, c_i, c_p, c_i, c_i, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "rh_fields_fwd_p2p": [c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_i64, c_p, c_p],
     "rh_ids_scatter": [c_p, c_i, c_p, c_i, c_p, c_i, c_i, c_i64, c_i64, c_p],
@@ -119,6 +120,8 @@ def lib():
                 fn.restype = _RESTYPES.get(name, ctypes.c_int)
             if handle.rh_abi_version() != 1:
                 raise EngineMissing("librechub_b200.so ABI version %d != 1" % handle.rh_abi_version())
+            from . import config
+            handle.rh_set_pdl(int(bool(config.pdl)))
             _lib = handle
     return _lib
 

@@ -82,6 +82,10 @@ fused_bn = _flag("RECHUB_B200_FUSED_BN", True)
 # ... and the last hidden layer's fused launch also does the tower's output layer + side terms + sigmoid (DeepFM / DIN heads).
 fused_bn_head = _flag("RECHUB_B200_FUSED_BN_HEAD", True)
 
+# Programmatic dependent launch of the hot-path kernels (rh_set_pdl): a kernel's scheduling and memory-free prologue overlap the drain
+# of its predecessor; captured as programmatic edges by CUDA graphs.  Off until measured.
+pdl = _flag("RECHUB_B200_PDL", False)
+
 # cudaLimitMaxL2FetchGranularity the engine sets on every device it touches (bytes; 0 = leave the process default).  Random 64-byte
 # table rows are the dominant DRAM access: measured DRAM reads per 106 k-row gather: 14.4 MB at 128, 7.7 MB (= algorithmic) at 64 / 32.
 l2_fetch_granularity = int(os.environ.get("RECHUB_B200_L2_FETCH_GRANULARITY", "32"))
