@@ -361,6 +361,12 @@ int rh_head_bwd(const float* x, int64_t x_ld, int64_t rows, int k, const float* 
                 const float* d_out, int apply_sigmoid, float* d_x, int64_t d_x_ld, float* d_w, float* d_b,
                 float* d_extra, void* stream);
 
+/* torch.nn.BCELoss(reduction="mean") on probabilities (the CTR trainer's criterion, trainers/ctr_trainer.py:68,88) in one launch each way:
+ *   *loss = mean_i -(y_i max(log p_i, -100) + (1 - y_i) max(log(1 - p_i), -100));   d_prob_i = *d_loss * (p_i - y_i) / max(p_i (1 - p_i), 1e-12) / n
+ * scratch: 65 floats, zeroed once by the caller (block partials + a ticket the kernel leaves zero); sums run in a fixed order. */
+int rh_bce_fwd(const float* prob, const float* target, int64_t n, float* scratch, float* loss, void* stream);
+int rh_bce_bwd(const float* prob, const float* target, const float* d_loss, int64_t n, float* d_prob, void* stream);
+
 /* One launch of SGD / Adam / Adagrad (kinds as rh_rowwise_update) over n_tensors small dense tensors — the tower's
  * weights (the dense half of optimizer.step(), trainers/ctr_trainer.py:99).  params/grads/state1/state2: host arrays of
  * device pointers; numel: host array.  lr_dev / bias_corr_dev: the device scalars of rh_opt_advance. */

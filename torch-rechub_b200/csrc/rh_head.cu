@@ -157,3 +157,68 @@ extern "C" int rh_head_bwd(const float* x, int64_t x_ld, int64_t rows, int k, co
   RH_LAUNCH_CHECK();
   return RH_OK;
 }
+
+// ---- BCELoss(mean) on probabilities (trainers/ctr_trainer.py:68,88: torch.nn.BCELoss) as one launch each way -----------------------
+// torch's arithmetic: loss_i = -(y log p + (1 - y) log(1 - p)) with both logs clamped at -100; d loss / d p = (p - y) / max(p (1 - p), 1e-12) / N.
+// Stock PyTorch runs four launches per step for it (element-wise loss, mean reduction, its backward, a fill); at batch 4096 each is pure
+// launch latency.  Forward: per-block partial sums + a last-block finalisation in a fixed order (deterministic); `partial` holds
+// gridDim floats + a ticket counter (zero on entry, left zero).
+namespace rh {
+__global__ void __launch_bounds__(256) bce_fwd_kernel(const float* __restrict__ p, const float* __restrict__ y, int64_t n, float* __restrict__ partial,
+                                                      unsigned* __restrict__ ticket, float* __restrict__ loss) {
+  __shared__ float sm[8];
+  __shared__ bool is_last;
+  pdl_wait();
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float pi = __ldg(p + i), yi = __ldg(y + i);
+    const float lp = fmaxf(logf(pi), -100.f), lq = fmaxf(log1pf(-pi), -100.f);
+    acc -= yi * lp + (1.f - yi) * lq;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sm[w];
+    partial[blockIdx.x] = t;
+    __threadfence();
+    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last || threadIdx.x != 0) return;
+  __threadfence();
+  float t = 0.f;
+  for (unsigned b = 0; b < gridDim.x; ++b) t += __ldcg(partial + b);
+  *loss = t / (float)n;
+  *ticket = 0u;
+}
+
+__global__ void __launch_bounds__(256) bce_bwd_kernel(const float* __restrict__ p, const float* __restrict__ y, const float* __restrict__ d_loss, int64_t n,
+                                                      float* __restrict__ d_p) {
+  pdl_wait();
+  const float s = __ldg(d_loss) / (float)n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float pi = __ldg(p + i);
+    d_p[i] = s * (pi - __ldg(y + i)) / fmaxf(pi * (1.f - pi), 1e-12f);
+  }
+}
+}  // namespace rh
+
+extern "C" int rh_bce_fwd(const float* prob, const float* target, int64_t n, float* scratch, float* loss, void* stream) {
+  RH_REQUIRE(prob && target && scratch && loss && n > 0, RH_ERR_INVALID_ARG, "rh_bce_fwd: bad arguments");
+  int64_t g = (n + 1023) / 1024;
+  if (g > 64) g = 64;
+  launch_k(rh::bce_fwd_kernel, dim3((unsigned)g), dim3(256), 0, (cudaStream_t)stream, prob, target, n, scratch, reinterpret_cast<unsigned*>(scratch + 64), loss);
+  RH_LAUNCH_CHECK();
+  return RH_OK;
+}
+
+extern "C" int rh_bce_bwd(const float* prob, const float* target, const float* d_loss, int64_t n, float* d_prob, void* stream) {
+  RH_REQUIRE(prob && target && d_loss && d_prob && n > 0, RH_ERR_INVALID_ARG, "rh_bce_bwd: bad arguments");
+  int64_t g = (n + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  launch_k(rh::bce_bwd_kernel, dim3((unsigned)g), dim3(256), 0, (cudaStream_t)stream, prob, target, d_loss, n, d_prob);
+  RH_LAUNCH_CHECK();
+  return RH_OK;
+}

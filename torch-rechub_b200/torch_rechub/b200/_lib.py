@@ -66,6 +66,8 @@ PROTOTYPES = {
     "rh_bn_act_fused_bwd": [c_p, c_i64, c_i64, c_i, c_p, c_f, c_p, c_p, c_i, c_p, c_f, c_f, ctypes.c_uint32, c_p, c_i64, c_p, c_p, c_p, c_i, c_p, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "rh_head_fwd": [c_p, c_i64, c_i64, c_i, c_p, c_p, c_p, c_p, c_i, c_p, c_p],
     "rh_head_bwd": [c_p, c_i64, c_i64, c_i, c_p, c_p, c_p, c_i, c_p, c_i64, c_p, c_p, c_p, c_p],
+    "rh_bce_fwd": [c_p, c_p, c_i64, c_p, c_p, c_p],
+    "rh_bce_bwd": [c_p, c_p, c_p, c_i64, c_p, c_p],
     "rh_dense_update": [c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_f, c_f, c_f, c_f, c_p],
     "rh_dense_stage_floats": [c_i, c_p],
     "rh_peer_barrier": [c_p, c_p, c_i, c_i, c_p, c_p],

@@ -1142,3 +1142,46 @@ def inbatch_cross_entropy(u, v, picks):
     if not (u.is_cuda and u.dim() == 2 and v.dim() == 2 and u.dtype == torch.float32 and v.dtype == torch.float32 and u.shape[1] == v.shape[1] and u.shape[1] <= 256 and u.shape[0] == v.shape[0]):
         return None
     return _InbatchCE.apply(u, v, picks.contiguous())
+
+
+# =====================================================================================================
+# BCELoss(mean) on probabilities: the CTR trainer's criterion
+# =====================================================================================================
+_bce_scratch = {}
+
+
+class _BCEMean(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, prob, target):
+        L = _lib.lib()
+        p, y = prob.contiguous(), target.contiguous()
+        dev = p.device
+        key = dev.index if dev.index is not None else torch.cuda.current_device()
+        sc = _bce_scratch.get(key)
+        if sc is None:
+            sc = _bce_scratch[key] = torch.zeros(65, dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        check(L.rh_bce_fwd(p.data_ptr(), y.data_ptr(), p.numel(), sc.data_ptr(), loss.data_ptr(), stream_ptr()), "rh_bce_fwd")
+        ctx.save_for_backward(p, y)
+        return loss
+
+    @staticmethod
+    def backward(ctx, d_loss):
+        L = _lib.lib()
+        p, y = ctx.saved_tensors
+        d_p = torch.empty_like(p)
+        g = d_loss.reshape(1).float().contiguous()
+        check(L.rh_bce_bwd(p.data_ptr(), y.data_ptr(), g.data_ptr(), p.numel(), d_p.data_ptr(), stream_ptr()), "rh_bce_bwd")
+        return d_p, None
+
+
+class EngineBCELoss(torch.nn.BCELoss):
+    """``torch.nn.BCELoss`` whose mean reduction over fp32 CUDA probabilities is one launch each way (``rh_bce_fwd`` / ``rh_bce_bwd``);
+    any other input (CPU, weights, other reductions, dtypes) takes the stock implementation."""
+
+    def forward(self, input, target):
+        if (input.is_cuda and self.reduction == "mean" and self.weight is None and input.dtype == torch.float32 and target.dtype == torch.float32 and input.shape == target.shape and input.numel() > 0
+                and not target.requires_grad):
+            return _BCEMean.apply(input, target)
+        return super().forward(input, target)

@@ -88,6 +88,9 @@ class CTRTrainer(object):
             self.scheduler = scheduler_fn(getattr(self.optimizer, "scheduler_target", self.optimizer), **scheduler_params)
         self.loss_mode = loss_mode
         self.criterion = torch.nn.BCELoss()
+        if self.device.type == "cuda":
+            from ..b200 import ops
+            self.criterion = ops.EngineBCELoss()  # an nn.BCELoss: same arithmetic, one launch each way on CUDA
         self.evaluate_fn = roc_auc_score
         self.n_epoch = n_epoch
         self.early_stopper = EarlyStopper(patience=earlystop_patience)
