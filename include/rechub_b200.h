@@ -361,6 +361,11 @@ int rh_head_bwd(const float* x, int64_t x_ld, int64_t rows, int k, const float* 
                 const float* d_out, int apply_sigmoid, float* d_x, int64_t d_x_ld, float* d_w, float* d_b,
                 float* d_extra, void* stream);
 
+/* One launch copying n (1..4) contiguous device buffers: a packed batch (id block, numeric block, sequence block, labels) into the
+ * captured step's static buffers (the reference moves one tensor per column, trainers/ctr_trainer.py:84).  dst/src/bytes: HOST arrays
+ * of device pointers / byte counts; buffers must not overlap. */
+int rh_copy_segments(int n, void* const* dst, const void* const* src, const int64_t* bytes, void* stream);
+
 /* torch.nn.BCELoss(reduction="mean") on probabilities (the CTR trainer's criterion, trainers/ctr_trainer.py:68,88) in one launch each way:
  *   *loss = mean_i -(y_i max(log p_i, -100) + (1 - y_i) max(log(1 - p_i), -100));   d_prob_i = *d_loss * (p_i - y_i) / max(p_i (1 - p_i), 1e-12) / n
  * scratch: 65 floats, zeroed once by the caller (block partials + a ticket the kernel leaves zero); sums run in a fixed order. */

@@ -66,6 +66,7 @@ PROTOTYPES = {
     "rh_bn_act_fused_bwd": [c_p, c_i64, c_i64, c_i, c_p, c_f, c_p, c_p, c_i, c_p, c_f, c_f, ctypes.c_uint32, c_p, c_i64, c_p, c_p, c_p, c_i, c_p, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "rh_head_fwd": [c_p, c_i64, c_i64, c_i, c_p, c_p, c_p, c_p, c_i, c_p, c_p],
     "rh_head_bwd": [c_p, c_i64, c_i64, c_i, c_p, c_p, c_p, c_i, c_p, c_i64, c_p, c_p, c_p, c_p],
+    "rh_copy_segments": [c_i, c_p, c_p, c_p, c_p],
     "rh_bce_fwd": [c_p, c_p, c_i64, c_p, c_p, c_p],
     "rh_bce_bwd": [c_p, c_p, c_p, c_i64, c_p, c_p],
     "rh_dense_update": [c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_f, c_f, c_f, c_f, c_p],

@@ -106,6 +106,16 @@ class GraphedStep(object):
     @staticmethod
     def _copy_batch(src_x, src_y, dst_x, dst_y):
         if isinstance(src_x, PackedColumns) and isinstance(dst_x, PackedColumns):
+            pairs = [(a, b) for a, b in ((src_x.ids, dst_x.ids), (src_x.nums, dst_x.nums), (src_x.seqs, dst_x.seqs), (src_y, dst_y)) if a is not None]
+            if all(a.is_cuda and b.is_cuda and a.device == b.device and a.dtype == b.dtype and a.shape == b.shape and a.is_contiguous() and b.is_contiguous() for a, b in pairs):
+                import ctypes
+                from . import _lib
+                n = len(pairs)
+                dst = (ctypes.c_void_p * n)(*[b.data_ptr() for _, b in pairs])
+                src = (ctypes.c_void_p * n)(*[a.data_ptr() for a, _ in pairs])
+                nbytes = (ctypes.c_int64 * n)(*[a.numel() * a.element_size() for a, _ in pairs])
+                _lib.check(_lib.lib().rh_copy_segments(n, dst, src, nbytes, _lib.stream_ptr()), "rh_copy_segments")  # one launch instead of <= 4 copies
+                return
             src_x.copy_into(dst_x)
         else:
             for k, v in src_x.items():
