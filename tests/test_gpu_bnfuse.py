@@ -138,6 +138,9 @@ def test_tower_fused_route_equals_two_kernel_route(act, p_drop, dims):
     for i in (1, 2, 3):
         assert (a[i] - b[i]).abs().max().item() <= 2e-5 * b[i].abs().max().item() + 1e-7, i
     for k in b[4]:
+        if k.endswith("alpha"):  # ONE scalar = a cancelling sum over rows x cols terms, accumulated in two different orders
+            assert (a[4][k] - b[4][k]).abs().max().item() <= 5e-3 * b[4][k].abs().max().item() + 2e-4, k
+            continue
         assert (a[4][k] - b[4][k]).abs().max().item() <= 3e-4 * b[4][k].abs().max().item() + 2e-6, k  # column sums: atomics vs a tree
     for k in b[5]:
         assert torch.allclose(a[5][k].float(), b[5][k].float(), rtol=1e-5, atol=1e-6), k

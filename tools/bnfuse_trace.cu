@@ -16,8 +16,8 @@ int main() {
       float *h, *y, *gamma, *beta, *stats, *scratch, *rm, *rv;
       long long* nbt;
       cudaMalloc(&h, rows * cols * 4); cudaMalloc(&y, rows * cols * 4); cudaMalloc(&gamma, cols * 4); cudaMalloc(&beta, cols * 4);
-      cudaMalloc(&stats, (2 * cols + 1) * 4); cudaMalloc(&scratch, (3 * cols + 8) * 4); cudaMalloc(&rm, cols * 4); cudaMalloc(&rv, cols * 4); cudaMalloc(&nbt, 8);
-      cudaMemset(h, 0, rows * cols * 4); cudaMemset(gamma, 0, cols * 4); cudaMemset(beta, 0, cols * 4); cudaMemset(scratch, 0, (3 * cols + 8) * 4);
+      cudaMalloc(&stats, (2 * cols + 1) * 4); cudaMalloc(&scratch, rh_bn_fused_scratch_floats(cols) * 4); cudaMalloc(&rm, cols * 4); cudaMalloc(&rv, cols * 4); cudaMalloc(&nbt, 8);
+      cudaMemset(h, 0, rows * cols * 4); cudaMemset(gamma, 0, cols * 4); cudaMemset(beta, 0, cols * 4); cudaMemset(scratch, 0, rh_bn_fused_scratch_floats(cols) * 4);
       cudaMemset(rm, 0, cols * 4); cudaMemset(rv, 0, cols * 4); cudaMemset(nbt, 0, 8);
       unsigned long long* trace;
       cudaMalloc(&trace, 148 * 8 * 8);

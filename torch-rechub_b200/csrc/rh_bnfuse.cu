@@ -47,7 +47,7 @@ struct BnFuseP {
   long long* nbt;
   float momentum;
   float* stats;    // (2 cols + 1): mean | biased var | step-counter bits      (forward: out; backward: in)
-  float* scratch;  // (3 cols + 8): sums | sums | sums | alpha, head bias, arrive, depart
+  float* scratch;  // rh_bn_fused_scratch_floats(cols): generation + two parity buffers (see FuseScratch)
   float* y;
   int64_t y_ld;
   // head
@@ -95,24 +95,33 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 constexpr int kFuseThreads = 512;  // 16 warps: at 8 warps / SM the kernel was bound by instruction latency (ncu: 10 % issue-active)
 constexpr int kFuseWarps = kFuseThreads / 32;
 
-// Scratch layout (floats): [0] generation (launches so far, uint) | [1] arrivals (uint, never reset) | [2..3] spare |
-// two parity buffers of (3 cols + 4) floats: sums | sums | sums | alpha, head bias, spare, spare.
-// Launch g uses buffer g & 1 (zero on entry) and, after its barrier, CTA 0 zeroes buffer (g + 1) & 1 — dirty since launch g - 1 —
-// and stores g + 1.  Nothing has to wait for "the last CTA out".
+// Scratch layout (floats): [0] generation (launches so far, uint), [1..31] spare | two parity buffers of kFuseHdr + 3 cols floats
+// (rounded up to 32: every buffer starts on its own 128-byte line): [0] arrivals of THIS launch (uint), [1] alpha, [2] head bias,
+// [32..) sums | sums | sums.  Launch g uses buffer g & 1 (all zero on entry) and, after its barrier, CTA 0 zeroes buffer
+// (g + 1) & 1 — dirty since launch g - 1, whose CTAs have all exited — and stores g + 1.  Nothing has to wait for "the last CTA
+// out", and launches of different grid sizes can share one scratch (the arrival count starts at zero for every launch; a
+// never-reset counter compared against (g + 1) * n_ctas deadlocked as soon as a shorter last batch changed the grid).
+constexpr int kFuseHdr = 32;
 struct FuseScratch {
   unsigned gen;
   unsigned* arrive;
+  float* extra;  // [1] alpha, [2] head bias
   float* sums;   // this launch's buffer
-  float* other;  // the buffer the next launch will use
+  float* other;  // the whole buffer the next launch will use (header included)
+  int other_floats;
 };
+__host__ __device__ __forceinline__ int fuse_buffer_floats(int cols) { return kFuseHdr + ((3 * cols + 31) / 32) * 32; }
 __device__ __forceinline__ FuseScratch fuse_scratch(float* scratch, int cols) {
   FuseScratch f;
   unsigned* hdr = reinterpret_cast<unsigned*>(scratch);
   f.gen = hdr[0];
-  f.arrive = hdr + 1;
-  const int per = 3 * cols + 4;
-  f.sums = scratch + 4 + (size_t)(f.gen & 1u) * per;
-  f.other = scratch + 4 + (size_t)((f.gen + 1u) & 1u) * per;
+  const int per = fuse_buffer_floats(cols);
+  float* mine = scratch + 32 + (size_t)(f.gen & 1u) * per;
+  f.arrive = reinterpret_cast<unsigned*>(mine);
+  f.extra = mine;
+  f.sums = mine + kFuseHdr;
+  f.other = scratch + 32 + (size_t)((f.gen + 1u) & 1u) * per;
+  f.other_floats = per;
   return f;
 }
 
@@ -122,8 +131,7 @@ __device__ __forceinline__ void grid_barrier(const FuseScratch& f, unsigned n_ct
   if (threadIdx.x == 0) {
     __threadfence();
     atomicAdd(f.arrive, 1u);
-    const unsigned target = (f.gen + 1u) * n_ctas;  // arrivals only grow: generation g is complete at (g + 1) * n_ctas
-    while ((int)(ld_acquire_u32(f.arrive) - target) < 0) __nanosleep(20);
+    while (ld_acquire_u32(f.arrive) < n_ctas) __nanosleep(20);
     __threadfence();
   }
   __syncthreads();
@@ -254,13 +262,17 @@ __global__ void __launch_bounds__(kFuseThreads) bn_fused_fwd_kernel(const BnFuse
   load_colconst<KMAX>(p.gamma, lane, cols, sc, 1.f);
   load_colconst<KMAX>(p.beta, lane, cols, bt, 0.f);
   if (HEAD) load_colconst<KMAX>(p.head_w, lane, cols, hw, 0.f);
+  // the grid's sums: ONE read per CTA into shared memory (every warp reading them from L2 put 16 x n_ctas requests on the same
+  // few lines, right behind the atomics: the apply phase spent most of its 6 us waiting there)
+  for (int i = threadIdx.x; i < (2 * cols) / 4; i += blockDim.x) reinterpret_cast<float4*>(smem)[i] = __ldcg(reinterpret_cast<const float4*>(fs.sums) + i);
+  __syncthreads();
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) {
     const int c0 = (k * 32 + lane) * 4;
     float4 t1 = f4_zero(), t2 = f4_zero();
     if (c0 < cols) {
-      t1 = __ldcg(reinterpret_cast<const float4*>(fs.sums + c0));
-      t2 = __ldcg(reinterpret_cast<const float4*>(fs.sums + cols + c0));
+      t1 = *reinterpret_cast<const float4*>(smem + c0);
+      t2 = *reinterpret_cast<const float4*>(smem + cols + c0);
     }
     const float a1[4] = {t1.x, t1.y, t1.z, t1.w}, a2[4] = {t2.x, t2.y, t2.z, t2.w};
 #pragma unroll
@@ -320,7 +332,7 @@ __global__ void __launch_bounds__(kFuseThreads) bn_fused_fwd_kernel(const BnFuse
   // ---- CTA 0 publishes the statistics and prepares the scratch of the next launch (concurrently with the other CTAs' phase 2) ----
   if (blockIdx.x != 0) return;
   for (int c = threadIdx.x; c < cols; c += blockDim.x) {
-    const float t1 = __ldcg(fs.sums + c), t2 = __ldcg(fs.sums + cols + c);
+    const float t1 = smem[c], t2 = smem[cols + c];
     const float mean = __ldg(p.h + c) + t1 / n;
     float v = (t2 - t1 * t1 / n) / n;
     if (v < 0.f) v = 0.f;
@@ -332,7 +344,7 @@ __global__ void __launch_bounds__(kFuseThreads) bn_fused_fwd_kernel(const BnFuse
       p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * unbiased;
     }
   }
-  for (int c = threadIdx.x; c < 3 * cols + 4; c += blockDim.x) fs.other[c] = 0.f;
+  for (int c = threadIdx.x; c < fs.other_floats; c += blockDim.x) fs.other[c] = 0.f;
   if (threadIdx.x == 0) {
     if (p.nbt != nullptr) *p.nbt = count;
     p.stats[2 * cols] = __int_as_float((int)counter);
@@ -529,21 +541,23 @@ __global__ void __launch_bounds__(kFuseThreads) bn_fused_bwd_kernel(const BnFuse
       ta += sm_alpha[wv];
       tb += sm_hb[wv];
     }
-    if (act == ACT_DICE || act == ACT_PRELU) atomicAdd(fs.sums + 3 * cols, ta);
-    if (HEAD) atomicAdd(fs.sums + 3 * cols + 1, tb);
+    if (act == ACT_DICE || act == ACT_PRELU) atomicAdd(fs.extra + 1, ta);
+    if (HEAD) atomicAdd(fs.extra + 2, tb);
   }
   grid_barrier(fs, gridDim.x);
 
   // ---- phase 2: d_h = gamma * rstd * (dz - mean(dz) - xhat * mean(dz * xhat)) from registers ----
   const float inv_rows = 1.f / (float)p.rows;
   float mb[KMAX][4], mg[KMAX][4];
+  for (int i = threadIdx.x; i < (NS * cols) / 4; i += blockDim.x) reinterpret_cast<float4*>(smem)[i] = __ldcg(reinterpret_cast<const float4*>(fs.sums) + i);
+  __syncthreads();
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) {
     const int c0 = (k * 32 + lane) * 4;
     float4 t1 = f4_zero(), t2 = f4_zero();
     if (c0 < cols) {
-      t1 = __ldcg(reinterpret_cast<const float4*>(fs.sums + c0));
-      t2 = __ldcg(reinterpret_cast<const float4*>(fs.sums + cols + c0));
+      t1 = *reinterpret_cast<const float4*>(smem + c0);
+      t2 = *reinterpret_cast<const float4*>(smem + cols + c0);
     }
     mb[k][0] = t1.x * inv_rows; mb[k][1] = t1.y * inv_rows; mb[k][2] = t1.z * inv_rows; mb[k][3] = t1.w * inv_rows;
     mg[k][0] = t2.x * inv_rows; mg[k][1] = t2.y * inv_rows; mg[k][2] = t2.z * inv_rows; mg[k][3] = t2.w * inv_rows;
@@ -566,15 +580,15 @@ __global__ void __launch_bounds__(kFuseThreads) bn_fused_bwd_kernel(const BnFuse
   // ---- CTA 0 writes the parameter gradients and prepares the scratch of the next launch ----
   if (blockIdx.x != 0) return;
   for (int c = threadIdx.x; c < cols; c += blockDim.x) {
-    if (p.d_beta != nullptr) p.d_beta[c] = __ldcg(fs.sums + c);
-    if (p.d_gamma != nullptr) p.d_gamma[c] = __ldcg(fs.sums + cols + c);
-    if (HEAD && p.d_head_w != nullptr) p.d_head_w[c] = __ldcg(fs.sums + 2 * cols + c);
+    if (p.d_beta != nullptr) p.d_beta[c] = smem[c];
+    if (p.d_gamma != nullptr) p.d_gamma[c] = smem[cols + c];
+    if (HEAD && p.d_head_w != nullptr) p.d_head_w[c] = smem[2 * cols + c];
     if (p.d_lin_bias != nullptr) p.d_lin_bias[c] = 0.f;  // a Linear bias in front of a batch-statistics BatchNorm: gradient exactly 0
   }
-  for (int c = threadIdx.x; c < 3 * cols + 4; c += blockDim.x) fs.other[c] = 0.f;
+  for (int c = threadIdx.x; c < fs.other_floats; c += blockDim.x) fs.other[c] = 0.f;
   if (threadIdx.x == 0) {
-    if (p.d_alpha != nullptr) *p.d_alpha = __ldcg(fs.sums + 3 * cols);
-    if (HEAD && p.d_head_b != nullptr) *p.d_head_b = __ldcg(fs.sums + 3 * cols + 1);
+    if (p.d_alpha != nullptr) *p.d_alpha = __ldcg(fs.extra + 1);
+    if (HEAD && p.d_head_b != nullptr) *p.d_head_b = __ldcg(fs.extra + 2);
     reinterpret_cast<unsigned*>(p.scratch)[0] = fs.gen + 1u;
   }
 }
@@ -612,7 +626,7 @@ static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) 
 
 using namespace rh;
 
-extern "C" int64_t rh_bn_fused_scratch_floats(int cols) { return 4 + 2 * (3 * (int64_t)cols + 4); }
+extern "C" int64_t rh_bn_fused_scratch_floats(int cols) { return 32 + 2 * (int64_t)fuse_buffer_floats(cols); }
 
 extern "C" int rh_bn_fused_supported(int64_t rows, int cols, int head) {
   FusePlan pl;

@@ -36,6 +36,10 @@ struct DenseDev {
   int32_t tile_col;
 };
 
+#ifdef RH_FIELDS_TRACE
+unsigned long long* g_fields_trace = nullptr;
+#endif
+
 struct FwdParams {
   FieldDev f[RH_MAX_FIELDS];
   DenseDev d[RH_MAX_DENSE];
@@ -50,7 +54,30 @@ struct FwdParams {
   float* ylr;
   float* fsum;
   int32_t* err;
+#ifdef RH_FIELDS_TRACE
+  unsigned long long* trace;  // tools/fields_trace.cu: [block][16]: clock64 stamps of thread 0 (0..6), globaltimer at entry (8) and exit (9)
+#endif
 };
+
+#ifdef RH_FIELDS_TRACE
+// stamp after `dep` is available (the unused asm input keeps the clock read behind the load it depends on)
+#define RH_FT(ev, dep)                                                                                  \
+  do {                                                                                                  \
+    if (p.trace != nullptr && threadIdx.x == 0) {                                                       \
+      unsigned long long t__;                                                                           \
+      asm volatile("mov.u64 %0, %%clock64;" : "=l"(t__) : "r"(__float_as_int((float)(dep))) : "memory"); \
+      p.trace[(size_t)blockIdx.x * 16 + (ev)] = t__;                                                    \
+      if ((ev) == 0 || (ev) == 6) {                                                                     \
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                                          \
+        p.trace[(size_t)blockIdx.x * 16 + ((ev) == 0 ? 8 : 9)] = t__;                                   \
+      }                                                                                                 \
+    }                                                                                                   \
+  } while (0)
+#else
+#define RH_FT(ev, dep) \
+  do {                 \
+  } while (0)
+#endif
 
 struct BwdParams {
   FieldDev f[RH_MAX_FIELDS];
@@ -94,46 +121,44 @@ __device__ __forceinline__ void st_tile4(float* p, const float4& v, bool vec) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward, 16-byte lanes (v5).
-//   warp  = 32 / (LPR * S) samples;  lane = (sample slot, field slot of S, 16-byte quarter of LPR)
-//           LPR = pow2 >= dim/4 lanes per row;  S = min(32 / LPR, pow2 >= n_fields) field slots per sample
-//   A sample's fields are walked S at a time (field = slot, slot + S, ...), CH row loads in flight per lane.
-// What the memory system sees per warp and pass: the ids of S consecutive fields of ONE sample (one 64-byte run of a
-// packed (B, F) id block), S random 64-byte rows, and ONE contiguous S * 64-byte piece of the sample's tile row.
-// FM / LR: registers -> (log2 S + log2 LPR) xor-shuffles; no shared-memory round trip, no block barrier after the loop.
-// The per-field descriptors are read from the kernel parameters with a per-lane index (the S field slots of a warp read S
-// different descriptors: an indexed constant load replays S times — measured cheaper than staging them in shared memory
-// behind a block barrier, which cost 17 % of the kernel's stall samples, profiles/r02_ncu_fields_fwd.md).
-// History: v4 (warp = field group x 8 samples, partials through shared memory) ran at 9.6 us for 4096 x 26 rows; the
-// microbenchmark (tools/microbench_gather.cu) does the bare gather + tile store of the same rows in 4.9 us, 2.3 us of
-// which is an empty launch of the same grid.
+// forward, 16-byte lanes.
+//   lane  = (sample slot, 16-byte quarter): LPR lanes per sample (LPR = pow2 >= dim/4), 32/LPR samples per warp
+//   warp  = field group g of NG: it gathers fields g, g+NG, g+2NG, ... for the block's samples
+// A 4096-sample, 26-field batch is 4096 warps of ~4 row loads each instead of 512 warps of 26: the first
+// version was bound by the instruction latency of ONE warp per scheduler (ncu r01: 5 % warps active,
+// 37 k cycles for 3.5 k instructions per warp), not by memory.  The per-field descriptor index is
+// warp-uniform (constant-bank loads).  FM / LR partials meet in shared memory; warp 0 finishes the sample.
+// Tried and measured slower (round 2, B200): warp = one sample with 8 field slots x 4 quarter lanes, shuffle reductions and a
+// contiguous 512-byte tile piece per pass ("v5"): 10.6 us with the descriptors staged in shared memory, 12.8 us with per-lane
+// indexed parameter reads (8 replays per constant load), against 9.5 us here; at B = 262144 it reached 1.89 TB/s against 3.16.
 // ------------------------------------------------------------------------------------------------
-template <int LPR>
-__global__ void __launch_bounds__(256) fields_fwd_v5(const __grid_constant__ FwdParams p, const int S) {
-  constexpr int CH = 4;  // row loads in flight per lane per chunk
+template <int LPR, int NG>
+__global__ void __launch_bounds__(NG * 32) fields_fwd_v4(const __grid_constant__ FwdParams p) {
+  constexpr int SPB = 32 / LPR;  // samples per block
+  constexpr int CH = 4;          // row loads in flight per lane per chunk
+  __shared__ float4 sm_s[NG][32];
+  __shared__ float sm_ss[NG][32];
+  __shared__ float sm_lr[NG][32];
+
   pdl_wait();
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
+  const int g = threadIdx.x >> 5;
   const int q = lane % LPR;
-  const int slot = (lane / LPR) & (S - 1);
-  const int sub = lane / (LPR * S);
-  const int spw = 32 / (LPR * S);  // samples per warp
-  const int b = (blockIdx.x * (int)(blockDim.x >> 5) + warp) * spw + sub;
+  const int b = blockIdx.x * SPB + lane / LPR;
   const int dim = p.dim;
   const bool live = b < p.batch;
   const bool lane_on = live && (4 * q < dim);
   const bool want_fm = p.yfm != nullptr || p.ylr != nullptr || p.fsum != nullptr;
-  float* trow = nullptr;
-  if (live && p.tile != nullptr) trow = p.dest_rows > 0 ? p.dest[b / p.dest_rows] + (int64_t)(b % p.dest_rows) * p.tile_ld : p.tile + (int64_t)b * p.tile_ld;
 
   float4 s = f4_zero();
   float ss = 0.f, lr = 0.f;
+  RH_FT(0, 0);
 
-  for (int f0 = slot; f0 < p.n_fields; f0 += S * CH) {
+  for (int f0 = g; f0 < p.n_fields; f0 += NG * CH) {
     int32_t rid[CH];
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
-      const int f = f0 + j * S;
+      const int f = f0 + j * NG;  // warp-uniform
       rid[j] = -1;
       if (f < p.n_fields && live) {
         const FieldDev& fd = p.f[f];
@@ -145,18 +170,23 @@ __global__ void __launch_bounds__(256) fields_fwd_v5(const __grid_constant__ Fwd
         }
       }
     }
+    RH_FT(1, rid[0] + rid[1] + rid[2] + rid[3]);
     float4 v[CH];
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
       v[j] = f4_zero();
-      if (rid[j] >= 0 && lane_on) v[j] = ldg_row16(p.f[f0 + j * S].table + (int64_t)rid[j] * dim + 4 * q);
+      if (rid[j] >= 0 && lane_on) v[j] = ldg_row16(p.f[f0 + j * NG].table + (int64_t)rid[j] * dim + 4 * q);
     }
+    RH_FT(2, v[0].x + v[1].x + v[2].x + v[3].x);
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
-      const int f = f0 + j * S;
+      const int f = f0 + j * NG;
       if (f < p.n_fields && lane_on) {
         const FieldDev& fd = p.f[f];
-        if (fd.tile_col >= 0 && trow != nullptr) st_tile4(trow + fd.tile_col + 4 * q, v[j], p.tile_vec != 0);
+        if (fd.tile_col >= 0 && p.tile != nullptr) {
+          float* trow = p.dest_rows > 0 ? p.dest[b / p.dest_rows] + (int64_t)(b % p.dest_rows) * p.tile_ld : p.tile + (int64_t)b * p.tile_ld;
+          st_tile4(trow + fd.tile_col + 4 * q, v[j], p.tile_vec != 0);
+        }
         if (fd.fm_slot >= 0 && want_fm) {
           s = f4_add(s, v[j]);
           ss += f4_dot(v[j], v[j]);
@@ -169,41 +199,49 @@ __global__ void __launch_bounds__(256) fields_fwd_v5(const __grid_constant__ Fwd
     }
   }
 
-  // numeric columns: the LPR * S lanes of a sample share its dense features
-  if (live && p.tile != nullptr && p.n_dense > 0) {
-    const int gl = slot * LPR + q, G = LPR * S;
-    float* drow = p.tile + (int64_t)b * p.tile_ld;
-    for (int j = gl; j < p.n_dense; j += G) {
+  RH_FT(3, ss);
+  // numeric columns: column j belongs to warp j % NG
+  if (live && p.tile != nullptr) {
+    for (int j = g; j < p.n_dense; j += NG) {
       const DenseDev& dd = p.d[j];
-      for (int k = 0; k < dd.width; ++k) drow[dd.tile_col + k] = load_dense_value(dd.src, (int64_t)b * dd.stride + k, dd.dtype);
+      for (int k = q; k < dd.width; k += LPR) {
+        p.tile[(int64_t)b * p.tile_ld + dd.tile_col + k] = load_dense_value(dd.src, (int64_t)b * dd.stride + k, dd.dtype);
+      }
     }
   }
 
-  if (!want_fm) return;  // grid-uniform
-  // sum over the field slots of a sample (xor offsets LPR .. LPR*S/2 stay inside the sample's lane group) ...
-  for (int o = LPR; o < LPR * S; o <<= 1) {
-    s.x += __shfl_xor_sync(0xffffffffu, s.x, o);
-    s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
-    s.z += __shfl_xor_sync(0xffffffffu, s.z, o);
-    s.w += __shfl_xor_sync(0xffffffffu, s.w, o);
-    ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    lr += __shfl_xor_sync(0xffffffffu, lr, o);
+  RH_FT(4, 0);
+  if (!want_fm) return;  // block-uniform
+  if (NG > 1) {
+    sm_s[g][lane] = s;
+    sm_ss[g][lane] = ss;
+    sm_lr[g][lane] = lr;
+    __syncthreads();
+    RH_FT(5, 0);
+    if (g != 0) return;
+#pragma unroll
+    for (int k = 1; k < NG; ++k) {
+      s = f4_add(s, sm_s[k][lane]);
+      ss += sm_ss[k][lane];
+      lr += sm_lr[k][lane];
+    }
   }
-  // ... then over the quarters of the row
   float t = (s.x * s.x + s.y * s.y) + (s.z * s.z + s.w * s.w) - ss;
 #pragma unroll
   for (int o = LPR / 2; o > 0; o >>= 1) {
     t += __shfl_xor_sync(0xffffffffu, t, o);
     lr += __shfl_xor_sync(0xffffffffu, lr, o);
   }
-  if (live && slot == 0 && q == 0) {
+  if (live && q == 0) {
     if (p.yfm != nullptr) p.yfm[b] = 0.5f * t;
     if (p.ylr != nullptr) p.ylr[b] = lr + (p.lrb != nullptr ? __ldg(p.lrb) : 0.f);
   }
-  if (p.fsum != nullptr && lane_on && slot == 0) {
+  if (p.fsum != nullptr && lane_on) {
     *reinterpret_cast<float4*>(p.fsum + (int64_t)b * dim + 4 * q) = s;
   }
+  RH_FT(6, t);
 }
+
 
 // forward, scalar lanes: any dim / any alignment, tile emission only (no FM/LR).
 __global__ void __launch_bounds__(256) fields_fwd_scalar(const __grid_constant__ FwdParams p) {
@@ -406,16 +444,20 @@ static int pack_fields(const rh_field* fields, int n_fields, FieldDev* out, bool
 }
 
 template <int LPR>
-static void launch_fwd_v5(const FwdParams& p, cudaStream_t st) {
-  constexpr int FPW = 32 / LPR;  // field slots a warp can give one sample
-  int S = pow2_ceil(p.n_fields > 0 ? p.n_fields : 1);
-  if (p.n_fields == 0) S = pow2_ceil((p.n_dense + LPR - 1) / LPR);  // dense columns only: enough lanes per sample for them
-  if (S > FPW) S = FPW;
-  const int spw = FPW / S;                       // samples per warp
-  const int warps = (p.batch + spw - 1) / spw;
-  const int wpb = 8;                             // 256 threads
-  const int grid = (warps + wpb - 1) / wpb;
-  launch_k(fields_fwd_v5<LPR>, dim3(grid), dim3(wpb * 32), 0, st, p, S);
+static void launch_fwd_v4(const FwdParams& p, cudaStream_t st) {
+  constexpr int SPB = 32 / LPR;
+  const int grid = (p.batch + SPB - 1) / SPB;
+  // enough field groups that every warp has at most ~4 row loads; small field counts need fewer warps
+  const int work = p.n_fields > p.n_dense ? p.n_fields : (p.n_dense + 3) / 4;
+  if (work <= 4) {
+    launch_k(fields_fwd_v4<LPR, 1>, dim3(grid), dim3(32), 0, st, p);
+  } else if (work <= 8) {
+    launch_k(fields_fwd_v4<LPR, 2>, dim3(grid), dim3(64), 0, st, p);
+  } else if (work <= 16) {
+    launch_k(fields_fwd_v4<LPR, 4>, dim3(grid), dim3(128), 0, st, p);
+  } else {
+    launch_k(fields_fwd_v4<LPR, 8>, dim3(grid), dim3(256), 0, st, p);
+  }
 }
 
 template <int LPR>
@@ -474,6 +516,9 @@ static int fields_fwd_impl(const rh_field* fields, int n_fields, int dim, const 
     p.d[j].width = dense[j].width;
     p.d[j].tile_col = dense[j].tile_col;
   }
+#ifdef RH_FIELDS_TRACE
+  p.trace = g_fields_trace;
+#endif
   p.n_fields = n_fields;
   p.n_dense = n_dense;
   p.batch = batch;
@@ -502,12 +547,12 @@ static int fields_fwd_impl(const rh_field* fields, int n_fields, int dim, const 
   if (vec_ok) {
     const int lpr = n_fields > 0 ? pow2_ceil(dim / 4) : 4;
     switch (lpr) {
-      case 1: launch_fwd_v5<1>(p, st); break;
-      case 2: launch_fwd_v5<2>(p, st); break;
-      case 4: launch_fwd_v5<4>(p, st); break;
-      case 8: launch_fwd_v5<8>(p, st); break;
-      case 16: launch_fwd_v5<16>(p, st); break;
-      default: launch_fwd_v5<32>(p, st); break;
+      case 1: launch_fwd_v4<1>(p, st); break;
+      case 2: launch_fwd_v4<2>(p, st); break;
+      case 4: launch_fwd_v4<4>(p, st); break;
+      case 8: launch_fwd_v4<8>(p, st); break;
+      case 16: launch_fwd_v4<16>(p, st); break;
+      default: launch_fwd_v4<32>(p, st); break;
     }
   } else {
     const int64_t work = (int64_t)batch * ((int64_t)n_fields * dim + 1);
