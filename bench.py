@@ -45,25 +45,66 @@ def peaks():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + clock-event (throttle) reasons sampled DURING the timed region (B200_PROFILING.md recipe).  NVML is queried in a
+    thread every 2 ms (the timed region of the default run is ~40 ms; `nvidia-smi -lms 100` saw a single sample of it); when NVML
+    cannot be loaded the nvidia-smi poller is the fallback."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index=0):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.thread, self.nv = index, [], None, None, None
+        self.stop_flag = threading.Event()
+        self.sm, self.bits, self.sm_max = [], 0, None
+
+    def _nvml_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        try:
+            ids = [int(v) for v in vis.split(",") if v.strip() != ""]
+            return ids[self.index] if ids else self.index
+        except Exception:
+            return self.index
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._nvml_index())
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nv = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
+
+    def _poll_nvml(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nv is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            nv = self.nv
+            masks = [nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlowdown, nv.nvmlClocksEventReasonSwThermalSlowdown, nv.nvmlClocksEventReasonSwPowerCap]
+            sm = sorted(self.sm)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.sm_max, "reasons": [n for n, m in zip(self.NAMES, masks) if self.bits & m], "samples": len(sm), "source": "nvml, 2 ms period"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -73,9 +114,8 @@ class ClockSampler(object):
             pass
         sm = sorted(int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit())
         mx = [int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for j, n in enumerate(names) if any(len(r) >= 6 and r[2 + j].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        reasons = [n for j, n in enumerate(self.NAMES) if any(len(r) >= 6 and r[2 + j].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm), "source": "nvidia-smi -lms 20"}
 
 
 # -----------------------------------------------------------------------------------------------------------------
@@ -590,14 +630,17 @@ def run_b200_arm(args):
         algo = ALGO_BYTES_FWD_PER_SAMPLE * BATCH
         achieved = algo / (avg_ms * 1e-3) / 1e9
         traffic = None
-        tf = os.path.join(ROOT, "profiles", "r01_fields_fwd_dram_bytes.json")
-        if os.path.exists(tf):
+        import glob
+        tfs = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_fields_fwd_dram_bytes.json")))  # the latest round's ncu --set full capture
+        traffic_src = None
+        if tfs:
             try:
-                traffic = json.load(open(tf)).get("dram_bytes_per_launch")
+                traffic = json.load(open(tfs[-1])).get("dram_bytes_per_launch")
+                traffic_src = "profiles/" + os.path.basename(tfs[-1])
             except Exception:
                 traffic = None
         roof = {"bound": "hbm", "kernel": "rh::fields_fwd_v4<4,8> (fused 26-field gather + FM + LR + tile, the north_star kernel)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "algorithmic_bytes_per_launch": algo, "avg_us": avg_ms * 1e3, "median_us": med_ms * 1e3, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": algo, "avg_us": avg_ms * 1e3, "median_us": med_ms * 1e3, "peak_source": peak_src,
                 "note": "latency floor, not bandwidth: 106 k random 64-B rows cost 8.8 us at any footprint (profiles/r01_microbench_gather.csv); the same kernel reaches 3.16 TB/s at B=262144 = the random-gather ceiling of this part (profiles/r01_sweep_fields_fwd.csv)"}
         gflops, gus = time_tower_gemms(device)
         try:
