@@ -256,32 +256,44 @@ __global__ void __launch_bounds__(kFuseThreads) bn_fused_fwd_kernel(const BnFuse
   grid_barrier(fs, gridDim.x);
   RH_BT(3);
 
-  // ---- phase 2: statistics -> per-column scale / shift, apply from registers ----
+  // ---- phase 2: statistics -> per-column mean / scale, apply from registers ----
+  // ONE thread per column turns the grid's sums into (mean, gamma * rstd) and shares them through shared memory.  (Every thread
+  // deriving them for its own 4 * KMAX columns — 5 IEEE divisions / square roots per column, 16x redundant across the CTA's warps,
+  // all of them hitting the same few L2 lines right behind the atomics — was ~6 us of an 11 us kernel, tools/bnfuse_trace.cu.)
   const float n = (float)p.rows;
+  float* s_mu = smem;
+  float* s_sc = smem + cols;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    const float t1 = __ldcg(fs.sums + c), t2 = __ldcg(fs.sums + cols + c);
+    const float mean = __ldg(p.h + c) + t1 / n;
+    float v = (t2 - t1 * t1 / n) / n;
+    if (v < 0.f) v = 0.f;
+    s_mu[c] = mean;
+    s_sc[c] = (p.gamma != nullptr ? __ldg(p.gamma + c) : 1.f) * (1.f / sqrtf(v + p.bn_eps));
+    if (blockIdx.x == 0) {  // CTA 0 publishes the statistics (concurrently with everybody's apply phase)
+      p.stats[c] = mean;
+      p.stats[cols + c] = v;
+      if (p.running_mean != nullptr) p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * mean;
+      if (p.running_var != nullptr) {
+        const float unbiased = p.rows > 1 ? v * (n / (n - 1.f)) : v;
+        p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * unbiased;
+      }
+    }
+  }
+  __syncthreads();
   float mu[KMAX][4], sc[KMAX][4], bt[KMAX][4], hw[KMAX][4];
-  load_colconst<KMAX>(p.gamma, lane, cols, sc, 1.f);
   load_colconst<KMAX>(p.beta, lane, cols, bt, 0.f);
   if (HEAD) load_colconst<KMAX>(p.head_w, lane, cols, hw, 0.f);
-  // the grid's sums: ONE read per CTA into shared memory (every warp reading them from L2 put 16 x n_ctas requests on the same
-  // few lines, right behind the atomics: the apply phase spent most of its 6 us waiting there)
-  for (int i = threadIdx.x; i < (2 * cols) / 4; i += blockDim.x) reinterpret_cast<float4*>(smem)[i] = __ldcg(reinterpret_cast<const float4*>(fs.sums) + i);
-  __syncthreads();
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) {
     const int c0 = (k * 32 + lane) * 4;
-    float4 t1 = f4_zero(), t2 = f4_zero();
+    float4 m4 = f4_zero(), s4 = f4_zero();
     if (c0 < cols) {
-      t1 = *reinterpret_cast<const float4*>(smem + c0);
-      t2 = *reinterpret_cast<const float4*>(smem + cols + c0);
+      m4 = *reinterpret_cast<const float4*>(s_mu + c0);
+      s4 = *reinterpret_cast<const float4*>(s_sc + c0);
     }
-    const float a1[4] = {t1.x, t1.y, t1.z, t1.w}, a2[4] = {t2.x, t2.y, t2.z, t2.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float v = (a2[j] - a1[j] * a1[j] / n) / n;
-      if (v < 0.f) v = 0.f;
-      mu[k][j] = sh[k][j] + a1[j] / n;
-      sc[k][j] *= 1.f / sqrtf(v + p.bn_eps);
-    }
+    mu[k][0] = m4.x; mu[k][1] = m4.y; mu[k][2] = m4.z; mu[k][3] = m4.w;
+    sc[k][0] = s4.x; sc[k][1] = s4.y; sc[k][2] = s4.z; sc[k][3] = s4.w;
   }
   const float alpha = p.alpha != nullptr ? __ldg(p.alpha) : 0.f;
   const bool drop = p.p_drop > 0.f;
@@ -329,21 +341,8 @@ __global__ void __launch_bounds__(kFuseThreads) bn_fused_fwd_kernel(const BnFuse
   }
   RH_BT(4);
 
-  // ---- CTA 0 publishes the statistics and prepares the scratch of the next launch (concurrently with the other CTAs' phase 2) ----
+  // ---- CTA 0 prepares the scratch of the next launch ----
   if (blockIdx.x != 0) return;
-  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
-    const float t1 = smem[c], t2 = smem[cols + c];
-    const float mean = __ldg(p.h + c) + t1 / n;
-    float v = (t2 - t1 * t1 / n) / n;
-    if (v < 0.f) v = 0.f;
-    p.stats[c] = mean;
-    p.stats[cols + c] = v;
-    if (p.running_mean != nullptr) p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * mean;
-    if (p.running_var != nullptr) {
-      const float unbiased = p.rows > 1 ? v * (n / (n - 1.f)) : v;
-      p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * unbiased;
-    }
-  }
   for (int c = threadIdx.x; c < fs.other_floats; c += blockDim.x) fs.other[c] = 0.f;
   if (threadIdx.x == 0) {
     if (p.nbt != nullptr) *p.nbt = count;
@@ -371,14 +370,20 @@ __global__ void __launch_bounds__(kFuseThreads) bn_fused_bwd_kernel(const BnFuse
 
   float mu[KMAX][4], rstd[KMAX][4], gam[KMAX][4], bet[KMAX][4], hw[KMAX][4];
   load_colconst<KMAX>(p.stats, lane, cols, mu, 0.f);
-  load_colconst<KMAX>(p.stats + cols, lane, cols, rstd, 1.f);
   load_colconst<KMAX>(p.gamma, lane, cols, gam, 1.f);
   load_colconst<KMAX>(p.beta, lane, cols, bet, 0.f);
   if (HEAD) load_colconst<KMAX>(p.head_w, lane, cols, hw, 0.f);
+  // rstd: one thread per column (an IEEE division + square root per column per THREAD was 16x redundant), shared through smem
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) smem[c] = 1.f / sqrtf(__ldg(p.stats + cols + c) + p.bn_eps);
+  __syncthreads();
 #pragma unroll
-  for (int k = 0; k < KMAX; ++k)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) rstd[k][j] = 1.f / sqrtf(rstd[k][j] + p.bn_eps);
+  for (int k = 0; k < KMAX; ++k) {
+    const int c0 = (k * 32 + lane) * 4;
+    float4 r4 = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (c0 < cols) r4 = *reinterpret_cast<const float4*>(smem + c0);
+    rstd[k][0] = r4.x; rstd[k][1] = r4.y; rstd[k][2] = r4.z; rstd[k][3] = r4.w;
+  }
+  __syncthreads();  // the per-warp slabs below reuse this shared memory
   const float alpha = p.alpha != nullptr ? __ldg(p.alpha) : 0.f;
   const bool drop = p.p_drop > 0.f;
   const float keep_scale = drop ? 1.f / (1.f - p.p_drop) : 1.f;
@@ -644,14 +649,17 @@ unsigned long long* g_bn_trace = nullptr;
       case 1 * 16 + 2: launch_k(KERNEL<1, 2, ACTV, HEADV>, dim3(pl.grid), dim3(kFuseThreads), smem, st, p); break;             \
       case 1 * 16 + 4: launch_k(KERNEL<1, 4, ACTV, HEADV>, dim3(pl.grid), dim3(kFuseThreads), smem, st, p); break;             \
       case 2 * 16 + 2: launch_k(KERNEL<2, 2, ACTV, HEADV>, dim3(pl.grid), dim3(kFuseThreads), smem, st, p); break;             \
-      case 4 * 16 + 1: launch_k(KERNEL<4, 1, ACTV, HEADV>, dim3(pl.grid), dim3(kFuseThreads), smem, st, p); break;             \
+      case 4 * 16 + 1:                                                                                                         \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(KERNEL<4, 1, ACTV, HEADV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); \
+        launch_k(KERNEL<4, 1, ACTV, HEADV>, dim3(pl.grid), dim3(kFuseThreads), smem, st, p);                                   \
+        break;                                                                                                                 \
       default: set_error("bn_fused: no instantiation for kmax %d rpw %d", pl.kmax, pl.rpw); return RH_ERR_UNSUPPORTED; \
     }                                                                                                        \
   } while (0)
 
 #define RH_FUSE_DISPATCH(KERNEL, HEADV)                                      \
   do {                                                                       \
-    if (smem > 48 * 1024) {                                                  \
+    if (smem > 64 * 1024 || (smem > 48 * 1024 && pl.kmax != 4)) {            \
       set_error("bn_fused: %zu bytes of shared memory", smem);               \
       return RH_ERR_UNSUPPORTED;                                             \
     }                                                                        \

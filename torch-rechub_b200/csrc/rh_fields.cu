@@ -154,15 +154,30 @@ __global__ void __launch_bounds__(NG * 32) fields_fwd_v4(const __grid_constant__
   float ss = 0.f, lr = 0.f;
   RH_FT(0, 0);
 
+  // numeric columns, part 1: this warp's first two columns are loaded NOW so that their latency hides behind the gather
+  // (loaded after it they were a third dependent memory round trip, tools/fields_trace.cu)
+  float dv[2] = {0.f, 0.f};
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int j = g + NG * t;
+    if (live && p.tile != nullptr && j < p.n_dense && q < p.d[j].width) dv[t] = load_dense_value(p.d[j].src, (int64_t)b * p.d[j].stride + q, p.d[j].dtype);
+  }
+  const bool want_lr = want_fm && p.lrw != nullptr;
+
   for (int f0 = g; f0 < p.n_fields; f0 += NG * CH) {
     int32_t rid[CH];
+    float4 w[CH];
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
       const int f = f0 + j * NG;  // warp-uniform
       rid[j] = -1;
+      w[j] = f4_zero();
       if (f < p.n_fields && live) {
         const FieldDev& fd = p.f[f];
         const int64_t id = load_id(fd.ids, (int64_t)b * fd.id_stride, fd.is_i32 != 0);
+        // The LR weights of the chunk's fields do not depend on the ids: they travel with them.  (Loaded in the consume loop below
+        // they sat behind the volatile tile stores — four SERIAL L2 round trips, 2.7 us of a 7.9 us launch in tools/fields_trace.cu.)
+        if (want_lr && fd.fm_slot >= 0 && lane_on) w[j] = __ldg(reinterpret_cast<const float4*>(p.lrw + (int64_t)fd.fm_slot * dim + 4 * q));
         if ((uint64_t)id < (uint64_t)fd.vocab) {
           rid[j] = (int32_t)id;
         } else if (q == 0 && p.err != nullptr) {
@@ -190,23 +205,24 @@ __global__ void __launch_bounds__(NG * 32) fields_fwd_v4(const __grid_constant__
         if (fd.fm_slot >= 0 && want_fm) {
           s = f4_add(s, v[j]);
           ss += f4_dot(v[j], v[j]);
-          if (p.lrw != nullptr) {
-            const float4 w = __ldg(reinterpret_cast<const float4*>(p.lrw + (int64_t)fd.fm_slot * dim + 4 * q));
-            lr += f4_dot(v[j], w);
-          }
+          lr += f4_dot(v[j], w[j]);
         }
       }
     }
   }
 
   RH_FT(3, ss);
-  // numeric columns: column j belongs to warp j % NG
+  // numeric columns, part 2: store the preloaded values; anything beyond them (more than 2 NG columns, widths above LPR) the slow way
   if (live && p.tile != nullptr) {
+    float* drow = p.tile + (int64_t)b * p.tile_ld;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int j = g + NG * t;
+      if (j < p.n_dense && q < p.d[j].width) drow[p.d[j].tile_col + q] = dv[t];
+    }
     for (int j = g; j < p.n_dense; j += NG) {
       const DenseDev& dd = p.d[j];
-      for (int k = q; k < dd.width; k += LPR) {
-        p.tile[(int64_t)b * p.tile_ld + dd.tile_col + k] = load_dense_value(dd.src, (int64_t)b * dd.stride + k, dd.dtype);
-      }
+      for (int k = q + (j < g + 2 * NG ? LPR : 0); k < dd.width; k += LPR) drow[dd.tile_col + k] = load_dense_value(dd.src, (int64_t)b * dd.stride + k, dd.dtype);
     }
   }
 
@@ -305,21 +321,16 @@ __global__ void __launch_bounds__(128) fields_bwd_v4(const __grid_constant__ Bwd
     w = __ldg(reinterpret_cast<const float4*>(p.lrw + (int64_t)fd.fm_slot * dim + 4 * q));
   }
 
-  int32_t rid[ITER];
+  // Everything a sample needs except the table row itself is addressed by the sample, not by its id: those loads are issued
+  // together with the id loads (behind the id check they were a second dependent round trip; an out-of-range id only costs the
+  // loads of that sample, and nothing is written for it).
+  int64_t idv[ITER];
 #pragma unroll
   for (int i = 0; i < ITER; ++i) {
     const int b = base + i * spi + sl;
-    rid[i] = -1;
-    if (b < p.batch) {
-      const int64_t id = load_id(fd.ids, (int64_t)b * fd.id_stride, fd.is_i32 != 0);
-      if ((uint64_t)id < (uint64_t)fd.vocab) {
-        rid[i] = (int32_t)id;
-      } else if (q == 0 && p.err != nullptr) {
-        *p.err = 1 + f;
-      }
-    }
+    idv[i] = -1;
+    if (b < p.batch) idv[i] = load_id(fd.ids, (int64_t)b * fd.id_stride, fd.is_i32 != 0);
   }
-
   float4 g[ITER], e[ITER], S[ITER];
   float dyf[ITER], dyl[ITER];
 #pragma unroll
@@ -330,11 +341,10 @@ __global__ void __launch_bounds__(128) fields_bwd_v4(const __grid_constant__ Bwd
     S[i] = f4_zero();
     dyf[i] = 0.f;
     dyl[i] = 0.f;
-    if (rid[i] >= 0 && lane_on) {
+    if (b < p.batch && lane_on) {
       if (has_dtile) g[i] = ld_tile4(p.dtile + (int64_t)b * p.dtile_ld + fd.tile_col + 4 * q, p.dtile_vec != 0);
       if (fm) {
-        e[i] = from_tile ? ld_tile4(p.tile + (int64_t)b * p.tile_ld + fd.tile_col + 4 * q, p.tile_vec != 0)
-                         : ldg_row16(fd.table + (int64_t)rid[i] * dim + 4 * q);
+        if (from_tile) e[i] = ld_tile4(p.tile + (int64_t)b * p.tile_ld + fd.tile_col + 4 * q, p.tile_vec != 0);
         if (p.dyfm != nullptr) {
           S[i] = ldg_row16(p.fsum + (int64_t)b * dim + 4 * q);
           dyf[i] = __ldg(p.dyfm + b);
@@ -342,6 +352,20 @@ __global__ void __launch_bounds__(128) fields_bwd_v4(const __grid_constant__ Bwd
         if (p.dylr != nullptr) dyl[i] = __ldg(p.dylr + b);
       }
     }
+  }
+  int32_t rid[ITER];
+#pragma unroll
+  for (int i = 0; i < ITER; ++i) {
+    const int b = base + i * spi + sl;
+    rid[i] = -1;
+    if (b < p.batch) {
+      if ((uint64_t)idv[i] < (uint64_t)fd.vocab) {
+        rid[i] = (int32_t)idv[i];
+      } else if (q == 0 && p.err != nullptr) {
+        *p.err = 1 + f;
+      }
+    }
+    if (fm && !from_tile && rid[i] >= 0 && lane_on) e[i] = ldg_row16(fd.table + (int64_t)rid[i] * dim + 4 * q);  // no saved tile: re-gather
   }
 
   float4 dw = f4_zero();

@@ -164,9 +164,9 @@ extern "C" int rh_head_bwd(const float* x, int64_t x_ld, int64_t rows, int k, co
 // launch latency.  Forward: per-block partial sums + a last-block finalisation in a fixed order (deterministic); `partial` holds
 // gridDim floats + a ticket counter (zero on entry, left zero).
 namespace rh {
-__global__ void __launch_bounds__(256) bce_fwd_kernel(const float* __restrict__ p, const float* __restrict__ y, int64_t n, float* __restrict__ partial,
+__global__ void __launch_bounds__(1024) bce_fwd_kernel(const float* __restrict__ p, const float* __restrict__ y, int64_t n, float* __restrict__ partial,
                                                       unsigned* __restrict__ ticket, float* __restrict__ loss) {
-  __shared__ float sm[8];
+  __shared__ float sm[32];
   __shared__ bool is_last;
   pdl_wait();
   float acc = 0.f;
@@ -181,9 +181,14 @@ __global__ void __launch_bounds__(256) bce_fwd_kernel(const float* __restrict__ 
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sm[w];
-    partial[blockIdx.x] = t;
-    __threadfence();
-    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    if (gridDim.x == 1) {
+      *loss = t / (float)n;
+      is_last = false;
+    } else {
+      partial[blockIdx.x] = t;
+      __threadfence();
+      is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
   }
   __syncthreads();
   if (!is_last || threadIdx.x != 0) return;
@@ -207,9 +212,11 @@ __global__ void __launch_bounds__(256) bce_bwd_kernel(const float* __restrict__ 
 
 extern "C" int rh_bce_fwd(const float* prob, const float* target, int64_t n, float* scratch, float* loss, void* stream) {
   RH_REQUIRE(prob && target && scratch && loss && n > 0, RH_ERR_INVALID_ARG, "rh_bce_fwd: bad arguments");
-  int64_t g = (n + 1023) / 1024;
+  // up to 16 k probabilities: ONE 1024-thread block (no ticket, no fence: a training batch's loss is launch latency, not bandwidth)
+  const bool one = n <= 16384;
+  int64_t g = one ? 1 : (n + 2047) / 2048;
   if (g > 64) g = 64;
-  launch_k(rh::bce_fwd_kernel, dim3((unsigned)g), dim3(256), 0, (cudaStream_t)stream, prob, target, n, scratch, reinterpret_cast<unsigned*>(scratch + 64), loss);
+  launch_k(rh::bce_fwd_kernel, dim3((unsigned)g), dim3(one ? 1024 : 256), 0, (cudaStream_t)stream, prob, target, n, scratch, reinterpret_cast<unsigned*>(scratch + 64), loss);
   RH_LAUNCH_CHECK();
   return RH_OK;
 }
