@@ -421,6 +421,10 @@ int rh_gemm_tf32x3(const float* A, int64_t lda, int a_mn_major,
                    const float* B, int64_t ldb, int b_mn_major,
                    float* C, int64_t ldc, int M, int N, int K,
                    const float* bias, int split_k, void* stream);
+/* Output-tile width of rh_gemm_tf32x3: 0 = chosen per problem (64 when 128-wide tiles would leave more than half of the SMs idle and
+ * the 64-wide grid still fits one wave), 64 / 128 = forced (A/B runs, tests).  Returns the setting in force. */
+int rh_gemm_tile_n(int set);
+
 
 /* The same GEMM (split_k = 1) with BatchNorm1d's training-mode column statistics of C = A B^T + bias computed in the epilogue —
  * rh_gemm_tf32x3 followed by rh_colstats in one launch (MLP.forward, basic/layers.py:282-283: Linear then BatchNorm1d).

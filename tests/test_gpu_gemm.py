@@ -53,6 +53,23 @@ def test_tower_shapes(M, N, K, a_mn, b_mn, bias, split_k):
     assert rel < 2e-6, rel
 
 
+@pytest.mark.parametrize("tile_n", [64, 128])
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn,bias,split_k", [
+    (4096, 256, 429, False, False, True, 1), (4096, 429, 256, False, True, False, 1), (128, 256, 4096, True, True, False, 32), (256, 429, 4096, True, True, False, 16),
+    (300, 70, 50, False, False, True, 1), (257, 200, 96, True, False, True, 2), (130, 64, 40, False, True, True, 1)])
+def test_both_tile_widths(tile_n, M, N, K, a_mn, b_mn, bias, split_k):
+    """The 128 x 64 and 128 x 128 output tiles (rh_gemm_tile_n forces one; 0 = chosen per problem) give fp32-level results for every
+    operand-major combination, N / K tails, bias and split-K."""
+    from torch_rechub.b200 import _lib
+    L = _lib.lib()
+    assert L.rh_gemm_tile_n(tile_n) == tile_n
+    try:
+        rel, C = _run(M, N, K, a_mn, b_mn, bias, split_k, lda_pad=1, ldb_pad=2)
+    finally:
+        L.rh_gemm_tile_n(0)
+    assert rel < 2e-6, rel
+
+
 def test_is_more_accurate_than_tf32_and_matches_fp32_level():
     from torch_rechub.b200 import ops
     g = torch.Generator().manual_seed(1)

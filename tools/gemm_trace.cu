@@ -34,7 +34,9 @@ int main() {
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
+  for (int tn : {128, 64})
   for (const Shape& s : shapes) {
+    rh_gemm_tile_n(tn);
     const int lda = s.a_mn ? (s.M + 3) / 4 * 4 : (s.K + 3) / 4 * 4;
     const int ldb = s.b_mn ? (s.N + 3) / 4 * 4 : (s.K + 3) / 4 * 4;
     const int ldc = (s.N + 3) / 4 * 4;
@@ -54,10 +56,10 @@ int main() {
     int split = s.split < kb ? s.split : kb;
     const int per = (kb + split - 1) / split;
     split = (kb + per - 1) / per;
-    const int ctas = ((s.M + 127) / 128) * ((s.N + 127) / 128) * split;
+    const int ctas = ((s.M + 127) / 128) * ((s.N + tn - 1) / tn) * split;
     std::vector<unsigned long long> h((size_t)ctas * 16);
     cudaMemcpy(h.data(), trace, h.size() * 8, cudaMemcpyDeviceToHost);
-    printf("%s M=%d N=%d K=%d split=%d ctas=%d k-blocks/cta=%d  event time (single launch, idle GPU) %.2f us\n", s.name, s.M, s.N, s.K, split, ctas, per, ms * 1e3);
+    printf("%s tile 128x%d  M=%d N=%d K=%d split=%d ctas=%d k-blocks/cta=%d  event time (single launch, idle GPU) %.2f us\n", s.name, tn, s.M, s.N, s.K, split, ctas, per, ms * 1e3);
     for (int ev = 1; ev < 12; ++ev) {
       std::vector<double> d;
       for (int c = 0; c < ctas; ++c) {

@@ -5,7 +5,8 @@
 // hi*hi + hi*lo + lo*hi in fp32 TMEM accumulators) restores ~2^-22 per product — fp32-level — at 3 tensor-core MMAs
 // per k-step, still ~10x the fp32 SIMT rate the reference-equivalent cuBLAS sgemm runs at on this part.
 //
-// Structure (one 128x128 output tile per CTA, BLOCK_K = 32 floats = one 128-byte swizzle row, 3-stage ring):
+// Structure (one 128 x BN output tile per CTA, BN = 128 or — when 128-wide tiles would leave more than half of the SMs idle — 64;
+// BLOCK_K = 32 floats = one 128-byte swizzle row, 3-stage ring):
 //   warp 0      TMA producer: cp.async.bulk.tensor.2d of the raw fp32 A / B tiles (SWIZZLE_128B), mbarrier tx bytes
 //   warps 2..7  splitters: read the raw tiles, write hi (truncated) back in place and lo into the twin tiles,
 //               fence.proxy.async, arrive on `ready`
@@ -116,6 +117,7 @@ struct GemmP {
   int a_mn, b_mn;   // operand majors: 0 = K-major, 1 = MN-major
   int kblocks_per_split;
   int reduce;       // 1: red.global.add into C (split-K), 0: plain stores
+  int bn;           // output tile width: 128 or 64 (B tile = bn x 32 floats; the stage layout keeps its 16 KB slots)
   // STATS instantiation only (BatchNorm column statistics of C in the epilogue):
   float* stats;            // (2N + 1): mean | biased variance | step counter bits
   float* partial;          // [n_tile][m_tile][2][128]: per-tile column mean and M2
@@ -183,7 +185,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * kBN;
+  const int bn = STATS ? kBN : p.bn;
+  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * bn;
   const int total_kb = (p.K + kBK - 1) / kBK;
   const int kb0 = blockIdx.z * p.kblocks_per_split;
   int kb1 = kb0 + p.kblocks_per_split;
@@ -223,7 +226,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const uint32_t ph = (it / kStages) & 1;
         mbar_wait(&empty[s], ph ^ 1);
         uint8_t* st = smem + (size_t)s * kStageBytes;
-        mbar_arrive_expect_tx(&full[s], 2 * kTileBytes);
+        mbar_arrive_expect_tx(&full[s], kTileBytes + bn * kBK * 4);
         const int k0 = (kb0 + it) * kBK;
         if (p.a_mn) {
           for (int i = 0; i < 4; ++i) tma_load_2d(st + i * 4096, &map_a, &full[s], m0 + 32 * i, k0);
@@ -231,7 +234,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           tma_load_2d(st, &map_a, &full[s], k0, m0);
         }
         if (p.b_mn) {
-          for (int i = 0; i < 4; ++i) tma_load_2d(st + kTileBytes + i * 4096, &map_b, &full[s], n0 + 32 * i, k0);
+          for (int i = 0; i < bn / 32; ++i) tma_load_2d(st + kTileBytes + i * 4096, &map_b, &full[s], n0 + 32 * i, k0);
         } else {
           tma_load_2d(st + kTileBytes, &map_b, &full[s], k0, n0);
         }
@@ -241,7 +244,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) | ((uint32_t)(kBN >> 3) << 17) |
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) | ((uint32_t)(bn >> 3) << 17) |
                            ((uint32_t)(kBM >> 4) << 24);
     const uint32_t a_step = p.a_mn ? (1024u >> 4) : (32u >> 4);
     const uint32_t b_step = p.b_mn ? (1024u >> 4) : (32u >> 4);
@@ -281,7 +284,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       mbar_wait(&full[s], ph);
       if (t == 0 && it == 0) RH_TR(4);
       uint8_t* st = smem + (size_t)s * kStageBytes;
-      for (int i = t; i < 2 * kTileBytes / 16; i += kSplitWarps * 32) {
+      for (int i = t; i < (kTileBytes + bn * kBK * 4) / 16; i += kSplitWarps * 32) {  // A tile, then the bn x 32 B tile right behind it
         float4* src = reinterpret_cast<float4*>(st + (size_t)i * 16);
         float4* dst = reinterpret_cast<float4*>(st + 2 * kTileBytes + (size_t)i * 16);
         const float4 x = *src;
@@ -311,7 +314,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       const bool add_bias = p.bias != nullptr && blockIdx.z == 0;
       const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15u) == 0);
 #pragma unroll 1
-      for (int c = 0; c < kBN / 32; ++c) {
+      for (int c = 0; c < bn / 32; ++c) {
         uint32_t r[32], x[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
         tmem_ld32(taddr, r);
@@ -471,9 +474,9 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// rows x K fp32 matrix used as a [rows, K] operand.  K-major: stored [rows][ld] -> box {32 (K), 128 (rows)}.
-// MN-major: stored [K][ld] with `rows` contiguous -> box {32 (rows), 32 (K)}.
-static int make_map(CUtensorMap* map, const float* base, int64_t ld, int rows, int K, bool mn_major) {
+// rows x K fp32 matrix used as a [rows, K] operand.  K-major: stored [rows][ld] -> box {32 (K), tile_rows}.
+// MN-major: stored [K][ld] with `rows` contiguous -> box {32 (rows), 32 (K)} (tile_rows / 32 boxes per tile).
+static int make_map(CUtensorMap* map, const float* base, int64_t ld, int rows, int K, bool mn_major, int tile_rows) {
   EncodeTiledFn fn = encode_fn();
   RH_REQUIRE(fn != nullptr, RH_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t gdim[2], gstride[1];
@@ -487,7 +490,7 @@ static int make_map(CUtensorMap* map, const float* base, int64_t ld, int rows, i
     gdim[0] = (cuuint64_t)K;
     gdim[1] = (cuuint64_t)rows;
     box[0] = 32;
-    box[1] = 128;
+    box[1] = (cuuint32_t)tile_rows;
   }
   gstride[0] = (cuuint64_t)ld * sizeof(float);
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -513,6 +516,12 @@ struct StatsArgs {
 #ifdef RH_GEMM_TRACE
 unsigned long long* g_gemm_trace = nullptr;  // set by tools/gemm_trace.cu
 #endif
+static int g_tile_n = 0;  // 0 = choose per problem, 64 / 128 = forced (rh_gemm_tile_n: A/B runs and tests)
+
+extern "C" int rh_gemm_tile_n(int set) {
+  if (set == 0 || set == 64 || set == 128) g_tile_n = set;
+  return g_tile_n;
+}
 
 static int gemm_impl(const float* A, int64_t lda, int a_mn_major, const float* B, int64_t ldb, int b_mn_major, float* C, int64_t ldc, int M, int N,
                      int K, const float* bias, int split_k, void* stream, const StatsArgs* st) {
@@ -528,10 +537,19 @@ static int gemm_impl(const float* A, int64_t lda, int a_mn_major, const float* B
   const int per = (total_kb + split_k - 1) / split_k;
   split_k = (total_kb + per - 1) / per;  // no empty splits
 
+  // Tile width: the tower's GEMMs are small (M = 4096, N <= 429): 128-wide tiles give 32-64 CTAs for 148 SMs, and the k-loop of a
+  // CTA is bound by its own shared-memory traffic (~1400 cycles per k-block, tools/gemm_trace.cu), so halving the B tile both
+  // doubles the CTAs and shortens each k-block.  64 only while the grid still fits one wave.
+  const int m_tiles = (M + kBM - 1) / kBM;
+  int bn = kBN;
+  if (st == nullptr && g_tile_n != 128) {
+    const int64_t ctas128 = (int64_t)m_tiles * ((N + 127) / 128) * split_k, ctas64 = (int64_t)m_tiles * ((N + 63) / 64) * split_k;
+    if (g_tile_n == 64 || (ctas128 * 2 <= num_sms() && ctas64 <= num_sms())) bn = 64;
+  }
   CUtensorMap map_a, map_b;
-  int rc = make_map(&map_a, A, lda, M, K, a_mn_major != 0);
+  int rc = make_map(&map_a, A, lda, M, K, a_mn_major != 0, kBM);
   if (rc != RH_OK) return rc;
-  rc = make_map(&map_b, B, ldb, N, K, b_mn_major != 0);
+  rc = make_map(&map_b, B, ldb, N, K, b_mn_major != 0, bn);
   if (rc != RH_OK) return rc;
 
   GemmP p;
@@ -546,10 +564,11 @@ static int gemm_impl(const float* A, int64_t lda, int a_mn_major, const float* B
   p.b_mn = b_mn_major != 0;
   p.kblocks_per_split = per;
   p.reduce = split_k > 1 ? 1 : 0;
+  p.bn = bn;
 #ifdef RH_GEMM_TRACE
   p.trace = g_gemm_trace;
 #endif
-  dim3 grid((M + kBM - 1) / kBM, (N + kBN - 1) / kBN, split_k);
+  dim3 grid(m_tiles, (N + bn - 1) / bn, split_k);
 
   static bool configured[2] = {false, false};
   const int which = st != nullptr ? 1 : 0;

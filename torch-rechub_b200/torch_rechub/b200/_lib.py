@@ -66,6 +66,7 @@ PROTOTYPES = {
     "rh_bn_act_fused_bwd": [c_p, c_i64, c_i64, c_i, c_p, c_f, c_p, c_p, c_i, c_p, c_f, c_f, ctypes.c_uint32, c_p, c_i64, c_p, c_p, c_p, c_i, c_p, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "rh_head_fwd": [c_p, c_i64, c_i64, c_i, c_p, c_p, c_p, c_p, c_i, c_p, c_p],
     "rh_head_bwd": [c_p, c_i64, c_i64, c_i, c_p, c_p, c_p, c_i, c_p, c_i64, c_p, c_p, c_p, c_p],
+    "rh_gemm_tile_n": [c_i],
     "rh_copy_segments": [c_i, c_p, c_p, c_p, c_p],
     "rh_bce_fwd": [c_p, c_p, c_i64, c_p, c_p, c_p],
     "rh_bce_bwd": [c_p, c_p, c_p, c_i64, c_p, c_p],
@@ -125,6 +126,7 @@ def lib():
                 raise EngineMissing("librechub_b200.so ABI version %d != 1" % handle.rh_abi_version())
             from . import config
             handle.rh_set_pdl(int(bool(config.pdl)))
+            handle.rh_gemm_tile_n(int(config.gemm_tile_n))
             _lib = handle
     return _lib
 

@@ -92,3 +92,7 @@ l2_fetch_granularity = int(os.environ.get("RECHUB_B200_L2_FETCH_GRANULARITY", "3
 
 # Set by the graph runner while inputs live in static buffers that the next batch overwrites.
 static_inputs = False
+
+# Output-tile width of the tower GEMM (rh_gemm_tile_n): 0 = the library chooses per problem (128 x 64 tiles when 128 x 128 would leave
+# more than half of the SMs idle), 64 / 128 force one (A/B runs).
+gemm_tile_n = int(os.environ.get("RECHUB_B200_GEMM_TILE_N", "0"))
