@@ -18,3 +18,16 @@ except Exception as e:
 PY
 done
 timeout -k 10 200 python tools/kernel_times.py > gpurun_out/${T}_ktimes.txt 2>&1; grep -v Warn gpurun_out/${T}_ktimes.txt | head -24 | cut -c1-150
+# software prefetch of the next batch's rows into L2 (e2e path), L2 fetch granularity, concurrent optimisers
+for cfg in "RECHUB_B200_NEXT_BATCH_PREFETCH=1" "RECHUB_B200_L2_FETCH_GRANULARITY=64" "RECHUB_B200_CONCURRENT_OPT=1"; do
+  env $cfg timeout -k 10 300 python bench.py --no-cpu-baseline > gpurun_out/${T}_bench_ab.json 2> gpurun_out/${T}_bench_ab.err
+  python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/${T}_bench_ab.json").read().strip().splitlines()[-1])
+    print("BENCH $cfg value %.2f M/s  %.4f ms  e2e %.2f M/s  fwd %.2f us" % (d["value"]/1e6, d["ms_per_step"], d["e2e"]["value"]/1e6, d["roofline"]["avg_us"]))
+except Exception as e:
+    print("bench $cfg failed", e)
+PY
+  tail -2 gpurun_out/${T}_bench_ab.err | cut -c1-300
+done
