@@ -123,7 +123,10 @@ class CTRTrainer(object):
         else:
             y_pred, other_loss = self.model(x_dict)
             loss = self.criterion(y_pred, y) + other_loss
-        return loss + self.reg_loss_fn(self.model)
+        reg = self.reg_loss_fn(self.model)
+        if isinstance(reg, float) and reg == 0.0:  # no regularisation configured: `loss + 0.0` would still be a launch per step
+            return loss
+        return loss + reg
 
     def _train_step(self, x_dict, y):
         """zero_grad -> forward -> loss -> backward -> optimizer step; returns the loss tensor (reference ``:87-99``)."""
