@@ -403,6 +403,35 @@ def time_tower_gemms(device):
     return flops, sorted(ts)[len(ts) // 2]
 
 
+def kernel_times(step_fn, pool_dev, rank, steps=20, top=14):
+    """Per-kernel device time of `steps` more replays of the timed step (every rank runs them: the step is collective), as seen
+    by rank 0: calls per step, average duration, share of the summed kernel time.  Runs AFTER the timed regions."""
+    import torch
+    from collections import defaultdict
+    from torch.profiler import ProfilerActivity, profile
+    torch.cuda.synchronize()
+    if rank != 0:
+        for i in range(steps):
+            step_fn(*pool_dev[i % len(pool_dev)])
+        torch.cuda.synchronize()
+        return None
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for i in range(steps):
+            step_fn(*pool_dev[i % len(pool_dev)])
+        torch.cuda.synchronize()
+    agg = defaultdict(lambda: [0, 0.0])
+    for ev in prof.events():
+        if ev.device_type == torch.autograd.DeviceType.CUDA:
+            agg[ev.name][0] += 1
+            agg[ev.name][1] += ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
+    total = sum(v[1] for v in agg.values())
+    if total <= 0:
+        return {"error": "no device events recorded"}
+    rows = sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]
+    return {"steps": steps, "sum_us_per_step": round(total / steps, 1), "source": "torch.profiler (CUPTI), warm, rank 0, after the timed region",
+            "top": [{"kernel": name[:72], "per_step": round(n / steps, 2), "avg_us": round(t / n, 2), "share": round(t / total, 3)} for name, (n, t) in rows]}
+
+
 def sharded_parity_check(trainer, model, pool_dev, device, world, rank):
     """Checks the N-rank sharded engine ON THE BOX THAT PRODUCES THE NUMBER (run after the timed regions): one forward + backward
     of the field-sharded model (ids scattered to the owners, owner-side gather storing rows into the samples' GPUs, FM + LR on
@@ -651,6 +680,14 @@ def run_b200_arm(args):
                      "frac": gflops / gus / 1e6 / tpeak, "us_per_step": gus, "fp32_flops_per_step": gflops,
                      "note": "fp32-accurate 3xTF32: 3 tensor-core MMAs per fp32 product and TF32 peak is half the bf16 peak, so 1/6 of the bf16 peak is the ceiling of this scheme; ncu tensor-pipe 10-29 % (profiles/r01b_ncu_full_summary.json)"}
 
+    # ---- warm per-kernel durations of the step that was just timed (CUPTI through torch.profiler; rank 0's view) ----------------
+    ktimes = None
+    if not args.no_kernel_times:
+        try:
+            ktimes = kernel_times(step_fn, pool_dev, rank)
+        except Exception as e:  # a profiler that cannot attach must not cost the bench line
+            ktimes = {"error": str(e)[:200]}
+
     parity = {"ok": None, "note": "single GPU: this configuration is checked against the oracle by tests/test_gpu_fullshape.py (logits, gradients, the graph-replayed row-wise Adam step)"}
     if world > 1 and trainer._dist is not None and not args.no_check:
         parity = sharded_parity_check(trainer, model, pool_dev, device, world, rank)
@@ -689,6 +726,7 @@ def run_b200_arm(args):
         "roofline_gemm": gemm_roof if rank == 0 else None,
         "cpu_baseline": cpu,
         "parity": parity,
+        "kernel_times": ktimes,
         "final_loss": final_loss,
     }
     print(json.dumps(line), flush=True)
@@ -713,6 +751,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-times", action="store_true", help="skip the CUPTI per-kernel breakdown appended to the line")
     ap.add_argument("--no-check", action="store_true", help="skip the sharded-vs-single-GPU parity check of multi-GPU runs")
     ap.add_argument("--ids", default="uniform", choices=["uniform", "zipf"], help="id distribution of the synthetic batches (uniform = the headline workload)")
     ap.add_argument("--workload", default="deepfm", choices=["deepfm", "dcnv2", "din", "dssm"], help="deepfm = the headline metric of BASELINE.json (default); the others are its configs 3-5 (bench_workloads.py)")

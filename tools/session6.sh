@@ -4,13 +4,14 @@
 set -u
 mkdir -p gpurun_out
 T=${1:-s6}
-timeout -k 10 1500 python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider > gpurun_out/${T}_tests.log 2>&1
+PYTHONUNBUFFERED=1 timeout -k 10 900 python -m pytest tests -m gpu -q --timeout 300 --timeout-method=thread --durations=8 -p no:cacheprovider > gpurun_out/${T}_tests.log 2>&1
 grep -E "^FAILED|^ERROR|passed|failed" gpurun_out/${T}_tests.log | tail -25
+timeout -k 10 200 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
 timeout -k 10 400 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; tail -c 1500 gpurun_out/${T}_bench.json
 timeout -k 10 400 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/${T}_bench_ref.json 2> gpurun_out/${T}_bench_ref.err; tail -c 800 gpurun_out/${T}_bench_ref.json
 timeout -k 10 200 python tools/kernel_times.py > gpurun_out/${T}_ktimes.txt 2>&1; head -32 gpurun_out/${T}_ktimes.txt | cut -c1-160
 timeout -k 10 300 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${T}_launches.csv python tools/profile_step.py > gpurun_out/${T}_launches.log 2>&1
-timeout -k 10 600 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"fields_fwd_v5|fields_bwd|bn_fused|gemm_tf32x3|rowwise_update" -o gpurun_out/${T}_prof python tools/profile_step.py > gpurun_out/${T}_ncu.log 2>&1; tail -2 gpurun_out/${T}_ncu.log
+timeout -k 10 600 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"fields_fwd_v4|fields_bwd|bn_fused|gemm_tf32x3|rowwise_update" -o gpurun_out/${T}_prof python tools/profile_step.py > gpurun_out/${T}_ncu.log 2>&1; tail -2 gpurun_out/${T}_ncu.log
 python tools/ncu_summary.py gpurun_out/${T}_prof.ncu-rep > gpurun_out/${T}_ncu_full_summary.json 2> gpurun_out/${T}_ncu_summary.err; head -c 600 gpurun_out/${T}_ncu_full_summary.json
 timeout -k 10 100 tools/gemm_trace > gpurun_out/${T}_gemm_trace.txt 2>&1
 timeout -k 10 100 tools/bnfuse_trace > gpurun_out/${T}_bnfuse_trace.txt 2>&1; tail -12 gpurun_out/${T}_bnfuse_trace.txt
