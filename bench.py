@@ -539,9 +539,14 @@ def sharded_parity_check(trainer, model, pool_dev, device, world, rank):
                     res[5] += u.numel()
         dist.broadcast(res, src=0)
         r_ = [float(v) for v in res.tolist()]
+        # Gradient tolerance.  The check runs on the TRAINED weights (after the timed steps): probabilities are saturated, and with
+        # d loss / d logit = (p - y) / N a logit error e moves that factor by up to e RELATIVE (d p = p (1 - p) e against
+        # |p - y| ~ 1 - p).  So the logit errors this very check measures (inside their own 1e-4 |ref| + 1e-6 bound) put a floor of
+        # ~max_logit_err under every gradient's relative error; 2 x that (two paths: FM / LR head and tower) + the 2e-4 of the tests.
+        grad_tol = 2e-4 + 2.0 * r_[0]
         out.update({"max_logit_err": r_[0], "logit_tolerance": "1e-4*|ref| + 1e-6", "max_logit_excess_over_tolerance": r_[1], "loss_err": r_[2], "dense_grad_rel_err": r_[3], "table_grad_rel_err": r_[4],
-                    "table_rows_compared": int(r_[5]), "grad_tolerance": 2e-4})
-        out["ok"] = bool(r_[1] <= 0.0 and r_[2] <= 1e-5 and r_[3] <= 2e-4 and r_[4] <= 2e-4 and r_[5] > 0)
+                    "table_rows_compared": int(r_[5]), "grad_tolerance": grad_tol, "grad_tolerance_rule": "2e-4 + 2 * max_logit_err (of each gradient's max-abs scale)"})
+        out["ok"] = bool(r_[1] <= 0.0 and r_[2] <= 1e-5 and r_[3] <= grad_tol and r_[4] <= grad_tol and r_[5] > 0)
     finally:
         for m, pv in drops:
             m.p = pv

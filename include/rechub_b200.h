@@ -393,6 +393,11 @@ int64_t rh_dense_stage_floats(int n_tensors, const int64_t* numel);
  * of every rank's flags (8 int32, peer-mapped, zero-initialised; peer_flags[s] = rank s's array), wait until every rank has published it
  * into my_flags, then store it to *epoch_dev.  Everything this GPU wrote before the call is visible to a peer that passes the barrier. */
 int rh_peer_barrier(int32_t* const* peer_flags, const int32_t* my_flags, int rank, int world, int32_t* epoch_dev, void* stream);
+/* Wait until every rank's flag (my_flags[0..world), written by the peers' rh_dense_pack_signal of this step) has reached
+ * *epoch_dev + 1.  Because a rank publishes behind its backward kernels and a system fence, this also orders the peers' row-gradient
+ * REDs before whatever follows on `stream` — the step's third barrier without a signal round of its own. */
+int rh_peer_wait(const int32_t* my_flags, int world, const int32_t* epoch_dev, void* stream);
+
 /* Copy this rank's gradients (grads[i] NULL = zeros) and up to 4 extra device scalars into ITS staging slot of this step, then
  * publish the step number to every rank's flags (peer_flags[s] = rank s's flags array). */
 int rh_dense_pack_signal(int n_tensors, const float* const* grads, const int64_t* numel,

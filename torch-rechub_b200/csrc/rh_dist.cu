@@ -45,23 +45,37 @@ __device__ __forceinline__ int32_t ld_acquire_sys(const int32_t* p) {
   return v;
 }
 
+// One system-scope fence per LAUNCH, not per block: every block makes its copies visible device-wide (__threadfence) before it takes
+// its ticket; the last block — which therefore observes all of them — issues the only __threadfence_system() and publishes the flag
+// (fences are cumulative).  The first version ran ~2500 blocks with a system fence each: 25 us for a 600 KB copy.
 __global__ void __launch_bounds__(256) dense_pack_signal_kernel(const __grid_constant__ PackP p) {
   __shared__ int is_last;
+  pdl_wait();
   const int e = *p.epoch + 1;
   float* slot = p.stage + (size_t)(e & 1) * p.total;
   for (int ti = blockIdx.y; ti < p.n_tensors; ti += gridDim.y) {
     const float* g = p.g[ti];
     float* dst = slot + p.off[ti];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n[ti]; i += gridDim.x * blockDim.x) dst[i] = g != nullptr ? g[i] : 0.f;
+    const int n = p.n[ti];
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    if (g != nullptr && (reinterpret_cast<uintptr_t>(g) & 15u) == 0) {  // slot offsets are multiples of 4 floats
+      const int n4 = n >> 2;
+      for (int i = t0; i < n4; i += nt) reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(g) + i);
+      for (int i = (n4 << 2) + t0; i < n; i += nt) dst[i] = g[i];
+    } else {
+      for (int i = t0; i < n; i += nt) dst[i] = g != nullptr ? g[i] : 0.f;
+    }
   }
   if (blockIdx.x == 0 && blockIdx.y == 0 && (int)threadIdx.x < p.n_extra) slot[p.total - 4 + threadIdx.x] = *p.extra[threadIdx.x];
-  __threadfence_system();
+  __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) is_last = (atomicAdd(p.ticket, 1u) == gridDim.x * gridDim.y - 1) ? 1 : 0;
   __syncthreads();
   if (!is_last) return;
-  __threadfence_system();
-  if ((int)threadIdx.x < p.world) st_release_sys(p.peer_flags[threadIdx.x] + p.rank, e);
+  if ((int)threadIdx.x < p.world) {
+    __threadfence_system();
+    st_release_sys(p.peer_flags[threadIdx.x] + p.rank, e);
+  }
   if (threadIdx.x == 0) *p.ticket = 0u;
 }
 
@@ -86,6 +100,7 @@ struct ReduceP {
 
 __global__ void __launch_bounds__(256) dense_reduce_update_kernel(const __grid_constant__ ReduceP p) {
   __shared__ int is_last;
+  pdl_wait();
   const int e = *p.epoch + 1;
   if ((int)threadIdx.x < p.world) {
     while (ld_acquire_sys(p.flags + threadIdx.x) < e) __nanosleep(64);
@@ -99,7 +114,40 @@ __global__ void __launch_bounds__(256) dense_reduce_update_kernel(const __grid_c
     float* s1 = p.s1[ti];
     float* s2 = p.s2[ti];
     const size_t base = slot + p.off[ti];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n[ti]; i += gridDim.x * blockDim.x) {
+    const int n = p.n[ti];
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    int done = 0;
+    // four elements per thread with all peers' 16-byte loads in flight together: an NVLink read is a ~2 us round trip, and one
+    // element per thread meant four waves of blocks each paying it (15 us for 150 k elements at world 2)
+    if (p.kind == 1 && ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(s1) | reinterpret_cast<uintptr_t>(s2)) & 15u) == 0) {
+      const int n4 = n >> 2;
+      for (int i = t0; i < n4; i += nt) {
+        float4 gs[kMaxRanks];
+#pragma unroll
+        for (int s = 0; s < kMaxRanks; ++s)
+          if (s < p.world) gs[s] = __ldcg(reinterpret_cast<const float4*>(p.peer_stage[s] + base) + i);
+        float4 wv = reinterpret_cast<float4*>(w)[i], m4 = reinterpret_cast<float4*>(s1)[i], v4 = reinterpret_cast<float4*>(s2)[i];
+        float g[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int s = 0; s < kMaxRanks; ++s)
+          if (s < p.world) {  // rank order: identical sums everywhere
+            g[0] += gs[s].x; g[1] += gs[s].y; g[2] += gs[s].z; g[3] += gs[s].w;
+          }
+        float wa[4] = {wv.x, wv.y, wv.z, wv.w}, ma[4] = {m4.x, m4.y, m4.z, m4.w}, va[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float gr = fmaf(p.wd, wa[j], g[j]);
+          ma[j] = p.beta1 * ma[j] + (1.f - p.beta1) * gr;
+          va[j] = p.beta2 * va[j] + (1.f - p.beta2) * gr * gr;
+          wa[j] -= (lr / bc1) * (ma[j] / (sqrtf(va[j]) / bc2s + p.eps));
+        }
+        reinterpret_cast<float4*>(s1)[i] = make_float4(ma[0], ma[1], ma[2], ma[3]);
+        reinterpret_cast<float4*>(s2)[i] = make_float4(va[0], va[1], va[2], va[3]);
+        reinterpret_cast<float4*>(w)[i] = make_float4(wa[0], wa[1], wa[2], wa[3]);
+      }
+      done = n4 << 2;
+    }
+    for (int i = done + t0; i < n; i += nt) {
       float g = 0.f;
       for (int s = 0; s < p.world; ++s) g += __ldcg(p.peer_stage[s] + base + i);  // rank order: identical sums everywhere
       float wv = w[i];
@@ -142,6 +190,7 @@ struct PeerFlagPtrs {
   int32_t* p[kMaxRanks];
 };
 __global__ void __launch_bounds__(32) peer_barrier_kernel_v(const __grid_constant__ PeerFlagPtrs peers, const int32_t* my_flags, int rank, int world, int32_t* epoch) {
+  pdl_wait();
   const int e = *epoch + 1;
   __syncwarp();
   if ((int)threadIdx.x < world) {
@@ -153,9 +202,27 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel_v(const __grid_constan
   if (threadIdx.x == 0) *epoch = e;
 }
 
+// Wait only: the flags were (or will be) published by the peers' rh_dense_pack_signal launches of this step — which sit behind
+// their backward kernels in stream order and behind a system fence — so "every rank has published step e" also means "every rank's
+// row-gradient REDs have landed".  Replaces the third barrier of the step (no signal round of its own).
+__global__ void __launch_bounds__(32) peer_wait_kernel(const int32_t* my_flags, int world, const int32_t* epoch) {
+  pdl_wait();
+  const int e = *epoch + 1;
+  if ((int)threadIdx.x < world) {
+    while (ld_acquire_sys(my_flags + threadIdx.x) < e) __nanosleep(40);
+  }
+}
+
 }  // namespace rh
 
 using namespace rh;
+
+extern "C" int rh_peer_wait(const int32_t* my_flags, int world, const int32_t* epoch_dev, void* stream) {
+  RH_REQUIRE(my_flags && epoch_dev && world >= 1 && world <= kMaxRanks, RH_ERR_INVALID_ARG, "rh_peer_wait: bad arguments");
+  launch_k(peer_wait_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, my_flags, world, epoch_dev);
+  RH_LAUNCH_CHECK();
+  return RH_OK;
+}
 
 extern "C" int rh_peer_barrier(int32_t* const* peer_flags, const int32_t* my_flags, int rank, int world, int32_t* epoch_dev, void* stream) {
   RH_REQUIRE(peer_flags && my_flags && epoch_dev && world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world, RH_ERR_INVALID_ARG, "rh_peer_barrier: bad arguments");
@@ -165,7 +232,7 @@ extern "C" int rh_peer_barrier(int32_t* const* peer_flags, const int32_t* my_fla
     RH_REQUIRE(peer_flags[s] != nullptr, RH_ERR_INVALID_ARG, "rh_peer_barrier: flags of rank %d NULL", s);
     pf.p[s] = peer_flags[s];
   }
-  peer_barrier_kernel_v<<<1, 32, 0, (cudaStream_t)stream>>>(pf, my_flags, rank, world, epoch_dev);
+  launch_k(peer_barrier_kernel_v, dim3(1), dim3(32), 0, (cudaStream_t)stream, pf, my_flags, rank, world, epoch_dev);
   RH_LAUNCH_CHECK();
   return RH_OK;
 }
@@ -213,10 +280,12 @@ extern "C" int rh_dense_pack_signal(int n_tensors, const float* const* grads, co
   }
   p.n_tensors = n_tensors; p.n_extra = n_extra; p.stage = stage; p.rank = rank; p.world = world; p.epoch = epoch_dev;
   p.ticket = reinterpret_cast<unsigned*>(ticket_dev);
-  int gx = (int)((biggest + 255) / 256);
-  if (gx > 256) gx = 256;
   const int gy = n_tensors < 32 ? n_tensors : 32;
-  dense_pack_signal_kernel<<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>(p);
+  int gx = (int)((biggest / 4 + 255) / 256);  // one float4 per thread for the largest tensor ...
+  const int cap = (2 * num_sms() + gy - 1) / gy;  // ... but no more blocks than ~2 per SM in total (each ends with a fence + a ticket)
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  launch_k(dense_pack_signal_kernel, dim3(gx, gy), dim3(256), 0, (cudaStream_t)stream, p);
   RH_LAUNCH_CHECK();
   return RH_OK;
 }
@@ -251,10 +320,11 @@ extern "C" int rh_dense_reduce_update(int n_tensors, float* const* params, float
   p.n_tensors = n_tensors; p.n_extra = n_extra; p.flags = flags; p.rank = rank; p.world = world; p.epoch = epoch_dev;
   p.ticket = reinterpret_cast<unsigned*>(ticket_dev); p.extra_out = extra_out; p.kind = kind; p.beta1 = beta1; p.beta2 = beta2; p.eps = eps;
   p.wd = weight_decay; p.lr_dev = lr_dev; p.bc_dev = bias_corr_dev;
-  int gx = (int)((biggest + 255) / 256);
-  if (gx > 512) gx = 512;
   const int gy = n_tensors < 32 ? n_tensors : 32;
-  dense_reduce_update_kernel<<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>(p);
+  int gx = (int)((biggest / 4 + 255) / 256);  // four elements per thread (Adam); every block first polls the peers' flags
+  if (gx > 512) gx = 512;
+  if (gx < 1) gx = 1;
+  launch_k(dense_reduce_update_kernel, dim3(gx, gy), dim3(256), 0, (cudaStream_t)stream, p);
   RH_LAUNCH_CHECK();
   return RH_OK;
 }

@@ -42,6 +42,9 @@ p2p_allreduce = _flag("RECHUB_B200_P2P_ALLREDUCE", True)
 # ... and order the exchange's hand-overs with the engine's own flag barrier (rh_peer_barrier, one warp) instead of the symmetric-memory
 # library's barrier kernel.
 p2p_own_barrier = _flag("RECHUB_B200_P2P_OWN_BARRIER", True)
+# With the peer-memory reduction the post-backward barrier is a WAIT on the gradient-publication flags (rh_peer_wait): a rank publishes
+# behind its backward kernels and a system fence, so no separate signal round is needed.
+p2p_fold_barrier = _flag("RECHUB_B200_P2P_FOLD_BARRIER", True)
 
 # Check the device-side out-of-range-id flag after every forward (one D2H sync per step).  When off the
 # flag is checked at the trainer's existing sync points (``loss.item()``) and by ``check_errors()``.

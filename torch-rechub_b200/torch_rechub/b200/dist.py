@@ -520,11 +520,15 @@ class DistEngine(object):
         extra = (ctypes.c_void_p * 1)(lw.data_ptr())
         _lib.check(L.rh_dense_pack_signal(n, grads, pr["numel"], extra, 1, pr["stage"].data_ptr(), pr["flag_ptrs"], self.rank, self.world, pr["epoch"].data_ptr(), pr["ticket"].data_ptr(), st), "rh_dense_pack_signal")
         del keep
-        for f in self.fronts:  # every rank's row-gradient REDs must have landed before the owners consume their buffers
-            if f.deferred is not None:
-                f.deferred.barrier()
-                f.deferred = None
-                break
+        from . import config
+        if any(f.deferred is not None for f in self.fronts):
+            # Every rank's row-gradient REDs must have landed before the owners consume their buffers.  A rank publishes its
+            # gradients (above) behind its backward kernels and a system fence, so waiting for everybody's publication flag IS
+            # that barrier — without a signal round of its own.
+            if config.p2p_fold_barrier:
+                _lib.check(L.rh_peer_wait(pr["flags"].data_ptr(), self.world, pr["epoch"].data_ptr(), st), "rh_peer_wait")
+            else:
+                next(f for f in self.fronts if f.deferred is not None).deferred.barrier()
         for f in self.fronts:
             f.deferred = None
         rw, eng = opt.rowwise, opt.dense_engine
@@ -587,8 +591,10 @@ class DistEngine(object):
         opt = trainer.optimizer
         split = hasattr(opt, "rowwise") and hasattr(opt, "dense_engine")
         from . import config
+        peer = split and self.peer_reduce is not None
         for f in self.fronts:
-            f.lazy_clean, f.defer_barrier, f.deferred = not split, bool(config.p2p_defer_barrier), None
+            # peer-memory reduction: the post-backward barrier is replaced by a wait on the gradient-publication flags (below)
+            f.lazy_clean, f.defer_barrier, f.deferred = not split, bool(config.p2p_defer_barrier) or (peer and config.p2p_fold_barrier), None
         loss = trainer._loss(x_dict, y)
         loss.backward(self._inv_world)  # d(loss / world): the all-reduce SUM then yields the gradient of the global-batch mean
         for f in self.fronts:
