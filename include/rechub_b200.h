@@ -72,6 +72,10 @@ unsigned long long rh_launch_count(void);
  * on != 0 they are launched so that their scheduling and memory-free prologue overlap the drain of the preceding kernel in the stream
  * (each waits with griddepcontrol.wait before its first global access).  on < 0 only queries.  Returns the previous setting. */
 int rh_set_pdl(int on);
+/* Preferred shared-memory carveout (0..100 %, -1 = the driver's choice) applied to every kernel of the library at its next first launch;
+ * returns the previous setting.  An experiment switch (does a uniform carveout avoid L1 / shared-memory reconfigurations between the
+ * 198 KB GEMM CTAs and their neighbours?). */
+int rh_set_smem_carveout(int percent);
 /* L2 fetch granularity of the current device (cudaLimitMaxL2FetchGranularity): bytes L2 pulls from DRAM per sector miss.
  * set_bytes > 0 sets it first (32 / 64 / 128); returns the value in force, < 0 on a CUDA error.  Random 64-byte embedding rows
  * (basic/layers.py:83,85 lookups) cost twice their DRAM bytes at 128 — the engine's host side lowers it once per device. */

@@ -1,12 +1,29 @@
 // rh_api.cu — ABI bookkeeping: version + thread-local error message.
 #include <stdarg.h>
 
+#include <mutex>
+#include <unordered_set>
+
 #include "rh_common.cuh"
 
 namespace rh {
 static thread_local char g_err[512] = "";
 unsigned long long g_launches = 0;
 int g_pdl = 0;
+int g_carveout = -1;
+
+// rh_set_smem_carveout: apply the preferred shared-memory carveout to every kernel of the library, once per kernel, at its first
+// launch after the setting (an experiment switch: does a uniform carveout remove an L1 / shared-memory reconfiguration between the
+// 198 KB GEMM CTAs and their small-shared-memory neighbours?)
+void note_kernel(const void* fn) {
+  static std::mutex mu;
+  static std::unordered_set<const void*> seen;
+  std::lock_guard<std::mutex> lock(mu);
+  if (seen.insert(fn).second) {
+    cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, g_carveout);
+    cudaGetLastError();
+  }
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -19,6 +36,11 @@ void set_error(const char* fmt, ...) {
 extern "C" int rh_abi_version(void) { return RH_ABI_VERSION; }
 extern "C" const char* rh_last_error(void) { return rh::g_err; }
 extern "C" unsigned long long rh_launch_count(void) { return rh::g_launches; }
+extern "C" int rh_set_smem_carveout(int percent) {
+  const int old = rh::g_carveout;
+  if (percent >= -1 && percent <= 100) rh::g_carveout = percent;
+  return old;
+}
 extern "C" int rh_set_pdl(int on) {
   const int old = rh::g_pdl;
   if (on >= 0) rh::g_pdl = on != 0;
@@ -60,22 +82,49 @@ struct CopySegs {
 };
 __global__ void __launch_bounds__(256) copy_segs_kernel(CopySegs s) {
   pdl_wait();
+  // ONE index space over all segments (16-byte units): a thread's loads of different segments are independent of its stores, so
+  // the whole copy is a single load -> store round trip.  (Segment after segment, the stores of one — which may alias the next
+  // one's source as far as the compiler knows — serialised three round trips: 4.9 us for 1 MB.)
   const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
-  for (int k = 0; k < s.n; ++k) {
-    const int64_t b = s.bytes[k];
-    const bool v16 = ((reinterpret_cast<uintptr_t>(s.dst[k]) | reinterpret_cast<uintptr_t>(s.src[k])) & 15) == 0;
-    if (v16) {
-      const int4* src = static_cast<const int4*>(s.src[k]);
-      int4* dst = static_cast<int4*>(s.dst[k]);
-      const int64_t n16 = b >> 4;
-      for (int64_t i = t0; i < n16; i += nt) dst[i] = __ldg(src + i);
-      const char* sc = static_cast<const char*>(s.src[k]);
-      char* dc = static_cast<char*>(s.dst[k]);
-      for (int64_t i = (n16 << 4) + t0; i < b; i += nt) dc[i] = sc[i];
+  int64_t first[5];
+  bool v16 = true;
+  first[0] = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t b = k < s.n ? s.bytes[k] : 0;
+    first[k + 1] = first[k] + ((b + 15) >> 4);
+    if (k < s.n) v16 &= ((reinterpret_cast<uintptr_t>(s.dst[k]) | reinterpret_cast<uintptr_t>(s.src[k]) | (uintptr_t)b) & 15) == 0;
+  }
+  if (v16) {
+    constexpr int U = 4;
+    for (int64_t i0 = t0; i0 < first[4]; i0 += nt * U) {
+      int4 v[U];
+      int4* d[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + u * nt;
+        d[u] = nullptr;
+        if (i < first[4]) {
+          const int k = (i >= first[1]) + (i >= first[2]) + (i >= first[3]);
+          v[u] = __ldg(static_cast<const int4*>(s.src[k]) + (i - first[k]));
+          d[u] = static_cast<int4*>(s.dst[k]) + (i - first[k]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (d[u] != nullptr) *d[u] = v[u];
+    }
+    return;
+  }
+  for (int k = 0; k < s.n; ++k) {  // a ragged last batch: 4-byte words where possible, bytes otherwise
+    if (((reinterpret_cast<uintptr_t>(s.dst[k]) | reinterpret_cast<uintptr_t>(s.src[k]) | (uintptr_t)s.bytes[k]) & 3) == 0) {
+      const int32_t* sw = static_cast<const int32_t*>(s.src[k]);
+      int32_t* dw = static_cast<int32_t*>(s.dst[k]);
+      for (int64_t i = t0; i < (s.bytes[k] >> 2); i += nt) dw[i] = __ldg(sw + i);
     } else {
       const char* sc = static_cast<const char*>(s.src[k]);
       char* dc = static_cast<char*>(s.dst[k]);
-      for (int64_t i = t0; i < b; i += nt) dc[i] = sc[i];
+      for (int64_t i = t0; i < s.bytes[k]; i += nt) dc[i] = sc[i];
     }
   }
 }

@@ -22,6 +22,8 @@ void set_error(const char* fmt, ...);   // rh_api.cu (thread-local message)
 
 extern unsigned long long g_launches;  // rh_api.cu: kernels launched by this library (rh_launch_count)
 extern int g_pdl;                      // rh_api.cu: launch the hot-path kernels with programmatic dependent launch (rh_set_pdl)
+extern int g_carveout;                 // rh_api.cu: preferred shared-memory carveout for every kernel, -1 = the driver's choice (rh_set_smem_carveout)
+void note_kernel(const void* fn);      // rh_api.cu
 
 // Launch with the programmatic-stream-serialization attribute when rh_set_pdl(1): the kernel may be scheduled while its predecessor
 // in the stream drains; it calls pdl_wait() (griddepcontrol.wait) before its first global access, which returns once the predecessor
@@ -39,6 +41,7 @@ static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = g_pdl ? 1 : 0;
+  if (g_carveout >= 0) note_kernel(reinterpret_cast<const void*>(kernel));
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -37,6 +37,7 @@ PROTOTYPES = {
     "rh_launch_count": [],
     "rh_l2_fetch_granularity": [c_i],
     "rh_set_pdl": [c_i],
+    "rh_set_smem_carveout": [c_i],
     "rh_fields_fwd": [c_p, c_i, c_i, c_p, c_i, c_i, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "rh_fields_fwd_p2p": [c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_i64, c_p, c_p],
     "rh_ids_scatter": [c_p, c_i, c_p, c_i, c_p, c_i, c_i, c_i64, c_i64, c_p],
@@ -128,6 +129,7 @@ def lib():
             from . import config
             handle.rh_set_pdl(int(bool(config.pdl)))
             handle.rh_gemm_tile_n(int(config.gemm_tile_n))
+            handle.rh_set_smem_carveout(int(config.smem_carveout))
             _lib = handle
     return _lib
 

@@ -99,3 +99,6 @@ static_inputs = False
 # Output-tile width of the tower GEMM (rh_gemm_tile_n): 0 = the library chooses per problem (128 x 64 tiles when 128 x 128 would leave
 # more than half of the SMs idle), 64 / 128 force one (A/B runs).
 gemm_tile_n = int(os.environ.get("RECHUB_B200_GEMM_TILE_N", "0"))
+
+# Preferred shared-memory carveout for every kernel of the library (rh_set_smem_carveout): -1 = the driver's choice.  Experiment switch.
+smem_carveout = int(os.environ.get("RECHUB_B200_SMEM_CARVEOUT", "-1"))

@@ -134,7 +134,14 @@ class CTRTrainer(object):
             return self._dist.train_step(self, x_dict, y)
         loss = self._loss(x_dict, y)
         self.model.zero_grad()
-        loss.backward()
+        if loss.is_cuda and loss.dim() == 0 and loss.dtype == torch.float32:
+            # a cached unit gradient: `loss.backward()` would fill a fresh ones-tensor every step (one more launch on the chain)
+            one = getattr(self, "_unit_grad", None)
+            if one is None or one.device != loss.device:
+                one = self._unit_grad = torch.ones((), dtype=torch.float32, device=loss.device)
+            loss.backward(one)
+        else:
+            loss.backward()
         self.optimizer.step()
         return loss.detach()  # callers only read the value; holding the graph alive would pin AccumulateGrad nodes
 
