@@ -402,17 +402,18 @@ int rh_peer_barrier(int32_t* const* peer_flags, const int32_t* my_flags, int ran
  * REDs before whatever follows on `stream` — the step's third barrier without a signal round of its own. */
 int rh_peer_wait(const int32_t* my_flags, int world, const int32_t* epoch_dev, void* stream);
 
-/* Copy this rank's gradients (grads[i] NULL = zeros) and up to 4 extra device scalars into ITS staging slot of this step, then
- * publish the step number to every rank's flags (peer_flags[s] = rank s's flags array). */
+/* Push this rank's gradients (grads[i] NULL = zeros) and up to 4 extra device scalars into slot [rank] of EVERY rank's staging buffer
+ * (peer_stage[s] = rank s's buffer, peer-mapped: 2 step parities x world slots of rh_dense_stage_floats() floats), then publish the
+ * step number to every rank's flags (peer_flags[s] = rank s's flags array). */
 int rh_dense_pack_signal(int n_tensors, const float* const* grads, const int64_t* numel,
-                         const float* const* extra, int n_extra, float* stage,
+                         const float* const* extra, int n_extra, float* const* peer_stage,
                          int32_t* const* peer_flags, int rank, int world,
                          const int32_t* epoch_dev, int32_t* ticket_dev, void* stream);
-/* Wait for every rank's publication of this step, sum the W staging slots element-wise in rank order (peer_stage[s] = rank s's staging
- * buffer) and apply the SGD / Adam / Adagrad update (kinds and device scalars as rh_dense_update); extra_out (n_extra) receives the
- * summed extras.  Every rank ends with bit-identical parameters. */
+/* Wait for every rank's publication of this step, sum the W slots of THIS rank's staging buffer element-wise in rank order and apply
+ * the SGD / Adam / Adagrad update (kinds and device scalars as rh_dense_update); extra_out (n_extra) receives the summed extras.
+ * Every rank ends with bit-identical parameters. */
 int rh_dense_reduce_update(int n_tensors, float* const* params, float* const* state1, float* const* state2, const int64_t* numel,
-                           int n_extra, float* extra_out, const float* const* peer_stage, const int32_t* flags,
+                           int n_extra, float* extra_out, const float* stage, const int32_t* flags,
                            int rank, int world, int32_t* epoch_dev, int32_t* ticket_dev,
                            int kind, const float* lr_dev, const float* bias_corr_dev,
                            float beta1, float beta2, float eps, float weight_decay, void* stream);

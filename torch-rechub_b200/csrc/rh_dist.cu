@@ -5,16 +5,18 @@
 // 97-99).  The sharded engine (b200/dist.py) needs, once per step, the SUM over ranks of ~0.6 MB of tower gradients (+ the loss
 // scalar).  NCCL's ring all-reduce spends 21.6 us on it at 2 GPUs — pure latency (profiles/r01c_warm_kernel_times_n2_direct.txt).
 // Here:
-//   rh_dense_pack_signal        every rank copies its gradients (and extra device scalars) into ITS peer-mapped staging buffer
-//                               (double-buffered by step parity), then the last CTA to finish stores the step number into its flag
-//                               slot on every peer (st.release.sys after __threadfence_system).
+//   rh_dense_pack_signal        every rank PUSHES its gradients (and extra device scalars) into slot [rank] of EVERY rank's
+//                               peer-mapped staging buffer (posted NVLink stores, no round trip; double-buffered by step parity),
+//                               then the last CTA to finish stores the step number into its flag slot on every peer
+//                               (st.release.sys after ONE __threadfence_system).
 //   rh_dense_reduce_update      waits until every peer's flag shows this step (ld.acquire.sys spins on LOCAL memory), then each
-//                               element is the sum over ranks IN RANK ORDER of the peers' staging buffers (ld.global over NVLink) —
-//                               identical bits on every rank — and goes straight into the SGD / Adam / Adagrad update of the
-//                               parameter (rh_dense_update's arithmetic).  The summed extras are written out for the host.
-// One-shot (every rank reads all W copies): (W - 1) x 0.6 MB inbound per GPU — 4 MB at 8 ranks, ~6 us at NVLink rates, no second
-// exchange.  Step numbers only grow, so flags never need resetting; a buffer of parity p is rewritten two steps later, after this
-// rank has seen every peer's NEXT signal, which the peer issues after its reads of step p completed (stream order).
+//                               element is the sum over the W LOCAL slots IN RANK ORDER — identical bits on every rank — and goes
+//                               straight into the SGD / Adam / Adagrad update of the parameter (rh_dense_update's arithmetic).
+//                               The summed extras are written out for the host.
+// One-shot: (W - 1) x 0.6 MB outbound per GPU — 4 MB at 8 ranks — and no second exchange.  (The first version PULLED: every rank
+// read the peers' buffers inside the update kernel — 14-16 us against 4.5 us for the single-GPU update: NVLink read round trips.)
+// Step numbers only grow, so flags never need resetting; a slot of parity p is rewritten two steps later, after its writer has
+// seen every peer's NEXT signal, which a peer issues after its reads of step p completed (stream order).
 // Everything is static-shaped and reads its step number from device memory: CUDA-graph capturable.
 #include "rh_common.cuh"
 
@@ -29,7 +31,7 @@ struct PackP {
   int32_t off[kMaxPackTensors];      // float offset inside a staging slot
   const float* extra[4];
   int32_t n_tensors, n_extra, total;  // total = floats per slot (tensors + extras), padded to 4
-  float* stage;                       // MY staging buffer: 2 slots of `total` floats
+  float* peer_stage[kMaxRanks];       // staging buffer of every rank (peer-mapped): 2 parities x world slots of `total` floats; I write slot [rank] of each
   int32_t* peer_flags[kMaxRanks];     // flags array (kMaxRanks ints) of every rank (peer-mapped); I write element [rank]
   int32_t rank, world;
   const int32_t* epoch;               // completed all-reduces so far (device)
@@ -52,21 +54,32 @@ __global__ void __launch_bounds__(256) dense_pack_signal_kernel(const __grid_con
   __shared__ int is_last;
   pdl_wait();
   const int e = *p.epoch + 1;
-  float* slot = p.stage + (size_t)(e & 1) * p.total;
+  const size_t slot = ((size_t)(e & 1) * p.world + p.rank) * p.total;  // my slot in everybody's buffer
   for (int ti = blockIdx.y; ti < p.n_tensors; ti += gridDim.y) {
     const float* g = p.g[ti];
-    float* dst = slot + p.off[ti];
+    const size_t dst = slot + p.off[ti];
     const int n = p.n[ti];
     const int t0 = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    int done = 0;
     if (g != nullptr && (reinterpret_cast<uintptr_t>(g) & 15u) == 0) {  // slot offsets are multiples of 4 floats
       const int n4 = n >> 2;
-      for (int i = t0; i < n4; i += nt) reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(g) + i);
-      for (int i = (n4 << 2) + t0; i < n; i += nt) dst[i] = g[i];
-    } else {
-      for (int i = t0; i < n; i += nt) dst[i] = g != nullptr ? g[i] : 0.f;
+      for (int i = t0; i < n4; i += nt) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(g) + i);
+#pragma unroll
+        for (int s = 0; s < kMaxRanks; ++s)
+          if (s < p.world) reinterpret_cast<float4*>(p.peer_stage[s] + dst)[i] = v;  // posted NVLink stores: no round trip
+      }
+      done = n4 << 2;
+    }
+    for (int i = done + t0; i < n; i += nt) {
+      const float v = g != nullptr ? g[i] : 0.f;
+      for (int s = 0; s < p.world; ++s) p.peer_stage[s][dst + i] = v;
     }
   }
-  if (blockIdx.x == 0 && blockIdx.y == 0 && (int)threadIdx.x < p.n_extra) slot[p.total - 4 + threadIdx.x] = *p.extra[threadIdx.x];
+  if (blockIdx.x == 0 && blockIdx.y == 0 && (int)threadIdx.x < p.n_extra) {
+    const float v = *p.extra[threadIdx.x];
+    for (int s = 0; s < p.world; ++s) p.peer_stage[s][slot + p.total - 4 + threadIdx.x] = v;
+  }
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) is_last = (atomicAdd(p.ticket, 1u) == gridDim.x * gridDim.y - 1) ? 1 : 0;
@@ -86,7 +99,7 @@ struct ReduceP {
   int32_t n[kMaxPackTensors];
   int32_t off[kMaxPackTensors];
   int32_t n_tensors, n_extra, total;
-  const float* peer_stage[kMaxRanks];  // staging buffer (2 slots) of every rank, in rank order (peer-mapped; [rank] is local)
+  const float* stage;                  // MY staging buffer: 2 parities x world slots of `total` floats, slot s written by rank s
   const int32_t* flags;                // MY flags array: flags[s] = last step rank s has published
   int32_t rank, world;
   int32_t* epoch;
@@ -106,26 +119,25 @@ __global__ void __launch_bounds__(256) dense_reduce_update_kernel(const __grid_c
     while (ld_acquire_sys(p.flags + threadIdx.x) < e) __nanosleep(64);
   }
   __syncthreads();
-  const size_t slot = (size_t)(e & 1) * p.total;
+  const size_t par = (size_t)(e & 1) * p.world * p.total;  // this step's parity: world slots of `total` floats, slot s from rank s
   const float lr = *p.lr_dev;
   const float bc1 = p.kind == 1 ? p.bc_dev[0] : 1.f, bc2s = p.kind == 1 ? p.bc_dev[1] : 1.f;
   for (int ti = blockIdx.y; ti < p.n_tensors; ti += gridDim.y) {
     float* w = p.w[ti];
     float* s1 = p.s1[ti];
     float* s2 = p.s2[ti];
-    const size_t base = slot + p.off[ti];
+    const size_t base = par + p.off[ti];
     const int n = p.n[ti];
     const int t0 = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
     int done = 0;
-    // four elements per thread with all peers' 16-byte loads in flight together: an NVLink read is a ~2 us round trip, and one
-    // element per thread meant four waves of blocks each paying it (15 us for 150 k elements at world 2)
+    // four elements per thread, all ranks' 16-byte loads in flight together; the slots are LOCAL (the peers pushed them)
     if (p.kind == 1 && ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(s1) | reinterpret_cast<uintptr_t>(s2)) & 15u) == 0) {
       const int n4 = n >> 2;
       for (int i = t0; i < n4; i += nt) {
         float4 gs[kMaxRanks];
 #pragma unroll
         for (int s = 0; s < kMaxRanks; ++s)
-          if (s < p.world) gs[s] = __ldcg(reinterpret_cast<const float4*>(p.peer_stage[s] + base) + i);
+          if (s < p.world) gs[s] = __ldcg(reinterpret_cast<const float4*>(p.stage + base + (size_t)s * p.total) + i);
         float4 wv = reinterpret_cast<float4*>(w)[i], m4 = reinterpret_cast<float4*>(s1)[i], v4 = reinterpret_cast<float4*>(s2)[i];
         float g[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -149,7 +161,7 @@ __global__ void __launch_bounds__(256) dense_reduce_update_kernel(const __grid_c
     }
     for (int i = done + t0; i < n; i += nt) {
       float g = 0.f;
-      for (int s = 0; s < p.world; ++s) g += __ldcg(p.peer_stage[s] + base + i);  // rank order: identical sums everywhere
+      for (int s = 0; s < p.world; ++s) g += __ldcg(p.stage + base + (size_t)s * p.total + i);  // rank order: identical sums everywhere
       float wv = w[i];
       float gr = fmaf(p.wd, wv, g);
       if (p.kind == 0) {
@@ -170,7 +182,7 @@ __global__ void __launch_bounds__(256) dense_reduce_update_kernel(const __grid_c
   }
   if (blockIdx.x == 0 && blockIdx.y == 0 && (int)threadIdx.x < p.n_extra) {
     float t = 0.f;
-    for (int s = 0; s < p.world; ++s) t += __ldcg(p.peer_stage[s] + slot + p.total - 4 + threadIdx.x);
+    for (int s = 0; s < p.world; ++s) t += __ldcg(p.stage + par + (size_t)s * p.total + p.total - 4 + threadIdx.x);
     p.extra_out[threadIdx.x] = t;
   }
   __syncthreads();
@@ -257,9 +269,10 @@ static int layout(int n_tensors, const int64_t* numel, int32_t* n, int32_t* off,
   return RH_OK;
 }
 
-extern "C" int rh_dense_pack_signal(int n_tensors, const float* const* grads, const int64_t* numel, const float* const* extra, int n_extra, float* stage,
-                                    int32_t* const* peer_flags, int rank, int world, const int32_t* epoch_dev, int32_t* ticket_dev, void* stream) {
-  RH_REQUIRE(grads && numel && stage && peer_flags && epoch_dev && ticket_dev, RH_ERR_INVALID_ARG, "rh_dense_pack_signal: NULL pointer");
+extern "C" int rh_dense_pack_signal(int n_tensors, const float* const* grads, const int64_t* numel, const float* const* extra, int n_extra,
+                                    float* const* peer_stage, int32_t* const* peer_flags, int rank, int world, const int32_t* epoch_dev, int32_t* ticket_dev,
+                                    void* stream) {
+  RH_REQUIRE(grads && numel && peer_stage && peer_flags && epoch_dev && ticket_dev, RH_ERR_INVALID_ARG, "rh_dense_pack_signal: NULL pointer");
   RH_REQUIRE(world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world && n_extra >= 0 && n_extra <= 4, RH_ERR_INVALID_ARG, "rh_dense_pack_signal: bad rank/world/extras");
   static thread_local PackP p;
   memset(&p, 0, sizeof(p));
@@ -275,10 +288,11 @@ extern "C" int rh_dense_pack_signal(int n_tensors, const float* const* grads, co
     p.extra[i] = extra[i];
   }
   for (int s = 0; s < world; ++s) {
-    RH_REQUIRE(peer_flags[s] != nullptr, RH_ERR_INVALID_ARG, "rh_dense_pack_signal: flags of rank %d NULL", s);
+    RH_REQUIRE(peer_flags[s] != nullptr && peer_stage[s] != nullptr, RH_ERR_INVALID_ARG, "rh_dense_pack_signal: flags / staging buffer of rank %d NULL", s);
     p.peer_flags[s] = peer_flags[s];
+    p.peer_stage[s] = peer_stage[s];
   }
-  p.n_tensors = n_tensors; p.n_extra = n_extra; p.stage = stage; p.rank = rank; p.world = world; p.epoch = epoch_dev;
+  p.n_tensors = n_tensors; p.n_extra = n_extra; p.rank = rank; p.world = world; p.epoch = epoch_dev;
   p.ticket = reinterpret_cast<unsigned*>(ticket_dev);
   const int gy = n_tensors < 32 ? n_tensors : 32;
   int gx = (int)((biggest / 4 + 255) / 256);  // one float4 per thread for the largest tensor ...
@@ -291,10 +305,10 @@ extern "C" int rh_dense_pack_signal(int n_tensors, const float* const* grads, co
 }
 
 extern "C" int rh_dense_reduce_update(int n_tensors, float* const* params, float* const* state1, float* const* state2, const int64_t* numel, int n_extra,
-                                      float* extra_out, const float* const* peer_stage, const int32_t* flags, int rank, int world, int32_t* epoch_dev,
+                                      float* extra_out, const float* stage, const int32_t* flags, int rank, int world, int32_t* epoch_dev,
                                       int32_t* ticket_dev, int kind, const float* lr_dev, const float* bias_corr_dev, float beta1, float beta2, float eps,
                                       float weight_decay, void* stream) {
-  RH_REQUIRE(params && numel && peer_stage && flags && epoch_dev && ticket_dev && lr_dev, RH_ERR_INVALID_ARG, "rh_dense_reduce_update: NULL pointer");
+  RH_REQUIRE(params && numel && stage && flags && epoch_dev && ticket_dev && lr_dev, RH_ERR_INVALID_ARG, "rh_dense_reduce_update: NULL pointer");
   RH_REQUIRE(world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world && n_extra >= 0 && n_extra <= 4 && (n_extra == 0 || extra_out), RH_ERR_INVALID_ARG,
              "rh_dense_reduce_update: bad rank/world/extras");
   RH_REQUIRE(kind >= 0 && kind <= 2 && (kind != 1 || bias_corr_dev != nullptr) && (kind == 0 || state1 != nullptr) && (kind != 1 || state2 != nullptr), RH_ERR_INVALID_ARG,
@@ -313,10 +327,7 @@ extern "C" int rh_dense_reduce_update(int n_tensors, float* const* params, float
     RH_REQUIRE(kind != 1 || p.s2[i], RH_ERR_INVALID_ARG, "rh_dense_reduce_update: state2[%d] NULL", i);
     if (numel[i] > biggest) biggest = numel[i];
   }
-  for (int s = 0; s < world; ++s) {
-    RH_REQUIRE(peer_stage[s] != nullptr, RH_ERR_INVALID_ARG, "rh_dense_reduce_update: staging buffer of rank %d NULL", s);
-    p.peer_stage[s] = peer_stage[s];
-  }
+  p.stage = stage;
   p.n_tensors = n_tensors; p.n_extra = n_extra; p.flags = flags; p.rank = rank; p.world = world; p.epoch = epoch_dev;
   p.ticket = reinterpret_cast<unsigned*>(ticket_dev); p.extra_out = extra_out; p.kind = kind; p.beta1 = beta1; p.beta2 = beta2; p.eps = eps;
   p.wd = weight_decay; p.lr_dev = lr_dev; p.bc_dev = bias_corr_dev;

@@ -63,7 +63,7 @@ struct FwdParams {
 // stamp after `dep` is available (the unused asm input keeps the clock read behind the load it depends on)
 #define RH_FT(ev, dep)                                                                                  \
   do {                                                                                                  \
-    if (p.trace != nullptr && threadIdx.x == 0) {                                                       \
+    if (p.trace != nullptr && threadIdx.x == 0 && threadIdx.y == 0) {                                   \
       unsigned long long t__;                                                                           \
       asm volatile("mov.u64 %0, %%clock64;" : "=l"(t__) : "r"(__float_as_int((float)(dep))) : "memory"); \
       p.trace[(size_t)blockIdx.x * 16 + (ev)] = t__;                                                    \
@@ -123,7 +123,9 @@ __device__ __forceinline__ void st_tile4(float* p, const float4& v, bool vec) {
 // ------------------------------------------------------------------------------------------------
 // forward, 16-byte lanes.
 //   lane  = (sample slot, 16-byte quarter): LPR lanes per sample (LPR = pow2 >= dim/4), 32/LPR samples per warp
-//   warp  = field group g of NG: it gathers fields g, g+NG, g+2NG, ... for the block's samples
+//   warp  = (sample group sw of 8/NG, field group g of NG): it gathers fields g, g+NG, g+2NG, ... for its 32/LPR samples;
+//           blocks are always 8 warps (with few fields — an owner's 3-4 of 26 at 8 ranks — one-warp blocks ran at 20.9 us for
+//           131 k rows: 4096 blocks of 32 threads, half the warps an SM can hold)
 // A 4096-sample, 26-field batch is 4096 warps of ~4 row loads each instead of 512 warps of 26: the first
 // version was bound by the instruction latency of ONE warp per scheduler (ncu r01: 5 % warps active,
 // 37 k cycles for 3.5 k instructions per warp), not by memory.  The per-field descriptor index is
@@ -133,18 +135,20 @@ __device__ __forceinline__ void st_tile4(float* p, const float4& v, bool vec) {
 // indexed parameter reads (8 replays per constant load), against 9.5 us here; at B = 262144 it reached 1.89 TB/s against 3.16.
 // ------------------------------------------------------------------------------------------------
 template <int LPR, int NG>
-__global__ void __launch_bounds__(NG * 32) fields_fwd_v4(const __grid_constant__ FwdParams p) {
-  constexpr int SPB = 32 / LPR;  // samples per block
+__global__ void __launch_bounds__(256) fields_fwd_v4(const __grid_constant__ FwdParams p) {
+  constexpr int SPB = 32 / LPR;  // samples per warp row
+  constexpr int SW = 8 / NG;     // warp rows (sample groups) per block: always 8 warps per block
   constexpr int CH = 4;          // row loads in flight per lane per chunk
-  __shared__ float4 sm_s[NG][32];
-  __shared__ float sm_ss[NG][32];
-  __shared__ float sm_lr[NG][32];
+  __shared__ float4 sm_s[SW][NG][32];
+  __shared__ float sm_ss[SW][NG][32];
+  __shared__ float sm_lr[SW][NG][32];
 
   pdl_wait();
   const int lane = threadIdx.x & 31;
   const int g = threadIdx.x >> 5;
   const int q = lane % LPR;
-  const int b = blockIdx.x * SPB + lane / LPR;
+  const int sw = threadIdx.y;
+  const int b = (blockIdx.x * SW + sw) * SPB + lane / LPR;
   const int dim = p.dim;
   const bool live = b < p.batch;
   const bool lane_on = live && (4 * q < dim);
@@ -229,17 +233,17 @@ __global__ void __launch_bounds__(NG * 32) fields_fwd_v4(const __grid_constant__
   RH_FT(4, 0);
   if (!want_fm) return;  // block-uniform
   if (NG > 1) {
-    sm_s[g][lane] = s;
-    sm_ss[g][lane] = ss;
-    sm_lr[g][lane] = lr;
+    sm_s[sw][g][lane] = s;
+    sm_ss[sw][g][lane] = ss;
+    sm_lr[sw][g][lane] = lr;
     __syncthreads();
     RH_FT(5, 0);
     if (g != 0) return;
 #pragma unroll
     for (int k = 1; k < NG; ++k) {
-      s = f4_add(s, sm_s[k][lane]);
-      ss += sm_ss[k][lane];
-      lr += sm_lr[k][lane];
+      s = f4_add(s, sm_s[sw][k][lane]);
+      ss += sm_ss[sw][k][lane];
+      lr += sm_lr[sw][k][lane];
     }
   }
   float t = (s.x * s.x + s.y * s.y) + (s.z * s.z + s.w * s.w) - ss;
@@ -470,17 +474,17 @@ static int pack_fields(const rh_field* fields, int n_fields, FieldDev* out, bool
 template <int LPR>
 static void launch_fwd_v4(const FwdParams& p, cudaStream_t st) {
   constexpr int SPB = 32 / LPR;
-  const int grid = (p.batch + SPB - 1) / SPB;
-  // enough field groups that every warp has at most ~4 row loads; small field counts need fewer warps
+  // enough field groups that every warp has at most ~4 row loads; small field counts put more sample groups into the block instead
   const int work = p.n_fields > p.n_dense ? p.n_fields : (p.n_dense + 3) / 4;
-  if (work <= 4) {
-    launch_k(fields_fwd_v4<LPR, 1>, dim3(grid), dim3(32), 0, st, p);
-  } else if (work <= 8) {
-    launch_k(fields_fwd_v4<LPR, 2>, dim3(grid), dim3(64), 0, st, p);
-  } else if (work <= 16) {
-    launch_k(fields_fwd_v4<LPR, 4>, dim3(grid), dim3(128), 0, st, p);
-  } else {
-    launch_k(fields_fwd_v4<LPR, 8>, dim3(grid), dim3(256), 0, st, p);
+  const int ng = work <= 4 ? 1 : (work <= 8 ? 2 : (work <= 16 ? 4 : 8));
+  const int sw = 8 / ng;
+  const int grid = (p.batch + SPB * sw - 1) / (SPB * sw);
+  const dim3 block(ng * 32, sw);
+  switch (ng) {
+    case 1: launch_k(fields_fwd_v4<LPR, 1>, dim3(grid), block, 0, st, p); break;
+    case 2: launch_k(fields_fwd_v4<LPR, 2>, dim3(grid), block, 0, st, p); break;
+    case 4: launch_k(fields_fwd_v4<LPR, 4>, dim3(grid), block, 0, st, p); break;
+    default: launch_k(fields_fwd_v4<LPR, 8>, dim3(grid), block, 0, st, p); break;
   }
 }
 

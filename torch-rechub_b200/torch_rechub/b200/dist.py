@@ -492,7 +492,7 @@ class DistEngine(object):
         n = len(self.dense_params)
         numel = (ctypes.c_int64 * n)(*[p.numel() for p in self.dense_params])
         total = int(_lib.lib().rh_dense_stage_floats(n, numel))
-        stage = symm.empty(2 * total, dtype=torch.float32, device=self.device)
+        stage = symm.empty(2 * self.world * total, dtype=torch.float32, device=self.device)  # 2 step parities x world slots: rank s pushes into slot s of everybody
         flags = symm.empty(8, dtype=torch.int32, device=self.device)
         stage.zero_()
         flags.zero_()
@@ -518,7 +518,7 @@ class DistEngine(object):
         keep = [p.grad for p in self.dense_params]  # alive until the launch is queued
         lw = (loss.detach() * self._inv_world).reshape(1)
         extra = (ctypes.c_void_p * 1)(lw.data_ptr())
-        _lib.check(L.rh_dense_pack_signal(n, grads, pr["numel"], extra, 1, pr["stage"].data_ptr(), pr["flag_ptrs"], self.rank, self.world, pr["epoch"].data_ptr(), pr["ticket"].data_ptr(), st), "rh_dense_pack_signal")
+        _lib.check(L.rh_dense_pack_signal(n, grads, pr["numel"], extra, 1, pr["stage_ptrs"], pr["flag_ptrs"], self.rank, self.world, pr["epoch"].data_ptr(), pr["ticket"].data_ptr(), st), "rh_dense_pack_signal")
         del keep
         from . import config
         if any(f.deferred is not None for f in self.fronts):
@@ -541,7 +541,7 @@ class DistEngine(object):
         s1 = ptrs([eng.state[id(p)][0] for p in self.dense_params]) if rw.kind != 0 else None
         s2 = ptrs([eng.state[id(p)][1] for p in self.dense_params]) if rw.kind == 1 else None
         _lib.check(
-            L.rh_dense_reduce_update(n, ptrs(self.dense_params), s1, s2, pr["numel"], 1, pr["extra_out"].data_ptr(), pr["stage_ptrs"], pr["flags"].data_ptr(), self.rank, self.world, pr["epoch"].data_ptr(),
+            L.rh_dense_reduce_update(n, ptrs(self.dense_params), s1, s2, pr["numel"], 1, pr["extra_out"].data_ptr(), pr["stage"].data_ptr(), pr["flags"].data_ptr(), self.rank, self.world, pr["epoch"].data_ptr(),
                                      pr["ticket"].data_ptr(), rw.kind, rw._lr_dev.data_ptr(), rw._bc_dev.data_ptr(), rw.betas[0], rw.betas[1], rw.eps, rw.weight_decay, st), "rh_dense_reduce_update")
         return pr["extra_out"][0]
 
