@@ -225,3 +225,71 @@ def test_full_size_properties():
         assert torch.equal(gk[:, 0], counts) and torch.equal(gk[:, D - 1], counts)
     from torch_rechub.b200 import _lib
     _lib.check_errors()
+
+
+def test_hybrid_optimizer_state_dict_round_trip_resumes_bit_identically():
+    """the row-wise m / v / stamps, the step counter and the tower moments survive state_dict -> load_state_dict:
+    a trainer resumed from the checkpoint after 2 steps reproduces steps 3-4 of the uninterrupted run bit for bit."""
+    from torch_rechub.b200 import config
+    from torch_rechub.trainers import CTRTrainer
+    torch.manual_seed(5)
+    m_a, _, _ = small_deepfm()
+    old = config.rowwise_optimizer
+    config.rowwise_optimizer = True
+    try:
+        t_a = CTRTrainer(m_a, optimizer_params={"lr": 1e-2, "weight_decay": 1e-4}, device=DEV)
+        m_a.train()
+        batches = [batch(128, seed=10 + i) for i in range(4)]
+        dev = [({k: v.to(DEV) for k, v in x.items()}, y.to(DEV)) for x, y in batches]
+        for xd, yd in dev[:2]:
+            t_a._train_step(xd, yd)
+        torch.cuda.synchronize()
+        sd_opt = t_a.optimizer.state_dict()
+        assert sd_opt["step"] == 2 and sd_opt["rowwise"] and sd_opt["dense"]
+        m_b = copy.deepcopy(m_a)  # weights + BatchNorm running statistics after step 2
+        t_b = CTRTrainer(m_b, optimizer_params={"lr": 1e-2, "weight_decay": 1e-4}, device=DEV)
+        t_b.optimizer.load_state_dict(sd_opt)
+        m_b.train()
+        for xd, yd in dev[2:]:
+            la = t_a._train_step(xd, yd)
+            lb = t_b._train_step(xd, yd)
+            assert float(la) == float(lb)
+    finally:
+        config.rowwise_optimizer = old
+    for (n, p), q in zip(m_a.named_parameters(), m_b.parameters()):
+        assert torch.equal(p, q), n
+    with pytest.raises(ValueError):
+        t_b.optimizer.load_state_dict(torch.optim.Adam([torch.zeros(1, requires_grad=True)]).state_dict())
+
+
+def test_dense_optimizer_sparse_clean_survives_reused_id_buffers():
+    """with the default dense optimiser the rows to re-zero are remembered by VALUE — a caller that overwrites its device id
+    buffer in place between steps must not leave stale gradient rows behind; zero_grad(set_to_none=False) cannot grow the list
+    without bound."""
+    from torch_rechub.b200 import config, table
+    assert not config.rowwise_optimizer
+    torch.manual_seed(6)
+    m, _, _ = small_deepfm(n_sparse=1, vocab=64)
+    m.to(DEV).train()
+    w = m.embedding.embed_dict["C0"].weight
+    x, y = batch(32, n_sparse=1, vocab=64, seed=1, hi=8)  # rows 0..7
+    xd, yd = {k: v.to(DEV) for k, v in x.items()}, y.to(DEV)
+    torch.nn.BCELoss()(m(xd), yd).backward()
+    assert float(w.grad[:8].abs().sum()) > 0
+    xd["C0"].add_(32)  # the caller reuses its id buffer: rows 32..39 now
+    m.zero_grad(set_to_none=True)
+    torch.nn.BCELoss()(m(xd), yd).backward()
+    torch.cuda.synchronize()
+    assert float(w.grad[:8].abs().sum()) == 0.0, "stale gradient rows: the sparse clean read the overwritten id buffer"
+    assert float(w.grad[32:40].abs().sum()) > 0
+    slot = table.find_slot(w)
+    for _ in range(table._MAX_PENDING + 8):  # zero_grad(set_to_none=False) never reaches clean(): the list must stay bounded
+        m.zero_grad(set_to_none=False)
+        torch.nn.BCELoss()(m(xd), yd).backward()
+    assert len(slot.pending) <= table._MAX_PENDING
+    m.zero_grad(set_to_none=True)
+    torch.nn.BCELoss()(m(xd), yd).backward()
+    ref = w.grad.detach().clone()
+    m.zero_grad(set_to_none=True)
+    torch.nn.BCELoss()(m(xd), yd).backward()
+    assert torch.equal(w.grad, ref)  # after the full clean: exactly one step's gradient again

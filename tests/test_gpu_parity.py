@@ -169,6 +169,9 @@ def test_embedding_layer_layouts_and_pooling():
         SequenceFeature("s_mean", 25, 8, pooling="mean", padding_idx=0, initializer=INIT),
         SequenceFeature("s_sum", 25, 8, pooling="sum", initializer=INIT),
         SequenceFeature("s_shared", 40, 8, pooling="mean", shared_with="a"),
+        # the gradient skip follows the OWNING table's padding_idx, the pooling mask the feature's own
+        SequenceFeature("s_on_b", 30, 8, pooling="mean", shared_with="b"),  # feature padding_idx None (mask = -1), table "b" skips row 0
+        SequenceFeature("s_pad_on_a", 40, 8, pooling="sum", padding_idx=0, shared_with="a"),  # masks id 0, table "a" has no padding row
         DenseFeature("d0"),
         DenseFeature("dvec", embed_dim=3),
     ]
@@ -180,6 +183,8 @@ def test_embedding_layer_layouts_and_pooling():
         "s_mean": torch.randint(0, 25, (B, L), generator=g) * (torch.rand(B, L, generator=g) > 0.4),
         "s_sum": torch.randint(0, 25, (B, L), generator=g),
         "s_shared": torch.randint(0, 40, (B, L), generator=g),
+        "s_on_b": torch.randint(0, 30, (B, L), generator=g) * (torch.rand(B, L, generator=g) > 0.3),
+        "s_pad_on_a": torch.randint(0, 40, (B, L), generator=g) * (torch.rand(B, L, generator=g) > 0.3),
         "d0": torch.rand(B, generator=g).double(),
         "dvec": torch.rand(B, 3, generator=g),
     }

@@ -97,12 +97,17 @@ class SeqRef(object):
     """One pooled SequenceFeature column block of a plan (sum / mean pooling)."""
     __slots__ = ("weight", "ids", "vocab", "dim", "padding_idx", "mask_id", "mode", "tile_col")
 
-    def __init__(self, weight, ids, padding_idx, mode, tile_col):
+    def __init__(self, weight, ids, padding_idx, mode, tile_col, mask_id="same"):
         self.weight = weight
         self.ids = ids
         self.vocab, self.dim = weight.shape
+        # gradient skip = the OWNING table's nn.Embedding.padding_idx (aten::embedding_dense_backward); pooling mask = the
+        # FEATURE's padding_idx (InputMask rule, layers.py:154-157).  They differ when a SequenceFeature shares a table
+        # (shared_with) whose padding_idx is not its own.
         self.padding_idx = -1 if padding_idx is None else int(padding_idx)
-        self.mask_id = -1 if padding_idx is None else int(padding_idx)  # InputMask rule, layers.py:154-157
+        if isinstance(mask_id, str):
+            mask_id = padding_idx
+        self.mask_id = -1 if mask_id is None else int(mask_id)
         self.mode = mode
         self.tile_col = tile_col
 

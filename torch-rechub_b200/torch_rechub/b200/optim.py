@@ -251,4 +251,47 @@ class HybridOptimizer(object):
         self.dense.zero_grad(set_to_none)
 
     def state_dict(self):
-        return self.dense.state_dict()
+        """Everything a resume needs (the wrapped torch optimiser is never stepped, its own state is empty): the step counter, the
+        tables' row-wise moments + stamps and the tower's moments — keyed by POSITION in ``rowwise.params`` / ``dense_engine.params``
+        (the order ``build`` derives from ``model.modules()`` / ``model.parameters()``), as torch optimisers key by index."""
+        rw, de = self.rowwise, self.dense_engine
+        rows = {}
+        for i, p in enumerate(rw.params):
+            st = rw.state.get(id(p))
+            if st is not None:
+                rows[i] = {k: st[k].detach().clone() for k in ("m", "v", "stamp") if st.get(k) is not None}
+        dense = {}
+        for i, p in enumerate(de.params):
+            st = de.state.get(id(p))
+            if st is not None:
+                dense[i] = tuple(None if t is None else t.detach().clone() for t in st)
+        return {"format": "rechub_b200.hybrid/1", "kind": rw.kind, "step": int(rw._step_dev.item()), "bias_corr": rw._bc_dev.detach().clone(), "rowwise": rows, "dense": dense,
+                "param_groups": self.dense.state_dict()["param_groups"]}
+
+    def load_state_dict(self, sd):
+        if sd.get("format") != "rechub_b200.hybrid/1":
+            raise ValueError("not a HybridOptimizer state_dict (a dense torch optimiser's checkpoint cannot seed the row-wise state)")
+        rw, de = self.rowwise, self.dense_engine
+        if sd["kind"] != rw.kind or max(list(sd["rowwise"]) + [-1]) >= len(rw.params) or max(list(sd["dense"]) + [-1]) >= len(de.params):
+            raise ValueError("HybridOptimizer.load_state_dict: the checkpoint was written for another optimiser kind / parameter list")
+        rw._step_dev.fill_(int(sd["step"]))
+        rw._bc_dev.copy_(sd["bias_corr"])
+        for i, ent in sd["rowwise"].items():
+            st = rw._state(rw.params[i])
+            for k, t in ent.items():
+                if st.get(k) is None or st[k].shape != t.shape:
+                    raise ValueError("HybridOptimizer.load_state_dict: row-wise state %r of table %d does not fit" % (k, i))
+                st[k].copy_(t)
+        for i, ent in sd["dense"].items():
+            p = de.params[i]
+            cur = de.state.get(id(p))
+            if cur is None:
+                cur = (torch.zeros_like(p, memory_format=torch.contiguous_format) if rw.kind != 0 else None, torch.zeros_like(p, memory_format=torch.contiguous_format) if rw.kind == 1 else None)
+                de.state[id(p)] = cur
+            for dst, src in zip(cur, ent):
+                if dst is not None and src is not None:
+                    dst.copy_(src)
+        groups = sd.get("param_groups")
+        if groups:
+            for g, saved in zip(self.dense.param_groups, groups):
+                g.update({k: v for k, v in saved.items() if k != "params"})

@@ -107,11 +107,25 @@ def grad_target(weight):
     return buf, slot
 
 
+_MAX_PENDING = 64  # id lists remembered for the sparse re-zero before it degrades to one full zero_()
+
+
 def note_dirty(slot, ids):
-    """Record that the rows ``ids`` of the slot's buffer now hold gradient."""
-    if slot is None:
+    """Record that the rows ``ids`` of the slot's buffer now hold gradient.
+
+    The id list is SNAPSHOT unless the row-wise optimiser owns the step (it consumes and re-zeroes the rows inside the same step,
+    ``mark_clean``): with a dense ``torch.optim`` optimiser the list is read again at the NEXT ``zero_grad`` — by then a caller that
+    reuses its device id buffers (``PackedLoader`` staging, a captured step's static inputs) has overwritten it, and the sparse
+    clean would zero the wrong rows and leave stale gradients behind.  ``zero_grad(set_to_none=False)`` never reaches ``clean``;
+    the list is bounded: past ``_MAX_PENDING`` entries the slot is marked all-dirty (one full ``zero_()`` at the next clean).
+    """
+    if slot is None or slot.all_dirty:
         return
-    if config.static_inputs:
+    if not config.rowwise_optimizer and len(slot.pending) >= _MAX_PENDING:  # (the row-wise optimiser drains the list every step)
+        slot.pending = []
+        slot.all_dirty = True
+        return
+    if config.static_inputs or not config.rowwise_optimizer:
         slot.pending.append((ids.detach().clone(), True))
     else:
         slot.pending.append((ids.detach(), False))

@@ -193,7 +193,7 @@ class EmbeddingLayer(nn.Module):
                 plan.fields.append(ops.FieldRef(tbl.weight, ids, tbl.padding_idx, c, -1))
                 plan.by_name.setdefault(fea.name, plan.fields[-1])
             else:
-                plan.seqs.append(ops.SeqRef(tbl.weight, ids, fea.padding_idx, _POOL_MODES[fea.pooling], c))
+                plan.seqs.append(ops.SeqRef(tbl.weight, ids, tbl.padding_idx, _POOL_MODES[fea.pooling], c, mask_id=fea.padding_idx))
         plan.n_sparse_cols = col
         if with_dense:
             for fea in dense_feas:
