@@ -434,6 +434,12 @@ int rh_gemm_tf32x3(const float* A, int64_t lda, int a_mn_major,
 /* Output-tile width of rh_gemm_tf32x3: 0 = chosen per problem (64 when 128-wide tiles would leave more than half of the SMs idle and
  * the 64-wide grid still fits one wave), 64 / 128 = forced (A/B runs, tests).  Returns the setting in force. */
 int rh_gemm_tile_n(int set);
+/* Kernel variants of rh_gemm_tf32x3 (A/B runs, tests); an argument < 0 leaves that switch alone; returns bit 0 | bit 1 in force.
+ *   tma_epilogue (bit 0, default on): the accumulators leave through shared memory and cp.async.bulk.tensor stores (cp.reduce ... add
+ *     for split-K) issued by all 8 warps, instead of lane-per-row st.global / red.global from 4 warps (kept for C with ldc % 4 != 0);
+ *   concat_b (bit 1, default on): the (hi, lo) twins of the B tile lie back to back, so hi*hi and hi*lo are ONE tcgen05.mma of width
+ *     2 BN — 8 MMAs and 5 operand-tile reads per k-block instead of 12 and 6.  Same sums either way. */
+int rh_gemm_options(int tma_epilogue, int concat_b);
 
 
 /* The same GEMM (split_k = 1) with BatchNorm1d's training-mode column statistics of C = A B^T + bias computed in the epilogue —

@@ -84,7 +84,10 @@ def _check_table_grads(model, ref, rtol=2e-4):
         ids = torch.from_numpy(cg.ids).to(g.device)
         got = g.index_select(0, ids).cpu().numpy()
         scale = max(np.abs(cg.rows).max(), 1e-9)
-        _close_up_to_kinks(got, cg.rows, rtol, scale, k)
+        # a table row's gradient belongs to ONE sample (ids rarely repeat at 1M rows): a ReLU-kink flip of one of that sample's
+        # hidden units reaches its rows undiluted by any batch sum — measured 5.4 % of the tensor's largest entry on DCNv2
+        # (cross + deep paths), against < 5 % for the batch-summed tower gradients; the fraction of such entries stays bounded
+        _close_up_to_kinks(got, cg.rows, rtol, scale, k, outlier_cap=0.15)
         # nothing outside the touched rows: the whole buffer's |sum| equals the touched rows' |sum|
         assert abs(float(g.abs().sum()) - float(np.abs(got).sum())) <= 1e-4 * max(float(np.abs(got).sum()), 1e-9), k
         n += 1

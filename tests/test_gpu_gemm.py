@@ -70,6 +70,42 @@ def test_both_tile_widths(tile_n, M, N, K, a_mn, b_mn, bias, split_k):
     assert rel < 2e-6, rel
 
 
+@pytest.mark.parametrize("tma_epilogue,concat_b", [(1, 1), (0, 0), (1, 0), (0, 1)])
+@pytest.mark.parametrize("tile_n", [64, 128])
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn,bias,split_k", [
+    (4096, 256, 429, False, False, True, 1), (4096, 429, 256, False, True, False, 1), (256, 429, 4096, True, True, False, 16), (128, 256, 4096, True, True, False, 32),
+    (300, 70, 50, False, False, True, 1), (257, 200, 96, True, False, True, 2), (130, 64, 40, False, True, True, 1), (1000, 36, 32, False, False, True, 1)])
+def test_kernel_variants(tma_epilogue, concat_b, tile_n, M, N, K, a_mn, b_mn, bias, split_k):
+    """rh_gemm_options: the shared-memory + TMA-store epilogue (bulk reduce-add for split-K; rows / columns beyond (M, N) clipped by
+    the tensor map) and the concatenated-B MMA (one tcgen05.mma of width 2 BN for hi*hi and hi*lo) against the lane-per-row stores and
+    the three-MMA k-step, for both tile widths, every operand-major combination, tails, bias and split-K."""
+    from torch_rechub.b200 import _lib
+    L = _lib.lib()
+    before = L.rh_gemm_options(-1, -1)
+    assert L.rh_gemm_options(tma_epilogue, concat_b) == (tma_epilogue | (concat_b << 1))
+    L.rh_gemm_tile_n(tile_n)
+    try:
+        rel, C = _run(M, N, K, a_mn, b_mn, bias, split_k, lda_pad=1, ldb_pad=2)
+    finally:
+        L.rh_gemm_tile_n(0)
+        L.rh_gemm_options(before & 1, (before >> 1) & 1)
+    assert C.shape == (M, N)
+    assert rel < 2e-6, rel
+
+
+def test_tma_epilogue_leaves_the_padding_columns_alone():
+    """C with ldc > N (the tower's padded activations): the bulk stores are clipped at column N by the tensor map."""
+    from torch_rechub.b200 import ops
+    g = torch.Generator().manual_seed(3)
+    M, N, K = 300, 70, 64
+    A = torch.randn(M, K, generator=g).to(DEV)
+    B = torch.randn(N, K, generator=g).to(DEV)
+    buf = torch.full((M + 5, 72), 7.0, device=DEV)
+    ops.gemm3x(A, False, B, False, M, N, K, out=buf[:M])
+    assert torch.all(buf[:M, N:] == 7.0) and torch.all(buf[M:] == 7.0)
+    assert torch.allclose(buf[:M, :N], A @ B.t(), rtol=1e-4, atol=1e-4)
+
+
 def test_is_more_accurate_than_tf32_and_matches_fp32_level():
     from torch_rechub.b200 import ops
     g = torch.Generator().manual_seed(1)

@@ -263,6 +263,179 @@ __global__ void __launch_bounds__(256) fields_fwd_v4(const __grid_constant__ Fwd
 }
 
 
+// ------------------------------------------------------------------------------------------------
+// forward, 16-byte lanes, v6: the v4 mapping with the descriptor reads taken OFF the dependent chain.
+// What v4's trace + SASS showed (tools/fields_trace.cu, profiles/r02_fields_trace.txt): the ids arrived 1.95 us after block entry
+// and the four tile stores + FM updates took 2.3 us AFTER their rows had landed.  Neither is memory time: every use of p.f[f]
+// / p.d[j] is an INDEXED constant-bank read (LDC c[0x0][R+off]; the field index depends on the warp), the compiler re-reads the
+// descriptor word at each use, and the uses are separated by branches — 3-4 serial LDCs per field (tile_col -> dest_rows ->
+// dest[] -> fm_slot), the first touch of each 128-byte constant line per SM a miss to L2.  Here:
+//   * the block copies the used descriptors (n_fields x 48 B + n_dense x 24 B) into shared memory ONCE, one 16-byte piece per
+//     thread, all constant-bank misses in flight together; every later descriptor read is an LDS broadcast;
+//   * everything addressed by the sample alone (tile row pointer — in the peer-memory variant the destination GPU's tile and
+//     the integer division that picks it) is computed once per lane, not once per field;
+//   * the peer-memory route is a template flag, so the single-GPU kernel carries no division at all.
+// ------------------------------------------------------------------------------------------------
+template <int LPR, int NG, bool P2P>
+__global__ void __launch_bounds__(256, 4) fields_fwd_v6(const __grid_constant__ FwdParams p) {
+  constexpr int SPB = 32 / LPR;  // samples per warp row
+  constexpr int SW = 8 / NG;     // warp rows (sample groups) per block: always 8 warps per block
+  constexpr int CH = 4;          // row loads in flight per lane per chunk
+  __shared__ __align__(16) FieldDev s_f[RH_MAX_FIELDS];
+  __shared__ __align__(16) DenseDev s_d[RH_MAX_DENSE];
+  __shared__ float4 sm_s[SW][NG][32];
+  __shared__ float sm_ss[SW][NG][32];
+  __shared__ float sm_lr[SW][NG][32];
+  static_assert(sizeof(FieldDev) % 16 == 0 && (sizeof(DenseDev) * RH_MAX_DENSE) % 16 == 0, "descriptor arrays are copied in 16-byte pieces");
+
+  pdl_wait();
+  RH_FT(0, 0);
+  const int lane = threadIdx.x & 31;
+  const int g = threadIdx.x >> 5;
+  const int q = lane % LPR;
+  const int sw = threadIdx.y;
+  const int n_fields = p.n_fields, n_dense = p.n_dense;
+  {
+    const int tid = sw * (NG * 32) + (int)threadIdx.x;
+    const uint4* src = reinterpret_cast<const uint4*>(p.f);
+    uint4* dst = reinterpret_cast<uint4*>(s_f);
+    const int nf16 = n_fields * (int)(sizeof(FieldDev) / 16);
+    for (int i = tid; i < nf16; i += 256) dst[i] = src[i];
+    const uint4* srcd = reinterpret_cast<const uint4*>(p.d);
+    uint4* dstd = reinterpret_cast<uint4*>(s_d);
+    const int nd16 = (n_dense * (int)sizeof(DenseDev) + 15) / 16;  // rounds up inside the fixed-size array
+    for (int i = tid; i < nd16; i += 256) dstd[i] = srcd[i];
+  }
+  const int b = (blockIdx.x * SW + sw) * SPB + lane / LPR;
+  const int dim = p.dim;
+  const bool live = b < p.batch;
+  const bool lane_on = live && (4 * q < dim);
+  const bool want_fm = p.yfm != nullptr || p.ylr != nullptr || p.fsum != nullptr;
+  const bool want_lr = want_fm && p.lrw != nullptr;
+  const bool tile_vec = p.tile_vec != 0;
+  const float* const lrw = p.lrw;
+  // the sample's tile row (peer-memory variant: inside the tile of the GPU that holds the sample)
+  float* trow = nullptr;
+  if (live && p.tile != nullptr) {
+    if (P2P) {
+      const int dr = p.dest_rows;
+      const int which = b / dr;
+      trow = p.dest[which] + (int64_t)(b - which * dr) * p.tile_ld;
+    } else {
+      trow = p.tile + (int64_t)b * p.tile_ld;
+    }
+  }
+  __syncthreads();
+
+  float4 s = f4_zero();
+  float ss = 0.f, lr = 0.f;
+  // numeric columns, part 1: this warp's first two columns are loaded NOW so that their latency hides behind the gather
+  float dv[2] = {0.f, 0.f};
+  if (!P2P) {
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int j = g + NG * t;
+      if (trow != nullptr && j < n_dense) {
+        const DenseDev dd = s_d[j];
+        if (q < dd.width) dv[t] = load_dense_value(dd.src, (int64_t)b * dd.stride + q, dd.dtype);
+      }
+    }
+  }
+
+  for (int f0 = g; f0 < n_fields; f0 += NG * CH) {
+    int32_t rid[CH];
+    float4 w[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      const int f = f0 + j * NG;  // warp-uniform
+      rid[j] = -1;
+      w[j] = f4_zero();
+      if (f < n_fields) {
+        const FieldDev& fd = s_f[f];  // LDS broadcasts (descriptor words are re-read from shared memory where they are used:
+        if (live) {                    //  ~25 cycles each and independent across j — holding them cost 18 registers = one block/SM)
+          const int64_t id = load_id(fd.ids, (int64_t)b * fd.id_stride, fd.is_i32 != 0);
+          // the LR weights of the chunk's fields do not depend on the ids: they travel with them
+          if (want_lr && fd.fm_slot >= 0 && lane_on) w[j] = __ldg(reinterpret_cast<const float4*>(lrw + (int64_t)fd.fm_slot * dim + 4 * q));
+          if ((uint64_t)id < (uint64_t)fd.vocab) {
+            rid[j] = (int32_t)id;
+          } else if (q == 0 && p.err != nullptr) {
+            *p.err = 1 + f;
+          }
+        }
+      }
+    }
+    RH_FT(1, rid[0] + rid[1] + rid[2] + rid[3]);
+    float4 v[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      v[j] = f4_zero();
+      if (rid[j] >= 0 && lane_on) v[j] = ldg_row16(s_f[f0 + j * NG].table + (int64_t)rid[j] * dim + 4 * q);
+    }
+    RH_FT(2, v[0].x + v[1].x + v[2].x + v[3].x);
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      if (f0 + j * NG < n_fields && lane_on) {
+        const int tcol = s_f[f0 + j * NG].tile_col, slot = s_f[f0 + j * NG].fm_slot;
+        if (tcol >= 0 && trow != nullptr) st_tile4(trow + tcol + 4 * q, v[j], tile_vec);
+        if (slot >= 0 && want_fm) {
+          s = f4_add(s, v[j]);
+          ss += f4_dot(v[j], v[j]);
+          lr += f4_dot(v[j], w[j]);
+        }
+      }
+    }
+  }
+
+  RH_FT(3, ss);
+  // numeric columns, part 2: store the preloaded values; anything beyond them (more than 2 NG columns, widths above LPR) the slow way
+  if (!P2P && trow != nullptr) {
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int j = g + NG * t;
+      if (j < n_dense) {
+        const DenseDev dd = s_d[j];
+        if (q < dd.width) trow[dd.tile_col + q] = dv[t];
+      }
+    }
+    for (int j = g; j < n_dense; j += NG) {
+      const DenseDev dd = s_d[j];
+      for (int k = q + (j < g + 2 * NG ? LPR : 0); k < dd.width; k += LPR) trow[dd.tile_col + k] = load_dense_value(dd.src, (int64_t)b * dd.stride + k, dd.dtype);
+    }
+  }
+
+  RH_FT(4, 0);
+  if (!want_fm) return;  // block-uniform
+  if (NG > 1) {
+    sm_s[sw][g][lane] = s;
+    sm_ss[sw][g][lane] = ss;
+    sm_lr[sw][g][lane] = lr;
+    __syncthreads();
+    RH_FT(5, 0);
+    if (g != 0) return;
+#pragma unroll
+    for (int k = 1; k < NG; ++k) {
+      s = f4_add(s, sm_s[sw][k][lane]);
+      ss += sm_ss[sw][k][lane];
+      lr += sm_lr[sw][k][lane];
+    }
+  }
+  float t = (s.x * s.x + s.y * s.y) + (s.z * s.z + s.w * s.w) - ss;
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) {
+    t += __shfl_xor_sync(0xffffffffu, t, o);
+    lr += __shfl_xor_sync(0xffffffffu, lr, o);
+  }
+  if (live && q == 0) {
+    if (p.yfm != nullptr) p.yfm[b] = 0.5f * t;
+    if (p.ylr != nullptr) p.ylr[b] = lr + (p.lrb != nullptr ? __ldg(p.lrb) : 0.f);
+  }
+  if (p.fsum != nullptr && lane_on) {
+    *reinterpret_cast<float4*>(p.fsum + (int64_t)b * dim + 4 * q) = s;
+  }
+  RH_FT(6, t);
+}
+
+
 // forward, scalar lanes: any dim / any alignment, tile emission only (no FM/LR).
 __global__ void __launch_bounds__(256) fields_fwd_scalar(const __grid_constant__ FwdParams p) {
   const int dim = p.dim;
@@ -471,6 +644,15 @@ static int pack_fields(const rh_field* fields, int n_fields, FieldDev* out, bool
   return RH_OK;
 }
 
+// RECHUB_B200_FIELDS_FWD=4 keeps the round-1/2 kernel (descriptors read from the constant bank at every use) for A/B runs.
+static bool use_fwd_v4() {
+  static const int v = [] {
+    const char* e = getenv("RECHUB_B200_FIELDS_FWD");
+    return (e != nullptr && e[0] == '4') ? 1 : 0;
+  }();
+  return v != 0;
+}
+
 template <int LPR>
 static void launch_fwd_v4(const FwdParams& p, cudaStream_t st) {
   constexpr int SPB = 32 / LPR;
@@ -480,12 +662,28 @@ static void launch_fwd_v4(const FwdParams& p, cudaStream_t st) {
   const int sw = 8 / ng;
   const int grid = (p.batch + SPB * sw - 1) / (SPB * sw);
   const dim3 block(ng * 32, sw);
-  switch (ng) {
-    case 1: launch_k(fields_fwd_v4<LPR, 1>, dim3(grid), block, 0, st, p); break;
-    case 2: launch_k(fields_fwd_v4<LPR, 2>, dim3(grid), block, 0, st, p); break;
-    case 4: launch_k(fields_fwd_v4<LPR, 4>, dim3(grid), block, 0, st, p); break;
-    default: launch_k(fields_fwd_v4<LPR, 8>, dim3(grid), block, 0, st, p); break;
+  if (use_fwd_v4()) {
+    switch (ng) {
+      case 1: launch_k(fields_fwd_v4<LPR, 1>, dim3(grid), block, 0, st, p); break;
+      case 2: launch_k(fields_fwd_v4<LPR, 2>, dim3(grid), block, 0, st, p); break;
+      case 4: launch_k(fields_fwd_v4<LPR, 4>, dim3(grid), block, 0, st, p); break;
+      default: launch_k(fields_fwd_v4<LPR, 8>, dim3(grid), block, 0, st, p); break;
+    }
+    return;
   }
+  const bool p2p = p.dest_rows > 0;
+#define RH_FWD6(NGV)                                                                        \
+  do {                                                                                      \
+    if (p2p) launch_k(fields_fwd_v6<LPR, NGV, true>, dim3(grid), block, 0, st, p);          \
+    else launch_k(fields_fwd_v6<LPR, NGV, false>, dim3(grid), block, 0, st, p);             \
+  } while (0)
+  switch (ng) {
+    case 1: RH_FWD6(1); break;
+    case 2: RH_FWD6(2); break;
+    case 4: RH_FWD6(4); break;
+    default: RH_FWD6(8); break;
+  }
+#undef RH_FWD6
 }
 
 template <int LPR>

@@ -10,9 +10,15 @@
 //   warp 0      TMA producer: cp.async.bulk.tensor.2d of the raw fp32 A / B tiles (SWIZZLE_128B), mbarrier tx bytes
 //   warps 2..7  splitters: read the raw tiles, write hi (truncated) back in place and lo into the twin tiles,
 //               fence.proxy.async, arrive on `ready`
-//   warp 1      MMA issuer: one thread issues 12 tcgen05.mma.kind::tf32 (M128 N128 K8) per k-block, tcgen05.commit frees
-//               the stage; also owns the TMEM allocation (128 columns)
-//   warps 4..7  epilogue: tcgen05.ld 32x32b.x32 -> registers -> (+bias) -> st.global / red.global (split-K)
+//   warp 1      MMA issuer: one thread issues the tcgen05.mma.kind::tf32 (M128 K8) of a k-block, tcgen05.commit frees the stage;
+//               also owns the TMEM allocation (256 columns: main + cross-term accumulators).  With the B twins laid out back
+//               to back (concat_b, default) hi*hi and hi*lo are ONE MMA of width 2 BN (A_hi read once): 8 MMAs per k-block
+//               instead of 12, 5 operand-tile reads instead of 6
+//   all warps   epilogue (default): tcgen05.ld 32x32b.x32 of both accumulators -> registers -> (+bias) -> a 32 x 32 box in the
+//               idle stage ring (128-byte swizzle) -> ONE cp.async.bulk.tensor store (cp.reduce...add for split-K) per box.
+//               Warp w owns TMEM lane quadrant w % 4 and every second 32-column chunk.  (Round 2 trace: the lane-per-row
+//               st.global.v4 epilogue cost 7.2 k cycles per 128 x 128 tile — 32 scattered 16-byte stores per instruction, after
+//               TMEM reads that could not overlap them; kept as the fallback for unaligned C and for the STATS instantiation.)
 // Operands may be K-major (row-major [rows, K]) or MN-major (row-major [K, rows], i.e. the transposed use of a stored
 // matrix): dX = dH * W and dW = dH^T * X read W, dH and X as stored — no transposed copies.
 //
@@ -88,6 +94,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_addr, int c0, int c1, bool reduce_add) {
+  if (reduce_add) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_addr), "r"(c0), "r"(c1)
+                 : "memory");
+  } else {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_addr), "r"(c0), "r"(c1) : "memory");
+  }
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -118,6 +133,8 @@ struct GemmP {
   int kblocks_per_split;
   int reduce;       // 1: red.global.add into C (split-K), 0: plain stores
   int bn;           // output tile width: 128 or 64 (B tile = bn x 32 floats; the stage layout keeps its 16 KB slots)
+  int epi;          // 1: epilogue through shared memory + TMA stores (map_c), by all 8 warps; 0: lane-per-row stores by warps 4..7
+  int bcat;         // 1: stage = [A_hi | A_lo | B_hi | B_lo] with B_lo right behind B_hi: hi*hi and hi*lo are one MMA of width 2 bn
   // STATS instantiation only (BatchNorm column statistics of C in the epilogue):
   float* stats;            // (2N + 1): mean | biased variance | step counter bits
   float* partial;          // [n_tile][m_tile][2][128]: per-tile column mean and M2
@@ -174,7 +191,8 @@ __device__ __forceinline__ void welford_merge(float& n, float& mean, float& m2, 
 
 template <bool STATS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmP p) {
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_c,
+                   const GemmP p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kStageBytes);
@@ -192,10 +210,18 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   int kb1 = kb0 + p.kblocks_per_split;
   if (kb1 > total_kb) kb1 = total_kb;
   const int n_iter = kb1 - kb0;  // >= 1 by construction of the grid
+  // stage layout (byte offsets inside a 64 KB stage): legacy [A_hi][B_hi][A_lo][B_lo] in 16 KB slots; concat_b [A_hi][A_lo][B_hi][B_lo]
+  // with B_lo RIGHT behind the bn x 128 bytes of B_hi (one 2 bn-row operand for the MMA)
+  const bool bcat = !STATS && p.bcat != 0;
+  const uint32_t off_alo = bcat ? (uint32_t)kTileBytes : 2u * kTileBytes;
+  const uint32_t off_bhi = bcat ? 2u * kTileBytes : (uint32_t)kTileBytes;
+  const uint32_t off_blo = bcat ? 2u * kTileBytes + (uint32_t)bn * 128u : 3u * kTileBytes;
+  const uint32_t cross_col = bcat ? (uint32_t)bn : 128u;  // TMEM column of the cross-term accumulator
   if (threadIdx.x == 0) RH_TR(0);
   if (threadIdx.x == 32) {  // the descriptors' first use costs a fetch (~800 cycles before the first TMA issue, tools/gemm_trace.cu): start it now
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+    if (!STATS && p.epi) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_c)) : "memory");
   }
 
   if (threadIdx.x == 0) {
@@ -234,18 +260,20 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           tma_load_2d(st, &map_a, &full[s], k0, m0);
         }
         if (p.b_mn) {
-          for (int i = 0; i < bn / 32; ++i) tma_load_2d(st + kTileBytes + i * 4096, &map_b, &full[s], n0 + 32 * i, k0);
+          for (int i = 0; i < bn / 32; ++i) tma_load_2d(st + off_bhi + i * 4096, &map_b, &full[s], n0 + 32 * i, k0);
         } else {
-          tma_load_2d(st + kTileBytes, &map_b, &full[s], k0, n0);
+          tma_load_2d(st + off_bhi, &map_b, &full[s], k0, n0);
         }
         if (it == 0) RH_TR(2);
         if (it == n_iter - 1) RH_TR(3);
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     // ===== MMA issuer =====
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) | ((uint32_t)(bn >> 3) << 17) |
                            ((uint32_t)(kBM >> 4) << 24);
+    const uint32_t idesc2 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)((2 * bn) >> 3) << 17);  // the same MMA, N = 2 bn
     const uint32_t a_step = p.a_mn ? (1024u >> 4) : (32u >> 4);
     const uint32_t b_step = p.b_mn ? (1024u >> 4) : (32u >> 4);
     for (int it = 0; it < n_iter; ++it) {
@@ -256,8 +284,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       if (lane == 0) {
         if (it == 0) RH_TR(6);
         const uint32_t base = smem_u32(smem + (size_t)s * kStageBytes);
-        const uint64_t a_hi = make_desc(base, p.a_mn != 0), b_hi = make_desc(base + kTileBytes, p.b_mn != 0);
-        const uint64_t a_lo = make_desc(base + 2 * kTileBytes, p.a_mn != 0), b_lo = make_desc(base + 3 * kTileBytes, p.b_mn != 0);
+        const uint64_t a_hi = make_desc(base, p.a_mn != 0), b_hi = make_desc(base + off_bhi, p.b_mn != 0);
+        const uint64_t a_lo = make_desc(base + off_alo, p.a_mn != 0), b_lo = make_desc(base + off_blo, p.b_mn != 0);
 #pragma unroll
         for (int kk = 0; kk < kBK / 8; ++kk) {
           const uint64_t da = (uint64_t)(kk * a_step), db = (uint64_t)(kk * b_step);
@@ -265,9 +293,16 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           // bias (measured: 160 MMAs into one accumulator = 11x the fp32 error).  The small cross terms therefore get their
           // OWN accumulator; the main one sees one MMA per k-step.  The epilogue adds the two in fp32.
           const uint32_t first = (it > 0 || kk > 0) ? 1u : 0u;
-          umma_tf32(tmem_base, a_hi + da, b_hi + db, idesc, first);
-          umma_tf32(tmem_base + 128u, a_hi + da, b_lo + db, idesc, first);
-          umma_tf32(tmem_base + 128u, a_lo + da, b_hi + db, idesc, 1u);
+          if (bcat) {
+            // [B_hi ; B_lo] is one operand of 2 bn rows: columns [0, bn) of the accumulator block receive A_hi B_hi^T (main),
+            // columns [bn, 2 bn) A_hi B_lo^T (cross) — the same sums as the two MMAs below, with A_hi read once
+            umma_tf32(tmem_base, a_hi + da, b_hi + db, idesc2, first);
+            umma_tf32(tmem_base + cross_col, a_lo + da, b_hi + db, idesc, 1u);
+          } else {
+            umma_tf32(tmem_base, a_hi + da, b_hi + db, idesc, first);
+            umma_tf32(tmem_base + 128u, a_hi + da, b_lo + db, idesc, first);
+            umma_tf32(tmem_base + 128u, a_lo + da, b_hi + db, idesc, 1u);
+          }
         }
         umma_commit(&empty[s]);                       // stage free once these MMAs have read it
         if (it == n_iter - 1) umma_commit(tmem_full);  // accumulator complete
@@ -284,9 +319,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       mbar_wait(&full[s], ph);
       if (t == 0 && it == 0) RH_TR(4);
       uint8_t* st = smem + (size_t)s * kStageBytes;
-      for (int i = t; i < (kTileBytes + bn * kBK * 4) / 16; i += kSplitWarps * 32) {  // A tile, then the bn x 32 B tile right behind it
-        float4* src = reinterpret_cast<float4*>(st + (size_t)i * 16);
-        float4* dst = reinterpret_cast<float4*>(st + 2 * kTileBytes + (size_t)i * 16);
+      for (int i = t; i < (kTileBytes + bn * kBK * 4) / 16; i += kSplitWarps * 32) {  // the A tile's 1024 16-byte pieces, then the bn x 32 B tile's
+        const bool is_a = i < kTileBytes / 16;
+        const uint32_t so = is_a ? (uint32_t)i * 16u : off_bhi + (uint32_t)(i - kTileBytes / 16) * 16u;
+        float4* src = reinterpret_cast<float4*>(st + so);
+        float4* dst = reinterpret_cast<float4*>(st + so + (is_a ? off_alo : off_blo - off_bhi));
         const float4 x = *src;
         // lo = x - (top 19 bits of x): exact in fp32 (the 13 dropped mantissa bits); the tensor core keeps its top 11 bits.
         // (Rounding lo to tf32 with cvt.rna was measured to change nothing — the residual error is the accumulator's
@@ -304,8 +341,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       if (t == 0 && it == 0) RH_TR(5);
       if (t == 0 && it == n_iter - 1) RH_TR(8);
     }
-    // ===== epilogue (warps 4..7 own TMEM lane quadrants 0..3) =====
-    if (warp >= 4) {
+    // ===== lane-per-row epilogue (warps 4..7 own TMEM lane quadrants 0..3): STATS instantiation and unaligned C =====
+    if (warp >= 4 && (STATS || !p.epi)) {
       const int q = warp - 4;
       mbar_wait(tmem_full, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -318,7 +355,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         uint32_t r[32], x[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
         tmem_ld32(taddr, r);
-        tmem_ld32(taddr + 128u, x);
+        tmem_ld32(taddr + cross_col, x);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(x[j]));
@@ -449,6 +486,58 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       }
     }
   }
+  if (!STATS && p.epi) {
+    // ===== epilogue through shared memory + TMA stores, all 8 warps =====
+    // Warp w reads TMEM lane quadrant w % 4 (the hardware's access rule) = rows m0 + 32 (w % 4) ..+31 of the tile, and every second
+    // 32-column chunk (chunk c belongs to the warps with (c & 1) == w / 4).  Per chunk: both accumulators -> registers (lane = row),
+    // summed (+ bias), written as a 32 x 32 fp32 box into the idle stage ring in TMA's 128-byte swizzle (16-byte piece j of row r at
+    // position j ^ (r & 7): conflict-free wavefronts), fence.proxy.async, then ONE bulk tensor store — or, for split-K, one bulk
+    // reduce-add: L2 adds whole 16-byte vectors, rows and columns beyond (M, N) are clipped by the tensor map.  The stores drain
+    // while the warp reads its next chunk; 8 KB of staging per warp.
+    __syncwarp();
+    const int q = warp & 3, half = warp >> 2;
+    mbar_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (warp == 4 && lane == 0) RH_TR(9);
+    const bool add_bias = p.bias != nullptr && blockIdx.z == 0;
+    const int row0 = m0 + q * 32;
+    uint8_t* my_stage = smem + (size_t)warp * 8192;  // the ring's MMAs have all completed (tmem_full) and its TMA loads were consumed
+    int slot = 0;
+#pragma unroll 1
+    for (int c = half; c < bn / 32; c += 2, ++slot) {
+      const int nb = n0 + c * 32;
+      if (row0 >= p.M || nb >= p.N) continue;  // warp-uniform: nothing of this box lies inside C
+      uint32_t r[32], x[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
+      tmem_ld32(taddr, r);
+      tmem_ld32(taddr + cross_col, x);
+      float bv[32];
+      if (add_bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) bv[j] = (nb + j < p.N) ? __ldg(p.bias + nb + j) : 0.f;
+      }
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(x[j]));
+      if (add_bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + bv[j]);
+      }
+      const uint32_t box = smem_u32(my_stage + (slot & 1) * 4096);
+      const uint32_t rowaddr = box + (uint32_t)lane * 128u;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + (uint32_t)((j ^ (lane & 7)) << 4)), "r"(r[4 * j]), "r"(r[4 * j + 1]),
+                     "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+                     : "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA engine
+      __syncwarp();
+      if (lane == 0) tma_store_2d(&map_c, box, nb, row0, p.reduce != 0);
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the boxes have been read: shared memory may go
+    if (warp == 4 && lane == 0) RH_TR(10);
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (threadIdx.x == 0) RH_TR(11);
@@ -523,6 +612,37 @@ extern "C" int rh_gemm_tile_n(int set) {
   return g_tile_n;
 }
 
+// Kernel variants (A/B runs and tests): bit 0 = epilogue through shared memory + TMA stores, bit 1 = concatenated B twins.
+// Defaults: both on; RECHUB_B200_GEMM_TMA_EPILOGUE=0 / RECHUB_B200_GEMM_CONCAT_B=0 switch them off for the process.
+static int g_gemm_opts = -1;
+static int gemm_opts() {
+  if (g_gemm_opts < 0) {
+    const char* e = getenv("RECHUB_B200_GEMM_TMA_EPILOGUE");
+    const char* c = getenv("RECHUB_B200_GEMM_CONCAT_B");
+    g_gemm_opts = ((e == nullptr || e[0] != '0') ? 1 : 0) | ((c == nullptr || c[0] != '0') ? 2 : 0);
+  }
+  return g_gemm_opts;
+}
+extern "C" int rh_gemm_options(int tma_epilogue, int concat_b) {
+  int o = gemm_opts();
+  if (tma_epilogue >= 0) o = (o & ~1) | (tma_epilogue ? 1 : 0);
+  if (concat_b >= 0) o = (o & ~2) | (concat_b ? 2 : 0);
+  g_gemm_opts = o;
+  return o;
+}
+
+// C (M x N, row stride ldc) as 32 x 32 boxes for the epilogue's bulk stores / reduce-adds.
+static int make_map_c(CUtensorMap* map, float* base, int64_t ldc, int M, int N) {
+  EncodeTiledFn fn = encode_fn();
+  RH_REQUIRE(fn != nullptr, RH_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)M}, gstride[1] = {(cuuint64_t)ldc * sizeof(float)};
+  cuuint32_t box[2] = {32, 32}, estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RH_REQUIRE(r == CUDA_SUCCESS, RH_ERR_CUDA, "cuTensorMapEncodeTiled (C) failed (%d): base %p ldc %lld M %d N %d", (int)r, (void*)base, (long long)ldc, M, N);
+  return RH_OK;
+}
+
 static int gemm_impl(const float* A, int64_t lda, int a_mn_major, const float* B, int64_t ldb, int b_mn_major, float* C, int64_t ldc, int M, int N,
                      int K, const float* bias, int split_k, void* stream, const StatsArgs* st) {
   RH_REQUIRE(A && B && C, RH_ERR_INVALID_ARG, "rh_gemm_tf32x3: NULL pointer");
@@ -546,11 +666,19 @@ static int gemm_impl(const float* A, int64_t lda, int a_mn_major, const float* B
     const int64_t ctas128 = (int64_t)m_tiles * ((N + 127) / 128) * split_k, ctas64 = (int64_t)m_tiles * ((N + 63) / 64) * split_k;
     if (g_tile_n == 64 || (ctas128 * 2 <= num_sms() && ctas64 <= num_sms())) bn = 64;
   }
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a, map_b, map_c;
   int rc = make_map(&map_a, A, lda, M, K, a_mn_major != 0, kBM);
   if (rc != RH_OK) return rc;
   rc = make_map(&map_b, B, ldb, N, K, b_mn_major != 0, bn);
   if (rc != RH_OK) return rc;
+  const int opts = gemm_opts();
+  const bool tma_epi = st == nullptr && (opts & 1) != 0 && ldc % 4 == 0 && ((uintptr_t)C & 15u) == 0;  // TMA needs 16-byte rows of C
+  if (tma_epi) {
+    rc = make_map_c(&map_c, C, ldc, M, N);
+    if (rc != RH_OK) return rc;
+  } else {
+    map_c = map_a;  // unused by the kernel
+  }
 
   GemmP p;
   memset(&p, 0, sizeof(p));
@@ -565,6 +693,8 @@ static int gemm_impl(const float* A, int64_t lda, int a_mn_major, const float* B
   p.kblocks_per_split = per;
   p.reduce = split_k > 1 ? 1 : 0;
   p.bn = bn;
+  p.epi = tma_epi ? 1 : 0;
+  p.bcat = (st == nullptr && (opts & 2) != 0) ? 1 : 0;
 #ifdef RH_GEMM_TRACE
   p.trace = g_gemm_trace;
 #endif
@@ -588,9 +718,9 @@ static int gemm_impl(const float* A, int64_t lda, int a_mn_major, const float* B
     p.running_var = st->running_var;
     p.num_batches_tracked = reinterpret_cast<long long*>(st->num_batches_tracked);
     p.momentum = st->momentum;
-    launch_k(gemm_tf32x3_kernel<true>, grid, dim3(kGemmThreads), kGemmSmem, (cudaStream_t)stream, map_a, map_b, p);
+    launch_k(gemm_tf32x3_kernel<true>, grid, dim3(kGemmThreads), kGemmSmem, (cudaStream_t)stream, map_a, map_b, map_c, p);
   } else {
-    launch_k(gemm_tf32x3_kernel<false>, grid, dim3(kGemmThreads), kGemmSmem, (cudaStream_t)stream, map_a, map_b, p);
+    launch_k(gemm_tf32x3_kernel<false>, grid, dim3(kGemmThreads), kGemmSmem, (cudaStream_t)stream, map_a, map_b, map_c, p);
   }
   RH_LAUNCH_CHECK();
   return RH_OK;

@@ -68,6 +68,7 @@ PROTOTYPES = {
     "rh_head_fwd": [c_p, c_i64, c_i64, c_i, c_p, c_p, c_p, c_p, c_i, c_p, c_p],
     "rh_head_bwd": [c_p, c_i64, c_i64, c_i, c_p, c_p, c_p, c_i, c_p, c_i64, c_p, c_p, c_p, c_p],
     "rh_gemm_tile_n": [c_i],
+    "rh_gemm_options": [c_i, c_i],
     "rh_peer_wait": [c_p, c_i, c_p, c_p],
     "rh_copy_segments": [c_i, c_p, c_p, c_p, c_p],
     "rh_bce_fwd": [c_p, c_p, c_i64, c_p, c_p, c_p],

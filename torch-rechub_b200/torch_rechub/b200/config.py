@@ -93,6 +93,10 @@ pdl = _flag("RECHUB_B200_PDL", False)
 # table rows are the dominant DRAM access: measured DRAM reads per 106 k-row gather: 14.4 MB at 128, 7.7 MB (= algorithmic) at 64 / 32.
 l2_fetch_granularity = int(os.environ.get("RECHUB_B200_L2_FETCH_GRANULARITY", "32"))
 
+# The optimiser's step-counter / bias-correction launch (rh_opt_advance) is issued at the START of the step on the side stream
+# (RowwiseOptimizer.advance_early) instead of between the scatter-add and the row-wise update.
+early_opt_advance = _flag("RECHUB_B200_EARLY_OPT_ADVANCE", True)
+
 # Set by the graph runner while inputs live in static buffers that the next batch overwrites.
 static_inputs = False
 

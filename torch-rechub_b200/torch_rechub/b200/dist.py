@@ -591,6 +591,8 @@ class DistEngine(object):
         opt = trainer.optimizer
         split = hasattr(opt, "rowwise") and hasattr(opt, "dense_engine")
         from . import config
+        if split and self.device.type == "cuda":
+            opt.rowwise.advance_early()  # joined by rowwise.step() below
         peer = split and self.peer_reduce is not None
         for f in self.fronts:
             # peer-memory reduction: the post-backward barrier is replaced by a wait on the gradient-publication flags (below)

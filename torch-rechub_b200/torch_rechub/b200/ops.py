@@ -731,14 +731,21 @@ def _linear_bwd(d_h, x2, W, Wp, use_tc, need_dx):
     if use_tc:  # dW[cols, K] = d_h^T x: both operands read as stored (MN-major), K = rows split over CTAs
         concurrent = config.concurrent_tower_bwd and need_dx
         split = _split_k_for((cols + 127) // 128, (K + 127) // 128, (rows + 31) // 32, budget=64 if concurrent else 128)
-        d_W = torch.zeros((cols, K), dtype=torch.float32, device=dev) if split > 1 else torch.empty((cols, K), dtype=torch.float32, device=dev)
+        d_W = torch.empty((cols, K), dtype=torch.float32, device=dev)
         if concurrent:
-            # dW and dX only share their input d_h: dW runs on a second stream (half the SMs each), joined before returning
+            # dW and dX only share their input d_h: dW runs on a second stream (half the SMs each), joined before returning.  The
+            # zero fill of the split-K target goes with it: on the main stream it sat between the BatchNorm backward and dX
+            # (one more node on the step's critical path).  d_W is handed back after the join, so its allocation on the main
+            # stream's pool is safe.
             cur, fork = torch.cuda.current_stream(), _aux_stream(dev)
             fork.wait_stream(cur)
             with torch.cuda.stream(fork):
+                if split > 1:
+                    d_W.zero_()
                 gemm3x(d_h, True, x2, True, cols, K, rows, split_k=split, out=d_W)
         else:
+            if split > 1:
+                d_W.zero_()
             gemm3x(d_h, True, x2, True, cols, K, rows, split_k=split, out=d_W)
     else:
         d_W = torch.mm(d_h.t(), x2)

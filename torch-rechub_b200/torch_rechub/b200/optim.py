@@ -74,8 +74,29 @@ class RowwiseOptimizer(object):
         self.apply()
 
     def advance(self):
-        """Step counter += 1 and the Adam bias corrections, on the device (shared with the dense optimiser)."""
+        """Step counter += 1 and the Adam bias corrections, on the device (shared with the dense optimiser).  A step that called
+        ``advance_early`` only joins the side stream here."""
+        early = getattr(self, "_early", None)
+        if early is not None:
+            self._early = None
+            torch.cuda.current_stream(early.device).wait_stream(early)
+            return
         check(_lib.lib().rh_opt_advance(self._step_dev.data_ptr(), self._bc_dev.data_ptr(), self.betas[0], self.betas[1], stream_ptr()), "rh_opt_advance")
+
+    def advance_early(self):
+        """Called by the trainers at the START of a step: the counter / bias-correction launch depends on nothing the step computes
+        (only on the previous step's optimiser kernels having read the old values), so it runs on the side stream next to the
+        forward instead of between the scatter and the row-wise update — one node less on the step's critical path (captured
+        graphs keep the fork).  ``advance`` joins."""
+        from . import ops
+        dev = self.params[0].device
+        if dev.type != "cuda" or not config.early_opt_advance or getattr(self, "_early", None) is not None:
+            return
+        cur, aux = torch.cuda.current_stream(dev), ops._aux_stream(dev)
+        aux.wait_stream(cur)  # behind the previous step's rh_fields_rowwise_update / rh_dense_update (they read the old values)
+        with torch.cuda.stream(aux):
+            check(_lib.lib().rh_opt_advance(self._step_dev.data_ptr(), self._bc_dev.data_ptr(), self.betas[0], self.betas[1], stream_ptr()), "rh_opt_advance")
+        self._early = aux
 
     def apply(self):
         """Update (and re-zero the gradient of) every row touched since the last step."""

@@ -132,6 +132,9 @@ class CTRTrainer(object):
         """zero_grad -> forward -> loss -> backward -> optimizer step; returns the loss tensor (reference ``:87-99``)."""
         if self._dist is not None:
             return self._dist.train_step(self, x_dict, y)
+        rw = getattr(self.optimizer, "rowwise", None)
+        if rw is not None:
+            rw.advance_early()  # step counter / bias corrections: off the critical path (joined by optimizer.step())
         loss = self._loss(x_dict, y)
         self.model.zero_grad()
         if loss.is_cuda and loss.dim() == 0 and loss.dtype == torch.float32:
