@@ -36,6 +36,7 @@ typedef enum rh_status {
   RH_ERR_CUDA = 3           /* a CUDA runtime call failed (message holds cudaGetErrorString) */
 } rh_status;
 
+#define RH_ERRFLAG_SYNC_TIMEOUT 0x7ffffff0 /* err_flag value: a cross-GPU hand-over (rh_sync) saw no signal for ~2^24 polls */
 #define RH_MAX_FIELDS 64    /* id columns per rh_fields_* launch (callers chunk beyond it)  */
 #define RH_MAX_DENSE  32    /* numeric columns per rh_fields_fwd launch                     */
 
@@ -126,6 +127,46 @@ int rh_fields_fwd_p2p(const rh_field* fields, int n_fields, int dim, int batch,
 int rh_ids_scatter(const rh_field* cols, int n_cols, const int32_t* col_dest, int batch,
                    int64_t* const* dest_base, int n_dest, int fmax, int64_t slot_stride, int64_t sample_stride,
                    void* stream);
+
+/* The exchange's cross-GPU hand-overs folded INTO the launches (no barrier kernels between them).  Every rank keeps, per phase, a
+ * flags array of 8 int32 in peer-mapped memory: flags[s] = the last step for which rank s's data of that phase has landed here.
+ *   producer side  sig_flags[d] = destination d's flags array of the phase this launch PRODUCES (d < sig_world); when the grid's last
+ *                  CTA has finished, the step number goes to sig_flags[d][sig_rank] for every d (one system fence, st.release.sys);
+ *                  ticket: one zeroed unsigned per launch site, left zeroed.
+ *   consumer side  wait_flags = MY flags array of the phase this launch CONSUMES: every CTA waits (ld.acquire.sys) until
+ *                  wait_flags[s] >= *step for each s in wait_mask before it reads peer-written memory.
+ *   step           device int32, advanced once per exchange by rh_ids_scatter_signal (which publishes *step + 1).
+ *   id_snapshot_delta (bytes, owner-side gather): every id read at address a is also stored at a + delta — the local copy the
+ *                  owner's backward / optimiser use while the peers may already be refilling the id buffer.
+ * Step numbers only grow: no flag is ever reset.  All pointers NULL / masks 0 = no hand-over on that side. */
+typedef struct rh_sync {
+  const int32_t*  wait_flags;
+  const int32_t*  step;
+  int32_t* const* sig_flags;
+  int32_t*        ticket;
+  int32_t         wait_mask;
+  int32_t         sig_world;
+  int32_t         sig_rank;
+  int32_t         reserved;
+  int64_t         id_snapshot_delta;
+} rh_sync;
+
+/* rh_fields_fwd (dest_tiles == NULL) or rh_fields_fwd_p2p (dest_tiles != NULL: dense / lr / fm arguments must be NULL / 0) with the
+ * hand-overs of `sync` inside the launch. */
+int rh_fields_fwd_sync(const rh_field* fields, int n_fields, int dim,
+                       const rh_dense* dense, int n_dense, int batch,
+                       float* tile, int64_t tile_ld,
+                       const float* lr_weight, const float* lr_bias,
+                       float* y_fm, float* y_lr, float* field_sum,
+                       float* const* dest_tiles, int n_dest, int rows_per_dest,
+                       const rh_sync* sync, int32_t* err_flag, void* stream);
+
+/* rh_ids_scatter that advances the exchange's step counter and publishes it: when the last CTA has stored its ids, *step_dev + 1 goes
+ * to peer_flags[d][rank] for every d < world (the owners' id-phase flags) and into *step_dev. */
+int rh_ids_scatter_signal(const rh_field* cols, int n_cols, const int32_t* col_dest, int batch,
+                          int64_t* const* dest_base, int n_dest, int fmax, int64_t slot_stride, int64_t sample_stride,
+                          int32_t* const* peer_flags, int rank, int world, int32_t* step_dev, int32_t* ticket_dev,
+                          void* stream);
 
 /* Backward of rh_fields_fwd: the sparse-gradient scatter-add into the tables' gradient buffers.
  *
@@ -424,7 +465,10 @@ int rh_dense_reduce_update(int n_tensors, float* const* params, float* const* st
  *   (reference basic/layers.py:281-292; ATen addmm / mm there).
  *   a_mn_major == 0: A is stored row-major [M][lda] (K contiguous);  != 0: A is stored [K][lda] (M contiguous), i.e. the
  *   caller passes the matrix whose TRANSPOSE is the operand (dW = dH^T X reads dH and X as stored).  Same for B.
- *   lda, ldb must be multiples of 4 floats and A, B 16-byte aligned (TMA); C any ldc >= N.
+ *   lda, ldb must be multiples of 4 floats and A, B 16-byte aligned (TMA); C any ldc >= N.  Rows of C that are 16-byte aligned
+ *   (ldc % 4 == 0, C 16-byte aligned, ldc >= 4 * ceil(N / 4)) leave through bulk tensor stores whose clipping works on 16-byte
+ *   pieces: columns N .. 4 * ceil(N / 4) - 1 of such a row are PADDING and may be overwritten (with the zero products of the
+ *   out-of-range columns).  Any other C is written element-exactly by the lane-per-row epilogue.
  *   split_k > 1: K is cut into split_k slices accumulated with red.global.add — C must be zero on entry.
  * ------------------------------------------------------------------------------------------- */
 int rh_gemm_tf32x3(const float* A, int64_t lda, int a_mn_major,

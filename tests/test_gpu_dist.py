@@ -39,7 +39,7 @@ def _make(kind):
     return DCN(dense + sparse, n_cross_layers=2, mlp_params={"dims": [32, 16]})
 
 
-N_STEPS = 2
+N_STEPS = 3  # the third step meets id / row buffers and flags that two earlier exchanges have used
 
 
 def _batch(rank, step=0, b=256):
@@ -52,8 +52,10 @@ def _batch(rank, step=0, b=256):
 def _worker(rank, world, port, kind, variant, out):
     if PKG not in sys.path:
         sys.path.insert(0, PKG)
+    fused = "0" if variant.endswith("-barriers") else "1"  # "-barriers": the hand-overs as separate barrier kernels (the checker of the fused route)
+    variant = variant[0]
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
-                      RECHUB_B200_P2P_DIRECT_GRADS=variant, RECHUB_B200_P2P_FIELD_MAJOR=variant)
+                      RECHUB_B200_P2P_DIRECT_GRADS=variant, RECHUB_B200_P2P_FIELD_MAJOR=variant, RECHUB_B200_P2P_FUSED_SYNC=fused)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -62,6 +64,8 @@ def _worker(rank, world, port, kind, variant, out):
     model = _make(kind)
     full_sd = copy.deepcopy(model.state_dict())
     trainer = CTRTrainer(model, optimizer_fn=torch.optim.SGD, optimizer_params={"lr": 0.1}, device=str(dev))
+    from torch_rechub.b200 import config
+    assert config.p2p_fused_sync == (fused == "1")
     assert trainer._dist is not None
     assert (trainer._dist.grad_pool is not None) == (variant == "1")
     model.train()
@@ -77,8 +81,7 @@ def _worker(rank, world, port, kind, variant, out):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("variant", ["1", "0"])
-@pytest.mark.parametrize("kind", ["deepfm", "dcn"])
+@pytest.mark.parametrize("kind,variant", [("deepfm", "1"), ("deepfm", "0"), ("dcn", "1"), ("dcn", "0"), ("deepfm", "1-barriers")])
 def test_two_gpu_sharded_step(kind, variant):
     world = 2
     out = mp.get_context("spawn").Manager().dict()

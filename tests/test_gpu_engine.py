@@ -227,9 +227,10 @@ def test_full_size_properties():
     _lib.check_errors()
 
 
-def test_hybrid_optimizer_state_dict_round_trip_resumes_bit_identically():
+def test_hybrid_optimizer_state_dict_round_trip_resumes_the_run():
     """the row-wise m / v / stamps, the step counter and the tower moments survive state_dict -> load_state_dict:
-    a trainer resumed from the checkpoint after 2 steps reproduces steps 3-4 of the uninterrupted run bit for bit."""
+    a trainer resumed from the checkpoint after 2 steps reproduces steps 3-4 of the uninterrupted run (to fp32 rounding: the fused
+    BatchNorm sums columns with atomics; a resume WITHOUT the state restarts Adam's moments and moves every weight by ~lr = 1e-2)."""
     from torch_rechub.b200 import config
     from torch_rechub.trainers import CTRTrainer
     torch.manual_seed(5)
@@ -253,11 +254,11 @@ def test_hybrid_optimizer_state_dict_round_trip_resumes_bit_identically():
         for xd, yd in dev[2:]:
             la = t_a._train_step(xd, yd)
             lb = t_b._train_step(xd, yd)
-            assert float(la) == float(lb)
+            assert abs(float(la) - float(lb)) <= 1e-5 * abs(float(la))
     finally:
         config.rowwise_optimizer = old
     for (n, p), q in zip(m_a.named_parameters(), m_b.parameters()):
-        assert torch.equal(p, q), n
+        assert torch.allclose(p, q, rtol=1e-4, atol=2e-5), n
     with pytest.raises(ValueError):
         t_b.optimizer.load_state_dict(torch.optim.Adam([torch.zeros(1, requires_grad=True)]).state_dict())
 
@@ -292,4 +293,4 @@ def test_dense_optimizer_sparse_clean_survives_reused_id_buffers():
     ref = w.grad.detach().clone()
     m.zero_grad(set_to_none=True)
     torch.nn.BCELoss()(m(xd), yd).backward()
-    assert torch.equal(w.grad, ref)  # after the full clean: exactly one step's gradient again
+    assert torch.allclose(w.grad, ref, rtol=1e-5, atol=1e-8)  # after the full clean: one step's gradient again (REDs of duplicate ids: rounding order)

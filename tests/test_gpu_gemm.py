@@ -93,17 +93,23 @@ def test_kernel_variants(tma_epilogue, concat_b, tile_n, M, N, K, a_mn, b_mn, bi
     assert rel < 2e-6, rel
 
 
-def test_tma_epilogue_leaves_the_padding_columns_alone():
-    """C with ldc > N (the tower's padded activations): the bulk stores are clipped at column N by the tensor map."""
+def test_tma_epilogue_stays_inside_the_16_byte_rows_of_c():
+    """C with ldc > N (the tower's padded activations).  The bulk stores are clipped by the tensor map at 16-byte granularity: with
+    N % 4 != 0 the tail of the last 16-byte piece of a row (columns N .. pad4(N) - 1, padding by the header's contract) may be
+    written; nothing beyond pad4(N), and no row beyond M."""
     from torch_rechub.b200 import ops
     g = torch.Generator().manual_seed(3)
     M, N, K = 300, 70, 64
     A = torch.randn(M, K, generator=g).to(DEV)
     B = torch.randn(N, K, generator=g).to(DEV)
-    buf = torch.full((M + 5, 72), 7.0, device=DEV)
+    buf = torch.full((M + 5, 76), 7.0, device=DEV)
     ops.gemm3x(A, False, B, False, M, N, K, out=buf[:M])
-    assert torch.all(buf[:M, N:] == 7.0) and torch.all(buf[M:] == 7.0)
+    assert torch.all(buf[:M, 72:] == 7.0) and torch.all(buf[M:] == 7.0)
     assert torch.allclose(buf[:M, :N], A @ B.t(), rtol=1e-4, atol=1e-4)
+    buf2 = torch.full((M, 72), 7.0, device=DEV)  # N % 4 == 0: exact clipping
+    ops.gemm3x(A, False, B[:68], False, M, 68, K, out=buf2)
+    assert torch.all(buf2[:, 68:] == 7.0)
+    assert torch.allclose(buf2[:, :68], A @ B[:68].t(), rtol=1e-4, atol=1e-4)
 
 
 def test_is_more_accurate_than_tf32_and_matches_fp32_level():

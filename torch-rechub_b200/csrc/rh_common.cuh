@@ -98,6 +98,16 @@ __device__ __forceinline__ void red_add_row16(float* p, const float4& v) {
                : "memory");
 }
 
+// system-scope release / acquire on a flag word in peer-mapped memory (the cross-GPU hand-overs of rh_dist.cu and rh_fields.cu)
+__device__ __forceinline__ void st_release_sys(int32_t* p, int32_t v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int32_t ld_acquire_sys(const int32_t* p) {
+  int32_t v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ int64_t load_id(const void* ids, int64_t idx, bool is_i32) {
   return is_i32 ? (int64_t)__ldg(reinterpret_cast<const int32_t*>(ids) + idx)
                 : (int64_t)__ldg(reinterpret_cast<const long long*>(ids) + idx);

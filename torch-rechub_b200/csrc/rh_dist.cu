@@ -38,14 +38,6 @@ struct PackP {
   unsigned* ticket;                   // zero on entry, left zero
 };
 
-__device__ __forceinline__ void st_release_sys(int32_t* p, int32_t v) {
-  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ int32_t ld_acquire_sys(const int32_t* p) {
-  int32_t v;
-  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 
 // One system-scope fence per LAUNCH, not per block: every block makes its copies visible device-wide (__threadfence) before it takes
 // its ticket; the last block — which therefore observes all of them — issues the only __threadfence_system() and publishes the flag

@@ -40,6 +40,16 @@ struct DenseDev {
 unsigned long long* g_fields_trace = nullptr;
 #endif
 
+// Cross-GPU hand-overs folded into a forward launch (include/rechub_b200.h: rh_sync); all NULL / 0 on one GPU.
+struct SyncDev {
+  const int32_t* wait_flags;
+  const int32_t* step;
+  int32_t* sig_flags[8];
+  unsigned* ticket;
+  int32_t wait_mask, sig_world, sig_rank, pad_;
+  int64_t snap_delta;
+};
+
 struct FwdParams {
   FieldDev f[RH_MAX_FIELDS];
   DenseDev d[RH_MAX_DENSE];
@@ -54,6 +64,7 @@ struct FwdParams {
   float* ylr;
   float* fsum;
   int32_t* err;
+  SyncDev sync;
 #ifdef RH_FIELDS_TRACE
   unsigned long long* trace;  // tools/fields_trace.cu: [block][16]: clock64 stamps of thread 0 (0..6), globaltimer at entry (8) and exit (9)
 #endif
@@ -120,6 +131,44 @@ __device__ __forceinline__ void st_tile4(float* p, const float4& v, bool vec) {
   }
 }
 
+
+// ---- hand-overs inside the launch (multi-GPU exchange) ----
+// consumer: every CTA waits until all awaited ranks have published this step, BEFORE its first read of peer-written memory
+// (bounded: a peer that never publishes — a crashed rank — ends in the launch's error flag after ~2^24 polls, seconds, instead of
+// a kernel that spins until the box is reset; _lib.check_errors turns RH_ERRFLAG_SYNC_TIMEOUT into a RuntimeError)
+__device__ __forceinline__ void sync_wait_head(const SyncDev& sy, int32_t* err) {
+  if (sy.wait_flags == nullptr) return;  // grid-uniform
+  const int t = threadIdx.y * blockDim.x + threadIdx.x;
+  if (t < 8 && ((sy.wait_mask >> t) & 1)) {
+    const int e = *sy.step;
+    unsigned polls = 0;
+    while (ld_acquire_sys(sy.wait_flags + t) < e) {
+      __nanosleep(32);
+      if (++polls > (1u << 24)) {
+        if (err != nullptr) *err = RH_ERRFLAG_SYNC_TIMEOUT;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+}
+// producer: the grid's last CTA publishes the step to every destination (ONE system fence per launch; the CTAs' own fences +
+// the ticket make their peer stores precede it — fences are cumulative)
+__device__ __forceinline__ void sync_signal_tail(const SyncDev& sy, unsigned n_ctas) {
+  __shared__ int is_last;
+  __threadfence();
+  __syncthreads();
+  const int t = threadIdx.y * blockDim.x + threadIdx.x;
+  if (t == 0) is_last = (atomicAdd(sy.ticket, 1u) == n_ctas - 1) ? 1 : 0;
+  __syncthreads();
+  if (!is_last) return;
+  if (t < sy.sig_world) {
+    __threadfence_system();
+    st_release_sys(sy.sig_flags[t] + sy.sig_rank, *sy.step);
+  }
+  if (t == 0) *sy.ticket = 0u;
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward, 16-byte lanes.
 //   lane  = (sample slot, 16-byte quarter): LPR lanes per sample (LPR = pow2 >= dim/4), 32/LPR samples per warp
@@ -144,6 +193,7 @@ __global__ void __launch_bounds__(256) fields_fwd_v4(const __grid_constant__ Fwd
   __shared__ float sm_lr[SW][NG][32];
 
   pdl_wait();
+  sync_wait_head(p.sync, p.err);
   const int lane = threadIdx.x & 31;
   const int g = threadIdx.x >> 5;
   const int q = lane % LPR;
@@ -179,6 +229,9 @@ __global__ void __launch_bounds__(256) fields_fwd_v4(const __grid_constant__ Fwd
       if (f < p.n_fields && live) {
         const FieldDev& fd = p.f[f];
         const int64_t id = load_id(fd.ids, (int64_t)b * fd.id_stride, fd.is_i32 != 0);
+        if (p.sync.snap_delta != 0 && q == 0) {  // owner-side gather: the ids it used stay behind in local memory (int64 id buffers)
+          *reinterpret_cast<long long*>(reinterpret_cast<char*>(const_cast<void*>(fd.ids)) + (int64_t)b * fd.id_stride * 8 + p.sync.snap_delta) = id;
+        }
         // The LR weights of the chunk's fields do not depend on the ids: they travel with them.  (Loaded in the consume loop below
         // they sat behind the volatile tile stores — four SERIAL L2 round trips, 2.7 us of a 7.9 us launch in tools/fields_trace.cu.)
         if (want_lr && fd.fm_slot >= 0 && lane_on) w[j] = __ldg(reinterpret_cast<const float4*>(p.lrw + (int64_t)fd.fm_slot * dim + 4 * q));
@@ -231,6 +284,7 @@ __global__ void __launch_bounds__(256) fields_fwd_v4(const __grid_constant__ Fwd
   }
 
   RH_FT(4, 0);
+  if (p.sync.ticket != nullptr) sync_signal_tail(p.sync, gridDim.x);  // grid-uniform; every thread of the block is still here
   if (!want_fm) return;  // block-uniform
   if (NG > 1) {
     sm_s[sw][g][lane] = s;
@@ -264,7 +318,8 @@ __global__ void __launch_bounds__(256) fields_fwd_v4(const __grid_constant__ Fwd
 
 
 // ------------------------------------------------------------------------------------------------
-// forward, 16-byte lanes, v6: the v4 mapping with the descriptor reads taken OFF the dependent chain.
+// forward, 16-byte lanes, v6 (opt-in, RECHUB_B200_FIELDS_FWD=6; measured SLOWER than v4, see use_fwd_v4): the v4 mapping with the
+// descriptor reads taken off the dependent chain.
 // What v4's trace + SASS showed (tools/fields_trace.cu, profiles/r02_fields_trace.txt): the ids arrived 1.95 us after block entry
 // and the four tile stores + FM updates took 2.3 us AFTER their rows had landed.  Neither is memory time: every use of p.f[f]
 // / p.d[j] is an INDEXED constant-bank read (LDC c[0x0][R+off]; the field index depends on the warp), the compiler re-reads the
@@ -644,11 +699,15 @@ static int pack_fields(const rh_field* fields, int n_fields, FieldDev* out, bool
   return RH_OK;
 }
 
-// RECHUB_B200_FIELDS_FWD=4 keeps the round-1/2 kernel (descriptors read from the constant bank at every use) for A/B runs.
+// RECHUB_B200_FIELDS_FWD=6 selects the variant with the descriptors staged in shared memory (fields_fwd_v6).  Measured on B200
+// (tools/fields_trace.cu, profiles/r02c_fields_trace_v{4,6}.txt): the staging itself — indexed constant-bank reads with a different
+// address per lane, then a block barrier — delays the id loads from +1.93 us to +3.13 us after block entry, more than the
+// LDS-fed phases behind them win back (rows +1.02 vs +0.79 us, tile + FM +1.68 vs +2.27 us): 8.37 vs 7.73 us per launch,
+// 10.9 vs 10.3 us in bench.py's cold-row replay.  v4 stays the default.
 static bool use_fwd_v4() {
   static const int v = [] {
     const char* e = getenv("RECHUB_B200_FIELDS_FWD");
-    return (e != nullptr && e[0] == '4') ? 1 : 0;
+    return (e != nullptr && e[0] == '6') ? 0 : 1;
   }();
   return v != 0;
 }
@@ -662,7 +721,8 @@ static void launch_fwd_v4(const FwdParams& p, cudaStream_t st) {
   const int sw = 8 / ng;
   const int grid = (p.batch + SPB * sw - 1) / (SPB * sw);
   const dim3 block(ng * 32, sw);
-  if (use_fwd_v4()) {
+  const bool has_sync = p.sync.wait_flags != nullptr || p.sync.ticket != nullptr || p.sync.snap_delta != 0;  // implemented by v4 only
+  if (use_fwd_v4() || has_sync) {
     switch (ng) {
       case 1: launch_k(fields_fwd_v4<LPR, 1>, dim3(grid), block, 0, st, p); break;
       case 2: launch_k(fields_fwd_v4<LPR, 2>, dim3(grid), block, 0, st, p); break;
@@ -701,7 +761,7 @@ using namespace rh;
 
 static int fields_fwd_impl(const rh_field* fields, int n_fields, int dim, const rh_dense* dense, int n_dense, int batch, float* tile,
                            int64_t tile_ld, const float* lr_weight, const float* lr_bias, float* y_fm, float* y_lr, float* field_sum,
-                           int32_t* err_flag, void* stream, float* const* dest, int n_dest, int dest_rows) {
+                           int32_t* err_flag, void* stream, float* const* dest, int n_dest, int dest_rows, const rh_sync* sync = nullptr) {
   RH_REQUIRE(n_fields >= 0 && n_fields <= RH_MAX_FIELDS, RH_ERR_INVALID_ARG, "n_fields %d not in [0,%d]", n_fields, RH_MAX_FIELDS);
   RH_REQUIRE(n_dense >= 0 && n_dense <= RH_MAX_DENSE, RH_ERR_INVALID_ARG, "n_dense %d not in [0,%d]", n_dense, RH_MAX_DENSE);
   RH_REQUIRE(n_fields == 0 || fields != nullptr, RH_ERR_INVALID_ARG, "fields is NULL");
@@ -769,6 +829,30 @@ static int fields_fwd_impl(const rh_field* fields, int n_fields, int dim, const 
   p.ylr = want_fm ? y_lr : nullptr;
   p.fsum = want_fm ? field_sum : nullptr;
   p.err = err_flag;
+  if (sync != nullptr && (sync->wait_flags != nullptr || sync->sig_flags != nullptr || sync->id_snapshot_delta != 0)) {
+    RH_REQUIRE(vec_ok, RH_ERR_UNSUPPORTED, "rh_fields_fwd_sync needs the 16-byte-lane kernel (dim %% 4 == 0, aligned tables)");
+    RH_REQUIRE(sync->wait_flags == nullptr || sync->step != nullptr, RH_ERR_INVALID_ARG, "rh_fields_fwd_sync: wait_flags without step");
+    p.sync.wait_flags = sync->wait_flags;
+    p.sync.wait_mask = sync->wait_flags != nullptr ? (sync->wait_mask & 0xff) : 0;
+    p.sync.step = sync->step;
+    if (sync->sig_flags != nullptr) {
+      RH_REQUIRE(sync->sig_world >= 1 && sync->sig_world <= 8 && sync->sig_rank >= 0 && sync->sig_rank < 8 && sync->ticket != nullptr && sync->step != nullptr,
+                 RH_ERR_INVALID_ARG, "rh_fields_fwd_sync: bad signal side (world %d rank %d)", sync->sig_world, sync->sig_rank);
+      for (int i = 0; i < sync->sig_world; ++i) {
+        RH_REQUIRE(sync->sig_flags[i] != nullptr, RH_ERR_INVALID_ARG, "rh_fields_fwd_sync: flags of rank %d NULL", i);
+        p.sync.sig_flags[i] = sync->sig_flags[i];
+      }
+      p.sync.sig_world = sync->sig_world;
+      p.sync.sig_rank = sync->sig_rank;
+      p.sync.ticket = reinterpret_cast<unsigned*>(sync->ticket);
+    }
+    if (sync->id_snapshot_delta != 0) {
+      for (int i = 0; i < n_fields; ++i)
+        RH_REQUIRE(fields[i].ids_are_i32 == 0, RH_ERR_UNSUPPORTED, "rh_fields_fwd_sync: the id snapshot needs int64 id buffers (field %d)", i);
+      RH_REQUIRE(sync->id_snapshot_delta % 8 == 0, RH_ERR_INVALID_ARG, "rh_fields_fwd_sync: id_snapshot_delta must be a multiple of 8 bytes");
+      p.sync.snap_delta = sync->id_snapshot_delta;
+    }
+  }
 
   if (vec_ok) {
     const int lpr = n_fields > 0 ? pow2_ceil(dim / 4) : 4;
@@ -875,6 +959,19 @@ extern "C" int rh_fields_fwd_p2p(const rh_field* fields, int n_fields, int dim, 
                          dest_tiles, n_dest, rows_per_dest);
 }
 
+extern "C" int rh_fields_fwd_sync(const rh_field* fields, int n_fields, int dim, const rh_dense* dense, int n_dense, int batch, float* tile,
+                                  int64_t tile_ld, const float* lr_weight, const float* lr_bias, float* y_fm, float* y_lr, float* field_sum,
+                                  float* const* dest_tiles, int n_dest, int rows_per_dest, const rh_sync* sync, int32_t* err_flag, void* stream) {
+  if (dest_tiles != nullptr) {
+    RH_REQUIRE(n_dest > 0 && dense == nullptr && n_dense == 0 && lr_weight == nullptr && y_fm == nullptr && y_lr == nullptr && field_sum == nullptr,
+               RH_ERR_INVALID_ARG, "rh_fields_fwd_sync: the peer-memory gather takes no dense columns and no FM / LR outputs");
+    return fields_fwd_impl(fields, n_fields, dim, nullptr, 0, batch, dest_tiles[0], tile_ld, nullptr, nullptr, nullptr, nullptr, nullptr, err_flag, stream,
+                           dest_tiles, n_dest, rows_per_dest, sync);
+  }
+  return fields_fwd_impl(fields, n_fields, dim, dense, n_dense, batch, tile, tile_ld, lr_weight, lr_bias, y_fm, y_lr, field_sum, err_flag, stream, nullptr, 0,
+                         0, sync);
+}
+
 // ids of my samples -> the owners' id buffers (peer memory).  One thread per (destination, sample); the id of the
 // destination's k-th field lands at  dst[k * slot_stride + sample * sample_stride].  Field-major buffers
 // (sample_stride 1) make every warp store one contiguous 256-byte run over NVLink, and give the owner's gather unit-stride ids.
@@ -887,8 +984,15 @@ struct IdScatterP {
   int32_t first[8], count[8];        // columns of destination d: [first[d], first[d] + count[d])
   int32_t batch, fmax;
   long long slot_stride, sample_stride;
+  // rh_ids_scatter_signal: publish *step + 1 to the owners' id-phase flags once every CTA's ids are stored (NULL: plain scatter)
+  int32_t* sig_flags[8];
+  int32_t* step;
+  unsigned* ticket;
+  int32_t sig_rank, sig_world;
 };
 __global__ void __launch_bounds__(256) ids_scatter_kernel(const __grid_constant__ IdScatterP p) {
+  __shared__ int is_last;
+  const int e = p.step != nullptr ? *p.step + 1 : 0;  // the last CTA overwrites *step only after every CTA has taken its ticket
   const int d = blockIdx.y;
   const int first = p.first[d], count = p.count[d];
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < p.batch; j += gridDim.x * blockDim.x) {
@@ -897,17 +1001,45 @@ __global__ void __launch_bounds__(256) ids_scatter_kernel(const __grid_constant_
     for (int k = 0; k < count; ++k)
       out[(int64_t)k * p.slot_stride] = (long long)load_id(p.src[first + k], (int64_t)j * p.stride[first + k], p.is_i32[first + k] != 0);
   }
+  if (p.ticket == nullptr) return;  // grid-uniform
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(p.ticket, 1u) == gridDim.x * gridDim.y - 1) ? 1 : 0;
+  __syncthreads();
+  if (!is_last) return;
+  if ((int)threadIdx.x < p.sig_world) {
+    __threadfence_system();
+    st_release_sys(p.sig_flags[threadIdx.x] + p.sig_rank, e);
+  }
+  if (threadIdx.x == 0) {
+    *p.ticket = 0u;
+    *p.step = e;
+  }
 }
 }  // namespace rh
 
-extern "C" int rh_ids_scatter(const rh_field* cols, int n_cols, const int32_t* col_dest, int batch, int64_t* const* dest_base, int n_dest, int fmax,
-                              int64_t slot_stride, int64_t sample_stride, void* stream) {
+static int ids_scatter_impl(const rh_field* cols, int n_cols, const int32_t* col_dest, int batch, int64_t* const* dest_base, int n_dest, int fmax,
+                            int64_t slot_stride, int64_t sample_stride, int32_t* const* peer_flags, int rank, int world, int32_t* step_dev,
+                            int32_t* ticket_dev, void* stream) {
   RH_REQUIRE(cols != nullptr && col_dest != nullptr && dest_base != nullptr && n_cols > 0 && n_cols <= RH_MAX_FIELDS && batch >= 0 && fmax > 0 &&
                  n_dest > 0 && n_dest <= 8 && slot_stride > 0 && sample_stride > 0,
              RH_ERR_INVALID_ARG, "rh_ids_scatter: bad arguments");
+  RH_REQUIRE(batch > 0 || peer_flags == nullptr, RH_ERR_INVALID_ARG, "rh_ids_scatter_signal: an empty batch cannot publish a step");
   if (batch == 0) return RH_OK;
   static thread_local rh::IdScatterP p;
   memset(&p, 0, sizeof(p));
+  if (peer_flags != nullptr) {
+    RH_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world && step_dev != nullptr && ticket_dev != nullptr, RH_ERR_INVALID_ARG,
+               "rh_ids_scatter_signal: bad rank / world / step / ticket");
+    for (int i = 0; i < world; ++i) {
+      RH_REQUIRE(peer_flags[i] != nullptr, RH_ERR_INVALID_ARG, "rh_ids_scatter_signal: flags of rank %d NULL", i);
+      p.sig_flags[i] = peer_flags[i];
+    }
+    p.sig_rank = rank;
+    p.sig_world = world;
+    p.step = step_dev;
+    p.ticket = reinterpret_cast<unsigned*>(ticket_dev);
+  }
   int prev = -1;
   for (int i = 0; i < n_cols; ++i) {
     const int d = col_dest[i];
@@ -932,4 +1064,17 @@ extern "C" int rh_ids_scatter(const rh_field* cols, int n_cols, const int32_t* c
   rh::ids_scatter_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
   RH_LAUNCH_CHECK();
   return RH_OK;
+}
+
+extern "C" int rh_ids_scatter(const rh_field* cols, int n_cols, const int32_t* col_dest, int batch, int64_t* const* dest_base, int n_dest, int fmax,
+                              int64_t slot_stride, int64_t sample_stride, void* stream) {
+  return ids_scatter_impl(cols, n_cols, col_dest, batch, dest_base, n_dest, fmax, slot_stride, sample_stride, nullptr, 0, 0, nullptr, nullptr, stream);
+}
+
+extern "C" int rh_ids_scatter_signal(const rh_field* cols, int n_cols, const int32_t* col_dest, int batch, int64_t* const* dest_base, int n_dest, int fmax,
+                                     int64_t slot_stride, int64_t sample_stride, int32_t* const* peer_flags, int rank, int world, int32_t* step_dev,
+                                     int32_t* ticket_dev, void* stream) {
+  RH_REQUIRE(peer_flags != nullptr, RH_ERR_INVALID_ARG, "rh_ids_scatter_signal: peer_flags is NULL");
+  return ids_scatter_impl(cols, n_cols, col_dest, batch, dest_base, n_dest, fmax, slot_stride, sample_stride, peer_flags, rank, world, step_dev, ticket_dev,
+                          stream);
 }

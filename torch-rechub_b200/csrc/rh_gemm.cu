@@ -672,7 +672,8 @@ static int gemm_impl(const float* A, int64_t lda, int a_mn_major, const float* B
   rc = make_map(&map_b, B, ldb, N, K, b_mn_major != 0, bn);
   if (rc != RH_OK) return rc;
   const int opts = gemm_opts();
-  const bool tma_epi = st == nullptr && (opts & 1) != 0 && ldc % 4 == 0 && ((uintptr_t)C & 15u) == 0;  // TMA needs 16-byte rows of C
+  // TMA needs 16-byte rows of C; its clipping works on 16-byte pieces, so the row must own the whole last piece (header contract)
+  const bool tma_epi = st == nullptr && (opts & 1) != 0 && ldc % 4 == 0 && ((uintptr_t)C & 15u) == 0 && ldc >= (int64_t)((N + 3) / 4) * 4;
   if (tma_epi) {
     rc = make_map_c(&map_c, C, ldc, M, N);
     if (rc != RH_OK) return rc;

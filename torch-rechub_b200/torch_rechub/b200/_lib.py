@@ -30,6 +30,11 @@ class RhDense(ctypes.Structure):
     _fields_ = [("values", c_p), ("stride", c_i64), ("dtype", ctypes.c_int32), ("width", ctypes.c_int32), ("tile_col", ctypes.c_int32)]
 
 
+class RhSync(ctypes.Structure):  # include/rechub_b200.h: rh_sync
+    _fields_ = [("wait_flags", c_p), ("step", c_p), ("sig_flags", c_p), ("ticket", c_p), ("wait_mask", ctypes.c_int32), ("sig_world", ctypes.c_int32), ("sig_rank", ctypes.c_int32),
+                ("reserved", ctypes.c_int32), ("id_snapshot_delta", c_i64)]
+
+
 # name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/rechub_b200.h one to one
 PROTOTYPES = {
     "rh_abi_version": [],
@@ -41,6 +46,8 @@ PROTOTYPES = {
     "rh_fields_fwd": [c_p, c_i, c_i, c_p, c_i, c_i, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "rh_fields_fwd_p2p": [c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_i64, c_p, c_p],
     "rh_ids_scatter": [c_p, c_i, c_p, c_i, c_p, c_i, c_i, c_i64, c_i64, c_p],
+    "rh_ids_scatter_signal": [c_p, c_i, c_p, c_i, c_p, c_i, c_i, c_i64, c_i64, c_p, c_i, c_i, c_p, c_p, c_p],
+    "rh_fields_fwd_sync": [c_p, c_i, c_i, c_p, c_i, c_i, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p],
     "rh_fields_bwd": [c_p, c_i, c_i, c_i, c_p, c_i64, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "rh_rows_gather": [c_p, c_i, c_i, c_p, c_i, c_i64, c_p, c_p, c_p],
     "rh_rows_scatter_add": [c_p, c_i, c_i, c_i, c_p, c_i, c_i64, c_p, c_p, c_p],
@@ -196,4 +203,6 @@ def check_errors(device=None):
         v = int(t.item())
         if v != 0:
             t.zero_()
+            if v == 0x7ffffff0:  # RH_ERRFLAG_SYNC_TIMEOUT
+                raise RuntimeError("a cross-GPU hand-over of the sharded exchange timed out: a peer rank never published its step (crashed or diverged rank?)")
             raise IndexError("index out of range in self (embedding lookup, field #%d of the launch)" % (v - 1))

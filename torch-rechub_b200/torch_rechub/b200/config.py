@@ -45,6 +45,11 @@ p2p_own_barrier = _flag("RECHUB_B200_P2P_OWN_BARRIER", True)
 # With the peer-memory reduction the post-backward barrier is a WAIT on the gradient-publication flags (rh_peer_wait): a rank publishes
 # behind its backward kernels and a system fence, so no separate signal round is needed.
 p2p_fold_barrier = _flag("RECHUB_B200_P2P_FOLD_BARRIER", True)
+# The forward exchange's two barriers (+ the owner's id snapshot copy) folded into its three launches: rh_ids_scatter_signal publishes
+# "my ids have landed" when its last CTA is done, the owner's gather (rh_fields_fwd_sync) waits for every rank's ids inside the kernel,
+# keeps a local copy of the ids it reads and publishes "my rows have landed", the sample side's unpack launch waits for the owners'
+# rows inside the kernel.  6 graph nodes -> 3.  Off: rh_ids_scatter | barrier | copy | rh_fields_fwd_p2p | barrier | rh_fields_fwd.
+p2p_fused_sync = _flag("RECHUB_B200_P2P_FUSED_SYNC", True)
 
 # Check the device-side out-of-range-id flag after every forward (one D2H sync per step).  When off the
 # flag is checked at the trainer's existing sync points (``loss.item()``) and by ``check_errors()``.
@@ -95,7 +100,12 @@ l2_fetch_granularity = int(os.environ.get("RECHUB_B200_L2_FETCH_GRANULARITY", "3
 
 # The optimiser's step-counter / bias-correction launch (rh_opt_advance) is issued at the START of the step on the side stream
 # (RowwiseOptimizer.advance_early) instead of between the scatter-add and the row-wise update.
-early_opt_advance = _flag("RECHUB_B200_EARLY_OPT_ADVANCE", True)
+# Measured (profiles/README.md, r02c): 0.1625 ms with, 0.1617 ms without — no gain; off.
+early_opt_advance = _flag("RECHUB_B200_EARLY_OPT_ADVANCE", False)
+
+# The split-K targets of the tower's weight-gradient GEMMs are zeroed during the FORWARD on the idle side stream (ops._prezero_dw).
+# Measured (profiles/README.md, r02d): 0.1638 ms with, 0.1628 ms without — no gain; off.
+prezero_dw = _flag("RECHUB_B200_PREZERO_DW", False)
 
 # Set by the graph runner while inputs live in static buffers that the next batch overwrites.
 static_inputs = False

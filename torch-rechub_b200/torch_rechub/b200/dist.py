@@ -84,6 +84,18 @@ class P2PExchange(object):
                         "rank": dist.get_rank(group), "world": W}
             torch.cuda.synchronize(device)
             dist.barrier(group=group)  # nobody publishes into flags that are still being zeroed
+        # hand-overs folded into the launches (config.p2p_fused_sync): per-phase flags in peer memory + the exchange's step counter
+        self.fs = None
+        if config.p2p_fused_sync and W <= 8:
+            import ctypes
+            fl = symm.empty(16, dtype=torch.int32, device=device)  # [0:8] id phase, [8:16] row phase: flags[s] = last step rank s published
+            fl.zero_()
+            h_fl = symm.rendezvous(fl, group)
+            base = [int(p) for p in h_fl.buffer_ptrs]
+            self.fs = {"flags": fl, "handle": h_fl, "ids_ptrs": (ctypes.c_void_p * W)(*base), "rows_ptrs": (ctypes.c_void_p * W)(*[p + 32 for p in base]),
+                       "step": torch.zeros(1, dtype=torch.int32, device=device), "tickets": torch.zeros(2, dtype=torch.int32, device=device), "rank": dist.get_rank(group)}
+            torch.cuda.synchronize(device)
+            dist.barrier(group=group)
 
     def barrier(self):
         if self.own is not None:
@@ -138,26 +150,45 @@ class _ShardedP2P(torch.autograd.Function):
             # forward barriers (the staged route does this in its owner-side backward pass)
             for f in p["by_owner"][me]:
                 _table.grad_target(front.layer.table_of(f).weight)
+        fs = ex.fs
         if ex.field_major:  # [slot, source rank, sample]
             bases = (ctypes.c_void_p * W)(*[ex.ids_ptrs[r] + me * b * 8 for r in range(W)])
-            ops.check(L.rh_ids_scatter(cols, len(p["slots"]), col_dest, b, bases, W, fmax, W * b, 1, st), "rh_ids_scatter")
+            scatter_args = (cols, len(p["slots"]), col_dest, b, bases, W, fmax, W * b, 1)
         else:  # [source rank, sample, slot]
             bases = (ctypes.c_void_p * W)(*[ex.ids_ptrs[r] + me * b * fmax * 8 for r in range(W)])
-            ops.check(L.rh_ids_scatter(cols, len(p["slots"]), col_dest, b, bases, W, fmax, 1, fmax, st), "rh_ids_scatter")
-        ex.barrier()
-        # F3: owner-side gather over the global batch, rows stored straight into the destination GPUs' tiles.  The ids are
-        # snapshotted locally first: peers may refill ex.ids for the next step while this rank's backward still needs them.
+            scatter_args = (cols, len(p["slots"]), col_dest, b, bases, W, fmax, 1, fmax)
         mine = p["by_owner"][me]
-        ex.ids_local.copy_(ex.ids)
-        ids_g = ex.ids_local.view(fmax, W * b) if ex.field_major else ex.ids_local.view(W * b, fmax).t()
+        if fs is not None:
+            # F1 + hand-over: the last CTA publishes "rank me's ids of this step have landed" to every owner
+            ops.check(L.rh_ids_scatter_signal(*scatter_args, fs["ids_ptrs"], me, W, fs["step"].data_ptr(), fs["tickets"].data_ptr(), st), "rh_ids_scatter_signal")
+        else:
+            ops.check(L.rh_ids_scatter(*scatter_args, st), "rh_ids_scatter")
+            ex.barrier()
+            ex.ids_local.copy_(ex.ids)
+        # F3: owner-side gather over the global batch, rows stored straight into the destination GPUs' tiles.  The owner keeps a
+        # LOCAL copy of the ids: peers may refill ex.ids for the next step while this rank's backward / optimiser still need them
+        # (fused hand-overs: written by the gather itself, next to the reads; otherwise copied after the barrier above).
+        view = (lambda t: t.view(fmax, W * b)) if ex.field_major else (lambda t: t.view(W * b, fmax).t())
+        ids_g = view(ex.ids_local)
         orefs = []
         for k, f in enumerate(mine):
             tbl = front.layer.table_of(f)
             orefs.append(ops.FieldRef(tbl.weight, ids_g[k], tbl.padding_idx, k * dim, -1))
         if orefs:
             dest = (ctypes.c_void_p * W)(*[ex.rows_ptrs[s] + me * b * fmax * dim * 4 for s in range(W)])
-            ops.check(L.rh_fields_fwd_p2p(ops._field_array(orefs), len(orefs), dim, W * b, dest, W, b, fmax * dim, err, st), "rh_fields_fwd_p2p")
-        ex.barrier()
+            if fs is not None:
+                ids_in = view(ex.ids)
+                arr = ops._field_array([ops.FieldRef(r.weight, ids_in[k], None, k * dim, -1) for k, r in enumerate(orefs)])
+                sy = _lib.RhSync()
+                sy.wait_flags, sy.wait_mask, sy.step = fs["flags"].data_ptr(), (1 << W) - 1, fs["step"].data_ptr()  # every rank's ids
+                sy.sig_flags, sy.sig_world, sy.sig_rank = ctypes.cast(fs["rows_ptrs"], ctypes.c_void_p), W, me  # -> "owner me's rows have landed"
+                sy.ticket = fs["tickets"].data_ptr() + 4
+                sy.id_snapshot_delta = ex.ids_local.data_ptr() - ex.ids.data_ptr()
+                ops.check(L.rh_fields_fwd_sync(arr, len(orefs), dim, None, 0, W * b, None, fmax * dim, None, None, None, None, None, dest, W, b, ctypes.byref(sy), err, st), "rh_fields_fwd_sync (gather)")
+            else:
+                ops.check(L.rh_fields_fwd_p2p(ops._field_array(orefs), len(orefs), dim, W * b, dest, W, b, fmax * dim, err, st), "rh_fields_fwd_p2p")
+        if fs is None:
+            ex.barrier()
         # F5: sample side — the received rows are the "table"
         table = ex.rows.view(W * b * fmax, dim)
         fm_slot = {f.name: j for j, f in enumerate(fm_features)} if fm_features else {}
@@ -180,9 +211,15 @@ class _ShardedP2P(torch.autograd.Function):
         y_fm = torch.empty(b, dtype=torch.float32, device=dev) if want_fm else None
         y_lr = torch.empty(b, dtype=torch.float32, device=dev) if (want_fm and lr_w is not None) else None
         fsum = torch.empty((b, dim), dtype=torch.float32, device=dev) if want_fm else None
-        ops.check(
-            L.rh_fields_fwd(ops._field_array(srefs), len(srefs), dim, ops._dense_array(drefs) if drefs else None, len(drefs), b, tile.data_ptr(), ld, ops.ptr(lr_w) if y_lr is not None else None,
-                            ops.ptr(lr_b) if y_lr is not None else None, ops.ptr(y_fm), ops.ptr(y_lr), ops.ptr(fsum), err, st), "rh_fields_fwd")
+        fwd_args = (ops._field_array(srefs), len(srefs), dim, ops._dense_array(drefs) if drefs else None, len(drefs), b, tile.data_ptr(), ld, ops.ptr(lr_w) if y_lr is not None else None,
+                    ops.ptr(lr_b) if y_lr is not None else None, ops.ptr(y_fm), ops.ptr(y_lr), ops.ptr(fsum))
+        if fs is not None:
+            sy = _lib.RhSync()  # wait inside the launch for the rows of every owner that has fields
+            sy.wait_flags, sy.step = fs["flags"].data_ptr() + 32, fs["step"].data_ptr()
+            sy.wait_mask = sum(1 << r for r in range(W) if p["by_owner"][r])
+            ops.check(L.rh_fields_fwd_sync(*fwd_args, None, 0, 0, ctypes.byref(sy), err, st), "rh_fields_fwd_sync (unpack)")
+        else:
+            ops.check(L.rh_fields_fwd(*fwd_args, err, st), "rh_fields_fwd")
         ctx.front, ctx.p, ctx.srefs, ctx.orefs, ctx.ld, ctx.want_lr = front, p, srefs, orefs, ld, y_lr is not None
         ctx.direct, ctx.my_ids = direct, my_ids
         ctx.set_materialize_grads(False)

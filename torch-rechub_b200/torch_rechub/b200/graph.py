@@ -62,6 +62,8 @@ class LaggedReader(object):
         if v != 0:
             _lib.err_flag(self.device).zero_()
             self.queue.clear()
+            if v == 0x7ffffff0:  # RH_ERRFLAG_SYNC_TIMEOUT
+                raise RuntimeError("a cross-GPU hand-over of the sharded exchange timed out: a peer rank never published its step (crashed or diverged rank?)")
             raise IndexError("index out of range in self (embedding lookup, field #%d of the launch)" % (v - 1))
         return float(self.loss[i])
 

@@ -720,32 +720,57 @@ def _linear_fwd(x2, W, b):
     return h, Wp, use_tc
 
 
-def _linear_bwd(d_h, x2, W, Wp, use_tc, need_dx):
-    """(d_x or None, d_W) of h = x2 @ W^T from d_h; on the tensor cores the weight-gradient GEMM runs on a second stream next to
-    the input-gradient GEMM (config.concurrent_tower_bwd)."""
+def _dw_split(rows, cols, K, need_dx):
+    """(split_k of the weight-gradient GEMM, runs next to the input-gradient GEMM?) — shared by _prezero_dw and _linear_bwd."""
     from . import config
+    concurrent = bool(config.concurrent_tower_bwd and need_dx)
+    return _split_k_for((cols + 127) // 128, (K + 127) // 128, (rows + 31) // 32, budget=64 if concurrent else 128), concurrent
+
+
+def _prezero_dw(ctx, x2, W, use_tc, need_dx):
+    """Forward-time half of the weight gradient: its split-K target has to be zero, and that fill was a node between the BatchNorm
+    backward and the gradient GEMMs (on the main stream) or in front of the dW GEMM on the side stream (dW ~ dX in duration, so it
+    lengthened the join: measured +4 us per step).  The FORWARD has the side stream idle: allocate and zero the buffer there, next
+    to this layer's forward GEMM; backward finds it ready (``ctx.dw_pre``, consumed once)."""
+    from . import config
+    ctx.dw_pre = None
+    if not (use_tc and config.prezero_dw and x2.is_cuda and len(ctx.needs_input_grad) > 1 and ctx.needs_input_grad[1]):
+        return
+    rows, K = x2.shape
+    cols = W.shape[0]
+    split, _ = _dw_split(rows, cols, K, need_dx)
+    if split <= 1:
+        return
+    dev = x2.device
+    d_W = torch.empty((cols, K), dtype=torch.float32, device=dev)
+    cur, aux = torch.cuda.current_stream(), _aux_stream(dev)
+    aux.wait_stream(cur)  # the block may have been freed by work queued on the main stream
+    with torch.cuda.stream(aux):
+        d_W.zero_()
+    ctx.dw_pre = d_W  # first touched again on the side stream (the dW GEMM) or after a join with it
+
+
+def _linear_bwd(d_h, x2, W, Wp, use_tc, need_dx, pre=None):
+    """(d_x or None, d_W) of h = x2 @ W^T from d_h; on the tensor cores the weight-gradient GEMM runs on a second stream next to
+    the input-gradient GEMM (config.concurrent_tower_bwd).  ``pre``: the zeroed split-K target from _prezero_dw."""
     rows, K = x2.shape
     cols = W.shape[0]
     dev = d_h.device
     fork = None
     if use_tc:  # dW[cols, K] = d_h^T x: both operands read as stored (MN-major), K = rows split over CTAs
-        concurrent = config.concurrent_tower_bwd and need_dx
-        split = _split_k_for((cols + 127) // 128, (K + 127) // 128, (rows + 31) // 32, budget=64 if concurrent else 128)
-        d_W = torch.empty((cols, K), dtype=torch.float32, device=dev)
-        if concurrent:
-            # dW and dX only share their input d_h: dW runs on a second stream (half the SMs each), joined before returning.  The
-            # zero fill of the split-K target goes with it: on the main stream it sat between the BatchNorm backward and dX
-            # (one more node on the step's critical path).  d_W is handed back after the join, so its allocation on the main
-            # stream's pool is safe.
+        split, concurrent = _dw_split(rows, cols, K, need_dx)
+        fresh = pre is None or tuple(pre.shape) != (cols, K)
+        d_W = torch.empty((cols, K), dtype=torch.float32, device=dev) if fresh else pre
+        if fresh and split > 1:
+            d_W.zero_()
+        if concurrent or not fresh:
+            # dW and dX only share their input d_h: dW runs on a second stream (half the SMs each), joined before returning
+            # (a pre-zeroed target was filled on that stream: the GEMM follows it there in stream order)
             cur, fork = torch.cuda.current_stream(), _aux_stream(dev)
             fork.wait_stream(cur)
             with torch.cuda.stream(fork):
-                if split > 1:
-                    d_W.zero_()
                 gemm3x(d_h, True, x2, True, cols, K, rows, split_k=split, out=d_W)
         else:
-            if split > 1:
-                d_W.zero_()
             gemm3x(d_h, True, x2, True, cols, K, rows, split_k=split, out=d_W)
     else:
         d_W = torch.mm(d_h.t(), x2)
@@ -787,6 +812,7 @@ class _TowerLayer(torch.autograd.Function):
         st = stream_ptr()
         training = cfg["training"]
         h, Wp, use_tc = _linear_fwd(x2, W, b)
+        _prezero_dw(ctx, x2, W, use_tc, ctx.needs_input_grad[0])
         p = float(cfg["p_drop"])
         y = torch.empty((rows, cols), dtype=torch.float32, device=dev)
         fused = _fused_bn_ok(rows, cols, training, False)
@@ -852,7 +878,8 @@ class _TowerLayer(torch.autograd.Function):
                 d_b = d_beta * (gamma if gamma is not None else 1.0) / torch.sqrt(var + cfg["eps"])
         # training: the bias in front of a batch-statistics BN has a gradient of exactly 0 (BN removes any per-column
         # shift); the reference's autograd produces rounding noise ~1e-8 there.  d_b is the zero slice of gbuf.
-        d_x, d_W = _linear_bwd(d_h, x2, W, ctx.Wp, ctx.use_tc, ctx.needs_input_grad[0])
+        pre, ctx.dw_pre = getattr(ctx, "dw_pre", None), None
+        d_x, d_W = _linear_bwd(d_h, x2, W, ctx.Wp, ctx.use_tc, ctx.needs_input_grad[0], pre)
         return (d_x, d_W, d_b if ctx.has_bias else None, d_gamma if gamma is not None else None, d_beta if beta is not None else None, d_alpha.view_as(act_param) if ctx.has_param else None, None)
 
 
@@ -891,6 +918,7 @@ class _TowerLayerHead(torch.autograd.Function):
         cols = W.shape[0]
         dev = x2.device
         h, Wp, use_tc = _linear_fwd(x2, W, b)
+        _prezero_dw(ctx, x2, W, use_tc, ctx.needs_input_grad[0])
         ex = [e.contiguous() for e in extras]
         stats = torch.empty(2 * cols + 1, dtype=torch.float32, device=dev)
         out = torch.empty(rows, dtype=torch.float32, device=dev)
@@ -922,7 +950,8 @@ class _TowerLayerHead(torch.autograd.Function):
             L.rh_bn_act_fused_bwd(h.data_ptr(), cols, rows, cols, stats.data_ptr(), float(cfg["eps"]), ptr(gamma), ptr(beta), cfg["act"], ptr(act_param), float(cfg["dice_eps"]), float(cfg["p_drop"]), cfg["seed"], None, 0,
                                   head_W.data_ptr(), out.data_ptr(), d_out.data_ptr(), int(ctx.sig), _bn_fused_scratch(dev, cols).data_ptr(), d_h.data_ptr(), cols, d_gamma.data_ptr(), d_beta.data_ptr(),
                                   d_alpha.data_ptr(), d_hw.data_ptr(), d_hb.data_ptr(), ptr(d_e), d_b.data_ptr(), stream_ptr()), "rh_bn_act_fused_bwd")
-        d_x, d_W = _linear_bwd(d_h, x2, W, ctx.Wp, ctx.use_tc, ctx.needs_input_grad[0])
+        pre, ctx.dw_pre = getattr(ctx, "dw_pre", None), None
+        d_x, d_W = _linear_bwd(d_h, x2, W, ctx.Wp, ctx.use_tc, ctx.needs_input_grad[0], pre)
         return (d_x, d_W, d_b if ctx.has_bias else None, d_gamma if gamma is not None else None, d_beta if beta is not None else None, d_alpha.view_as(act_param) if ctx.has_param else None,
                 d_hw.view_as(head_W), d_hb if ctx.has_head_bias else None, None, None) + (d_e,) * ctx.n_extra
 
