@@ -669,13 +669,14 @@ def run_b200_arm(args):
         traffic_src = None
         if tfs:
             try:
-                traffic = json.load(open(tfs[-1])).get("dram_bytes_per_launch")
-                traffic_src = "profiles/" + os.path.basename(tfs[-1])
+                tj = json.load(open(tfs[-1]))
+                traffic = tj.get("dram_bytes_per_launch")
+                traffic_src = "profiles/" + os.path.basename(tfs[-1]) + ((": " + tj["note"]) if tj.get("note") else "")
             except Exception:
                 traffic = None
         roof = {"bound": "hbm", "kernel": "rh::fields_fwd_v4<4,8> (fused 26-field gather + FM + LR + tile, the north_star kernel)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": algo, "avg_us": avg_ms * 1e3, "median_us": med_ms * 1e3, "peak_source": peak_src,
-                "note": "latency floor, not bandwidth: 106 k random 64-B rows cost 8.8 us at any footprint (profiles/r01_microbench_gather.csv); the same kernel reaches 3.16 TB/s at B=262144 = the random-gather ceiling of this part (profiles/r01_sweep_fields_fwd.csv)"}
+                "note": "latency-bound at this batch, not bandwidth-bound: ids arrive 1.9 us after block entry, rows at 2.7 us, the tile is stored at 5.0 us (profiles/r02_fields_trace.txt); a bare gather + store of the same 106 k rows costs 4.9 us per launch of which 2.3 us is an empty launch (profiles/r02b_microbench_gather.csv); the same kernel moves 2.5 TB/s at B=262144 (profiles/r02_sweep_fields_fwd.csv)"}
         gflops, gus = time_tower_gemms(device)
         try:
             tpeak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
@@ -683,7 +684,7 @@ def run_b200_arm(args):
             tpeak = 1590.0
         gemm_roof = {"bound": "tensor", "kernel": "rh::gemm_tf32x3_kernel x6 (tower fwd/dX/dW; largest share of the step)", "achieved": gflops / gus / 1e6, "peak": tpeak, "unit": "TFLOP/s",
                      "frac": gflops / gus / 1e6 / tpeak, "us_per_step": gus, "fp32_flops_per_step": gflops,
-                     "note": "fp32-accurate 3xTF32: 3 tensor-core MMAs per fp32 product and TF32 peak is half the bf16 peak, so 1/6 of the bf16 peak is the ceiling of this scheme; ncu tensor-pipe 10-29 % (profiles/r01b_ncu_full_summary.json)"}
+                     "note": "fp32-accurate 3xTF32: 3 tensor-core MMAs per fp32 product and TF32 peak is half the bf16 peak, so 1/6 of the bf16 peak is the ceiling of this scheme; ncu tensor-pipe 12-29 % (profiles/r02_ncu_full_summary.json); per-CTA pipeline stamps in profiles/r02c_gemm_trace.txt"}
 
     # ---- warm per-kernel durations of the step that was just timed (CUPTI through torch.profiler; rank 0's view) ----------------
     ktimes = None

@@ -202,6 +202,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   uint64_t* tmem_full = bars + 3 * kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 1);
 
+  pdl_trigger();  // the successor may be scheduled as soon as every CTA of this grid is running (its pdl_wait still waits for our completion)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bn = STATS ? kBN : p.bn;
   const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * bn;
