@@ -69,10 +69,12 @@ int         rh_abi_version(void);
 const char* rh_last_error(void);
 /* Number of kernels this library has launched so far in this process (bench.py's gpu_launches). */
 unsigned long long rh_launch_count(void);
-/* Programmatic dependent launch for the hot-path kernels (GEMM, fused gather / scatter, fused BatchNorm, optimiser updates): with
- * on != 0 they are launched so that their scheduling and memory-free prologue overlap the drain of the preceding kernel in the stream
- * (each waits with griddepcontrol.wait before its first global access).  on < 0 only queries.  Returns the previous setting. */
-int rh_set_pdl(int on);
+/* Programmatic dependent launch for the hot-path kernels.  `mask` selects the kernel families that are LAUNCHED with the attribute
+ * (their CTAs may be scheduled as soon as every CTA of the preceding kernel in the stream has issued its trigger, run their
+ * memory-free prologue and block in griddepcontrol.wait until that kernel has completed and flushed):
+ *   1 GEMM   2 fused BatchNorm   4 fused gather / scatter   8 optimiser updates   16 loss   32 batch copy   64 multi-GPU hand-overs
+ * Every hot-path kernel issues the trigger at its top whatever the mask.  mask < 0 only queries.  Returns the previous mask. */
+int rh_set_pdl(int mask);
 /* Preferred shared-memory carveout (0..100 %, -1 = the driver's choice) applied to every kernel of the library at its next first launch;
  * returns the previous setting.  An experiment switch (does a uniform carveout avoid L1 / shared-memory reconfigurations between the
  * 198 KB GEMM CTAs and their neighbours?). */

@@ -4,6 +4,7 @@
 #include <mutex>
 #include <unordered_set>
 
+#define RH_PDL_FAMILY 32  /* rh_set_pdl mask bit of this file's kernels */
 #include "rh_common.cuh"
 
 namespace rh {
@@ -43,7 +44,7 @@ extern "C" int rh_set_smem_carveout(int percent) {
 }
 extern "C" int rh_set_pdl(int on) {
   const int old = rh::g_pdl;
-  if (on >= 0) rh::g_pdl = on != 0;
+  if (on >= 0) rh::g_pdl = on;  // a mask of kernel families (include/rechub_b200.h); 1 is NOT "all": use 0xff
   return old;
 }
 

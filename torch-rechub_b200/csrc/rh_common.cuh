@@ -29,6 +29,9 @@ void note_kernel(const void* fn);      // rh_api.cu
 // in the stream drains; it calls pdl_wait() (griddepcontrol.wait) before its first global access, which returns once the predecessor
 // has completed and flushed — so only launch latency and the memory-free prologue overlap.  Captured by CUDA graphs as a
 // programmatic edge.  Without the attribute pdl_wait() is a no-op.
+#ifndef RH_PDL_FAMILY
+#define RH_PDL_FAMILY 128
+#endif
 template <typename... KArgs, typename... Args>
 static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -40,7 +43,7 @@ static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = g_pdl ? 1 : 0;
+  cfg.numAttrs = (g_pdl & RH_PDL_FAMILY) ? 1 : 0;
   if (g_carveout >= 0) note_kernel(reinterpret_cast<const void*>(kernel));
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }

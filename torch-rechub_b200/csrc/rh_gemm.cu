@@ -27,6 +27,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#define RH_PDL_FAMILY 1  /* rh_set_pdl mask bit of this file's kernels */
 #include "rh_common.cuh"
 
 namespace rh {

@@ -11,6 +11,7 @@
 // Mapping: one warp owns one row; lane owns VEC consecutive columns per step (VEC = 4: 16-byte
 // accesses), KMAX steps cover the row, so Dice's per-row statistics are two warp reductions and the
 // per-column constants are hoisted into registers once per warp.
+#define RH_PDL_FAMILY 8  /* rh_set_pdl mask bit of this file's kernels */
 #include "rh_bn_common.cuh"
 
 namespace rh {

@@ -135,7 +135,7 @@ def lib():
             if handle.rh_abi_version() != 1:
                 raise EngineMissing("librechub_b200.so ABI version %d != 1" % handle.rh_abi_version())
             from . import config
-            handle.rh_set_pdl(int(bool(config.pdl)))
+            handle.rh_set_pdl(int(config.pdl))
             handle.rh_gemm_tile_n(int(config.gemm_tile_n))
             handle.rh_set_smem_carveout(int(config.smem_carveout))
             _lib = handle

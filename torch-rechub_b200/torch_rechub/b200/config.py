@@ -92,7 +92,7 @@ fused_bn_head = _flag("RECHUB_B200_FUSED_BN_HEAD", True)
 
 # Programmatic dependent launch of the hot-path kernels (rh_set_pdl): a kernel's scheduling and memory-free prologue overlap the drain
 # of its predecessor; captured as programmatic edges by CUDA graphs.  Off until measured.
-pdl = _flag("RECHUB_B200_PDL", False)
+pdl = int(os.environ.get("RECHUB_B200_PDL", "0"), 0)  # mask of kernel families launched early (rh_set_pdl); 0xff = all
 
 # cudaLimitMaxL2FetchGranularity the engine sets on every device it touches (bytes; 0 = leave the process default).  Random 64-byte
 # table rows are the dominant DRAM access: measured DRAM reads per 106 k-row gather: 14.4 MB at 128, 7.7 MB (= algorithmic) at 64 / 32.
