@@ -203,3 +203,35 @@ def test_packed_loader_int32_ids_feed_the_same_model_outputs():
         PackedLoader({"C0": np.array([2**31])}, np.array([0]), batch_size=1, id_names=["C0"], num_names=[], id_dtype=torch.int32)
     with pytest.raises(ValueError):
         PackedLoader(x, y, batch_size=n, id_dtype=torch.int16)
+
+
+_EXAMPLE_RUNNER = """import random, runpy, sys
+import numpy as np
+random.seed(0); np.random.seed(0)  # utils/data.py:206-241 shuffles and draws negatives from the unseeded `random` module
+script = sys.argv[1]
+sys.argv = [script] + sys.argv[2:]
+runpy.run_path(script, run_name="__main__")
+"""
+
+
+@pytest.mark.skipif(not live.live_reference_available() or not os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "torch_rechub")),
+                    reason="the reference's examples and its installed copy (oracle/_ref) only exist in the build container")
+@pytest.mark.parametrize("script,args", [("run_criteo.py", ["--model_name", "deepfm"]), ("run_criteo.py", ["--model_name", "dcn_v2"]), ("run_amazon_electronics.py", [])])
+def test_reference_quickstart_examples_run_unchanged_and_reproduce_the_reference(tmp_path, script, args):
+    """BASELINE configs[0]: the reference's own example scripts (examples/ranking/run_criteo.py on the shipped Criteo sample — DeepFM,
+    DCN-v2 — and run_amazon_electronics.py — DIN), byte for byte, on CPU: once against THIS package, once against the unmodified
+    reference installed under oracle/_ref.  Same seeds -> the same validation / test AUC lines, digit for digit."""
+    import shutil
+    ex = os.path.join(live.REFERENCE_ROOT, "examples", "ranking")
+    shutil.copy(os.path.join(ex, script), tmp_path / script)
+    sub = "criteo" if script == "run_criteo.py" else "amazon-electronics"
+    shutil.copytree(os.path.join(ex, "data", sub), tmp_path / "data" / sub)
+    (tmp_path / "runner.py").write_text(_EXAMPLE_RUNNER)
+    lines = {}
+    for name, path in (("package", PKG), ("reference", os.path.join(ROOT, "oracle", "_ref"))):
+        env = dict(os.environ, PYTHONPATH=path)
+        res = subprocess.run([sys.executable, "runner.py", script, "--epoch", "2", "--device", "cpu"] + args, env=env, cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0, (name, res.stdout[-2000:] + res.stderr[-2000:])
+        lines[name] = [ln.strip() for ln in res.stdout.splitlines() if "auc" in ln]
+        assert any(ln.startswith("test auc:") for ln in lines[name]), (name, res.stdout[-1000:])
+    assert lines["package"] == lines["reference"], lines
