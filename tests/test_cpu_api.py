@@ -235,3 +235,37 @@ def test_reference_quickstart_examples_run_unchanged_and_reproduce_the_reference
         lines[name] = [ln.strip() for ln in res.stdout.splitlines() if "auc" in ln]
         assert any(ln.startswith("test auc:") for ln in lines[name]), (name, res.stdout[-1000:])
     assert lines["package"] == lines["reference"], lines
+
+
+def test_ctypes_structures_match_the_header_layout(tmp_path):
+    """The C ABI's structs (rh_field, rh_dense, rh_sync) as gcc lays them out from include/rechub_b200.h against the ctypes mirrors in
+    torch_rechub.b200._lib: same field names in the same order, same offsets, same sizes (no compute, no GPU)."""
+    import ctypes
+    from torch_rechub.b200 import _lib
+    header = open(os.path.join(ROOT, "include", "rechub_b200.h")).read()
+    pairs = {"rh_field": _lib.RhField, "rh_dense": _lib.RhDense, "rh_sync": _lib.RhSync}
+    prog = ["#include <stdio.h>", "#include <stddef.h>", '#include "rechub_b200.h"', "int main(void) {"]
+    names = {}
+    for cname in pairs:
+        m = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), header, flags=re.S)
+        assert m, cname
+        body = re.sub(r"/\*.*?\*/", "", m.group(1), flags=re.S)
+        fields = [re.search(r"(\w+)\s*$", decl.strip()).group(1) for decl in body.split(";") if decl.strip()]
+        names[cname] = fields
+        prog.append('  printf("%s %%zu", sizeof(%s));' % (cname, cname))
+        for f in fields:
+            prog.append('  printf(" %%zu", offsetof(%s, %s));' % (cname, f))
+        prog.append('  printf("\\n");')
+    prog += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(prog))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    for line in out:
+        parts = line.split()
+        cname, size, offs = parts[0], int(parts[1]), [int(v) for v in parts[2:]]
+        st = pairs[cname]
+        assert [f[0] for f in st._fields_] == names[cname], (cname, [f[0] for f in st._fields_], names[cname])
+        assert ctypes.sizeof(st) == size, (cname, ctypes.sizeof(st), size)
+        assert [getattr(st, f).offset for f in names[cname]] == offs, cname
