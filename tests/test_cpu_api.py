@@ -269,3 +269,31 @@ def test_ctypes_structures_match_the_header_layout(tmp_path):
         assert [f[0] for f in st._fields_] == names[cname], (cname, [f[0] for f in st._fields_], names[cname])
         assert ctypes.sizeof(st) == size, (cname, ctypes.sizeof(st), size)
         assert [getattr(st, f).offset for f in names[cname]] == offs, cname
+
+
+def test_packed_loader_shuffled_batches_are_contiguous_views_of_chunk_buffers():
+    """the shuffled path no longer fancy-indexes into fresh pageable memory.  Every shuffled batch is a contiguous view
+    of one of two chunk buffers (pinned on a CUDA box) and carries exactly the rows `randperm` assigned to it — across chunk
+    boundaries, a ragged last batch, drop_last and a second epoch that reuses the buffers."""
+    from torch_rechub.b200.data import PackedLoader
+    n, bs = 1000, 64
+    x = {"a": np.arange(n), "b": np.arange(n) * 2, "f": np.arange(n).astype(np.float32) / 7, "s": np.arange(n * 3).reshape(n, 3)}
+    y = np.arange(n) % 2
+    for drop in (False, True):
+        loader = PackedLoader(x, y, batch_size=bs, shuffle=True, drop_last=drop)
+        loader._CHUNK_BATCHES = 3  # several chunk refills per epoch
+        for epoch in range(2):
+            torch.manual_seed(5 + epoch)
+            order = torch.randperm(n)
+            torch.manual_seed(5 + epoch)
+            rows, ptrs = 0, set()
+            for bi, (xb, yb) in enumerate(loader):
+                idx = order[bi * bs:min((bi + 1) * bs, n)]
+                assert torch.equal(xb["a"], torch.from_numpy(x["a"])[idx]) and torch.equal(xb["b"], torch.from_numpy(x["b"])[idx])
+                assert torch.allclose(xb["f"], torch.from_numpy(x["f"])[idx]) and torch.equal(xb["s"], torch.from_numpy(x["s"])[idx])
+                assert torch.equal(yb, torch.from_numpy(y).float()[idx])
+                assert xb.ids.is_contiguous() and xb.nums.is_contiguous() and xb.seqs.is_contiguous()
+                ptrs.add(xb.ids.untyped_storage().data_ptr())
+                rows += len(idx)
+            assert rows == (n // bs * bs if drop else n)
+            assert len(ptrs) <= 2  # two chunk buffers, no per-batch allocation

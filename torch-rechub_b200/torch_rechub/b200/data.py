@@ -72,13 +72,40 @@ class PackedLoader(object):
     def __len__(self):
         return self.n // self.batch_size if self.drop_last else (self.n + self.batch_size - 1) // self.batch_size
 
+    _CHUNK_BATCHES = 64  # shuffled batches gathered into one pinned chunk buffer at a time (two buffers, used alternately)
+
     def __iter__(self):
-        order = torch.randperm(self.n) if self.shuffle else None
-        for b in range(len(self)):
-            lo, hi = b * self.batch_size, min((b + 1) * self.batch_size, self.n)
-            if order is None:
-                sl = lambda t: None if t is None else t[lo:hi]
-            else:
-                idx = order[lo:hi]
-                sl = lambda t: None if t is None else t[idx]
-            yield PackedColumns(self.id_names, sl(self.ids), self.num_names, sl(self.nums), self.seq_names, sl(self.seqs)), sl(self.y)
+        mk = lambda sl: (PackedColumns(self.id_names, sl(self.ids), self.num_names, sl(self.nums), self.seq_names, sl(self.seqs)), sl(self.y))
+        if not self.shuffle:
+            for b in range(len(self)):
+                lo, hi = b * self.batch_size, min((b + 1) * self.batch_size, self.n)
+                yield mk(lambda t: None if t is None else t[lo:hi])
+            return
+        # Shuffled epochs.  Fancy-indexing a pinned array (`t[idx]`) lands in fresh PAGEABLE memory, and the trainer's non-blocking H2D
+        # copy of it degrades to a staged, synchronous one.  The permuted rows are therefore gathered chunk-wise (64 batches) into one
+        # of two PINNED chunk buffers and the batches are contiguous views of it — the same property the unshuffled path has.  A
+        # buffer is refilled 64 batches after its last batch was handed out; copies out of it are long queued by then, and a device
+        # synchronisation before the refill (once per 64 steps) makes sure they have completed whatever stream they run on.
+        order = torch.randperm(self.n)
+        nb, bs, R = len(self), self.batch_size, self._CHUNK_BATCHES
+        srcs = [self.ids, self.nums, self.seqs, self.y]
+        if getattr(self, "_chunks", None) is None:
+            pinned = bool(self.y.is_pinned()) if hasattr(self.y, "is_pinned") else False
+            rows = min(R * bs, self.n)
+            self._chunks = [[None if t is None else torch.empty((rows,) + tuple(t.shape[1:]), dtype=t.dtype, pin_memory=pinned) for t in srcs] for _ in range(2)]
+            self._chunk_used = [False, False]
+        for c, b0 in enumerate(range(0, nb, R)):
+            which = c & 1
+            bufs = self._chunks[which]
+            if self._chunk_used[which] and torch.cuda.is_available():
+                torch.cuda.synchronize()  # H2D copies out of this buffer (handed out >= 64 batches ago) are done
+            self._chunk_used[which] = True
+            lo_c, hi_c = b0 * bs, min((b0 + R) * bs, self.n if not self.drop_last else nb * bs)
+            idx = order[lo_c:hi_c]
+            for t, buf in zip(srcs, bufs):
+                if t is not None:
+                    torch.index_select(t, 0, idx, out=buf[:idx.numel()])
+            for b in range(b0, min(b0 + R, nb)):
+                lo, hi = b * bs - lo_c, min((b + 1) * bs, hi_c) - lo_c
+                ids_b, nums_b, seqs_b, y_b = (None if buf is None else buf[lo:hi] for buf in bufs)
+                yield PackedColumns(self.id_names, ids_b, self.num_names, nums_b, self.seq_names, seqs_b), y_b
