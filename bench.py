@@ -44,6 +44,20 @@ def peaks():
         return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
+
+def repeat_regions(timed_region, cover_ms=60.0, lo=3, hi=15):
+    """Run ``timed_region(r) -> (ms, result)`` for r = 0, 1, ...: once if the first region already covers ``cover_ms``, otherwise
+    ceil(cover_ms / first) times clamped to [lo, hi].  The count only depends on the FIRST region's time — which the caller all-reduces
+    over the ranks — so every rank runs the same number of regions.  Returns (list of ms, last result)."""
+    ms, res = timed_region(0)
+    out = [ms]
+    n = 1 if ms >= cover_ms else int(min(hi, max(lo, -(-cover_ms // max(ms, 1e-3)))))
+    for r in range(1, n):
+        ms, res = timed_region(r)
+        out.append(ms)
+    return out, res
+
+
 class ClockSampler(object):
     """SM clock + clock-event (throttle) reasons sampled DURING the timed region (B200_PROFILING.md recipe).  NVML is queried in a
     thread every 2 ms (the timed region of the default run is ~40 ms; `nvidia-smi -lms 100` saw a single sample of it); when NVML
@@ -622,13 +636,7 @@ def run_b200_arm(args):
     # moves the number).  The region is therefore repeated — every repetition is exactly K steps between its own barriers — until
     # ~60 ms are covered (3 to 15 regions; the count follows the all-reduced time of the first one, so every rank agrees), and the
     # MEDIAN region is reported.  The clock sampler runs across all of them.
-    region_ms = []
-    ms, loss = timed_region(n_warm)
-    region_ms.append(ms)
-    n_regions = 1 if ms >= 60.0 else int(min(15, max(3, -(-60.0 // max(ms, 1e-3)))))
-    for r in range(1, n_regions):
-        ms, loss = timed_region(n_warm + r * args.steps)
-        region_ms.append(ms)
+    region_ms, loss = repeat_regions(lambda r: timed_region(n_warm + r * args.steps))
     ms_total = sorted(region_ms)[len(region_ms) // 2]
     clocks = sampler.stop() if rank == 0 else None
     final_loss = float(loss.item())

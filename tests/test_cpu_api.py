@@ -297,3 +297,22 @@ def test_packed_loader_shuffled_batches_are_contiguous_views_of_chunk_buffers():
                 rows += len(idx)
             assert rows == (n // bs * bs if drop else n)
             assert len(ptrs) <= 2  # two chunk buffers, no per-batch allocation
+
+
+def test_bench_region_repetition_count_is_a_function_of_the_first_region_only():
+    """bench.py repeats its K-step timed region until ~60 ms are covered (3..15 regions) and reports the median; the count must follow
+    from the first region's (all-reduced) time alone, so that every rank of a multi-GPU run executes the same number of regions."""
+    sys.path.insert(0, ROOT)
+    try:
+        import bench
+    finally:
+        sys.path.remove(ROOT)
+    for first_ms, expect in ((3.3, 15), (33.0, 3), (25.0, 3), (10.0, 6), (61.0, 1), (0.0, 15)):
+        calls = []
+
+        def region(r, first_ms=first_ms):
+            calls.append(r)
+            return (first_ms if r == 0 else 1e9), r  # later regions (however long) never change the count
+
+        out, last = bench.repeat_regions(region)
+        assert calls == list(range(expect)) and len(out) == expect and last == expect - 1
