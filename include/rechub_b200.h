@@ -36,7 +36,7 @@ typedef enum rh_status {
   RH_ERR_CUDA = 3           /* a CUDA runtime call failed (message holds cudaGetErrorString) */
 } rh_status;
 
-#define RH_ERRFLAG_SYNC_TIMEOUT 0x7ffffff0 /* err_flag value: a cross-GPU hand-over (rh_sync) saw no signal for ~2^24 polls */
+#define RH_ERRFLAG_SYNC_TIMEOUT 0x7ffffff0 /* err_flag value: a cross-GPU hand-over (rh_sync) saw no signal for ~2^26 polls (tens of seconds) */
 #define RH_MAX_FIELDS 64    /* id columns per rh_fields_* launch (callers chunk beyond it)  */
 #define RH_MAX_DENSE  32    /* numeric columns per rh_fields_fwd launch                     */
 

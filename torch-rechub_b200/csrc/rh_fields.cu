@@ -135,7 +135,7 @@ __device__ __forceinline__ void st_tile4(float* p, const float4& v, bool vec) {
 
 // ---- hand-overs inside the launch (multi-GPU exchange) ----
 // consumer: every CTA waits until all awaited ranks have published this step, BEFORE its first read of peer-written memory
-// (bounded: a peer that never publishes — a crashed rank — ends in the launch's error flag after ~2^24 polls, seconds, instead of
+// (bounded: a peer that never publishes — a crashed rank — ends in the launch's error flag after ~2^26 polls, tens of seconds, instead of
 // a kernel that spins until the box is reset; _lib.check_errors turns RH_ERRFLAG_SYNC_TIMEOUT into a RuntimeError)
 __device__ __forceinline__ void sync_wait_head(const SyncDev& sy, int32_t* err) {
   if (sy.wait_flags == nullptr) return;  // grid-uniform
@@ -145,7 +145,7 @@ __device__ __forceinline__ void sync_wait_head(const SyncDev& sy, int32_t* err) 
     unsigned polls = 0;
     while (ld_acquire_sys(sy.wait_flags + t) < e) {
       __nanosleep(32);
-      if (++polls > (1u << 24)) {
+      if (++polls > (1u << 26)) {
         if (err != nullptr) *err = RH_ERRFLAG_SYNC_TIMEOUT;
         break;
       }
