@@ -4,7 +4,7 @@
 #include <mutex>
 #include <unordered_set>
 
-#ifndef RH_PDL_FAMILY  /* (tools/*.cu include several of these files into one unit: the first one names the family) */
+#ifndef RH_PDL_FAMILY  // (the trace tools include several of these files into one unit: the first one names the family)
 #define RH_PDL_FAMILY 32  /* rh_set_pdl mask bit of this file's kernels */
 #endif
 #include "rh_common.cuh"

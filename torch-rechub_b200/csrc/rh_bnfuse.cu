@@ -25,7 +25,7 @@
 // Tuning history (tools/bnfuse_trace.cu, ncu): the first version (256 threads, run-time activation switch inside the unrolled
 // element loops, last-CTA finalisation) spent 8 us in its apply phase at 10 % issue-active — 90 instructions per element, 8 warps
 // per SM — and 2.8 us in the serial tail; 16 warps, a compile-time activation and the parity buffers address exactly those.
-#ifndef RH_PDL_FAMILY  /* (tools/*.cu include several of these files into one unit: the first one names the family) */
+#ifndef RH_PDL_FAMILY  // (the trace tools include several of these files into one unit: the first one names the family)
 #define RH_PDL_FAMILY 2  /* rh_set_pdl mask bit of this file's kernels */
 #endif
 #include "rh_bn_common.cuh"

@@ -18,7 +18,7 @@
 // Step numbers only grow, so flags never need resetting; a slot of parity p is rewritten two steps later, after its writer has
 // seen every peer's NEXT signal, which a peer issues after its reads of step p completed (stream order).
 // Everything is static-shaped and reads its step number from device memory: CUDA-graph capturable.
-#ifndef RH_PDL_FAMILY  /* (tools/*.cu include several of these files into one unit: the first one names the family) */
+#ifndef RH_PDL_FAMILY  // (the trace tools include several of these files into one unit: the first one names the family)
 #define RH_PDL_FAMILY 64  /* rh_set_pdl mask bit of this file's kernels */
 #endif
 #include "rh_common.cuh"

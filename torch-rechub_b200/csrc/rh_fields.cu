@@ -12,7 +12,7 @@
 //             512 contiguous bytes per warp and pass.
 //   backward: one (field, sample-chunk) per block so the LR weight gradient reduces in registers;
 //             per-row gradient goes out as ONE 16-byte vector RED per lane (REDG.E.ADD.F32x4).
-#ifndef RH_PDL_FAMILY  /* (tools/*.cu include several of these files into one unit: the first one names the family) */
+#ifndef RH_PDL_FAMILY  // (the trace tools include several of these files into one unit: the first one names the family)
 #define RH_PDL_FAMILY 4  /* rh_set_pdl mask bit of this file's kernels */
 #endif
 #include "rh_common.cuh"

@@ -27,7 +27,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#ifndef RH_PDL_FAMILY  /* (tools/*.cu include several of these files into one unit: the first one names the family) */
+#ifndef RH_PDL_FAMILY  // (the trace tools include several of these files into one unit: the first one names the family)
 #define RH_PDL_FAMILY 1  /* rh_set_pdl mask bit of this file's kernels */
 #endif
 #include "rh_common.cuh"

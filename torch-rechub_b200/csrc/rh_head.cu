@@ -6,7 +6,7 @@
 // transposed gemv (+ split-K reduce) + a bias reduction backward — ten launches moving a (batch, 128) activation that one
 // warp per row reads once.  Both directions are HBM/latency-bound row maps; backward accumulates the weight gradient in
 // registers across a block's rows and finishes with one RED per column per block.
-#ifndef RH_PDL_FAMILY  /* (tools/*.cu include several of these files into one unit: the first one names the family) */
+#ifndef RH_PDL_FAMILY  // (the trace tools include several of these files into one unit: the first one names the family)
 #define RH_PDL_FAMILY 16  /* rh_set_pdl mask bit of this file's kernels */
 #endif
 #include "rh_common.cuh"

@@ -11,7 +11,7 @@
 // Mapping: one warp owns one row; lane owns VEC consecutive columns per step (VEC = 4: 16-byte
 // accesses), KMAX steps cover the row, so Dice's per-row statistics are two warp reductions and the
 // per-column constants are hoisted into registers once per warp.
-#ifndef RH_PDL_FAMILY  /* (tools/*.cu include several of these files into one unit: the first one names the family) */
+#ifndef RH_PDL_FAMILY  // (the trace tools include several of these files into one unit: the first one names the family)
 #define RH_PDL_FAMILY 8  /* rh_set_pdl mask bit of this file's kernels */
 #endif
 #include "rh_bn_common.cuh"

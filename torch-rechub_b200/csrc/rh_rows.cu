@@ -4,7 +4,7 @@
 // Reference arithmetic replaced: nn.Embedding forward/backward as called from basic/layers.py:83-99,
 // SumPooling/AveragePooling + InputMask (basic/layers.py:148-161, 209-251), the dense zero-fill of
 // embedding gradients and the table part of torch.optim.* (ctr_trainer.py:99).
-#ifndef RH_PDL_FAMILY  /* (tools/*.cu include several of these files into one unit: the first one names the family) */
+#ifndef RH_PDL_FAMILY  // (the trace tools include several of these files into one unit: the first one names the family)
 #define RH_PDL_FAMILY 8  /* rh_set_pdl mask bit of this file's kernels */
 #endif
 #include "rh_common.cuh"
