@@ -70,7 +70,7 @@ def _worker(rank, world, port, kind, out):
         assert n_owned == (1 if rank == 0 else 0)
     else:
         n_owned = sum(1 for f in trainer._dist.fronts for n, o in f.owner.items() if o == rank)
-        assert n_owned in (2, 3) and len(trainer._dist.foreign) == 5 - n_owned
+        assert n_owned == len([i for i in range(5) if i % world == rank]) and len(trainer._dist.foreign) == 5 - n_owned  # round-robin by field
     x, y = _batch(rank, kind=kind)
     model.train()
     loss = trainer._train_step(x, y)
@@ -80,9 +80,10 @@ def _worker(rank, world, port, kind, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kind", ["deepfm", "dcn", "din", "dcn_one_table"])
-def test_two_rank_sharded_step_matches_dataparallel_semantics(kind):
-    world = 2
+@pytest.mark.parametrize("kind,world", [("deepfm", 2), ("dcn", 2), ("din", 2), ("dcn_one_table", 2), ("deepfm", 4)])
+def test_two_rank_sharded_step_matches_dataparallel_semantics(kind, world):
+    """world 4 / 5 fields: owners hold 2, 1, 1, 1 tables — unequal shares, so the exchange buffers carry padding slots (fmax = 2) as the
+    26-field / 8-rank split of the benchmark does (4,4,3,3,3,3,3,3)."""
     out = mp.get_context("spawn").Manager().dict()
     mp.spawn(_worker, args=(world, _free_port(), kind, out), nprocs=world, join=True)
     # single-process emulation: per-rank sub-batch forward (own BatchNorm statistics), loss = mean over the global batch
@@ -103,13 +104,14 @@ def test_two_rank_sharded_step_matches_dataparallel_semantics(kind):
         loss.backward()
         total += float(loss)
     opt.step()
-    assert abs(out[0]["loss"] - total) < 1e-6 and abs(out[1]["loss"] - total) < 1e-6
+    assert all(abs(out[r]["loss"] - total) < 1e-6 for r in range(world))
     want = ref.state_dict()
     for k, v in out[0]["sd"].items():
         if "running_" in k or "num_batches" in k:
             continue  # buffers are per replica (DataParallel keeps replica 0's)
         assert torch.allclose(v, want[k], rtol=1e-5, atol=1e-6), k
-    for k, v in out[1]["sd"].items():  # both ranks hold identical replicated weights and identical gathered tables
-        if "running_" in k or "num_batches" in k:
-            continue
-        assert torch.equal(v, out[0]["sd"][k]), k
+    for r in range(1, world):  # every rank holds identical replicated weights and identical gathered tables
+        for k, v in out[r]["sd"].items():
+            if "running_" in k or "num_batches" in k:
+                continue
+            assert torch.equal(v, out[0]["sd"][k]), (r, k)
